@@ -1,0 +1,307 @@
+// bis_context.cu -- context, vectors, device scalars, timers.
+// C-ABI: include/bis_b200.h ("context", "vectors", "device scalars").
+#include "bis_internal.cuh"
+
+#include <cstring>
+
+static thread_local char g_err[1024] = "";
+
+void bis_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *bis_last_error(void) { return g_err; }
+extern "C" int bis_version(void) { return BIS_VERSION; }
+
+extern "C" int bis_device_count(int *count) {
+    BIS_REQUIRE(count, "bis_device_count: null output");
+    BIS_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+
+static int context_init(bis_context *c, int device) {
+    int ndev = 0;
+    BIS_CUDA(cudaGetDeviceCount(&ndev));
+    BIS_REQUIRE(ndev > 0, "no CUDA device: this library has no CPU fallback");
+    BIS_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    c->device = device;
+    BIS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BIS_CUDA(cudaGetDeviceProperties(&prop, device));
+    BIS_REQUIRE(prop.major >= 10,
+                "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+    c->sm_count = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    BIS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    BIS_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    BIS_CUDA(cudaEventCreate(&c->ev_timer0));
+    BIS_CUDA(cudaEventCreate(&c->ev_timer1));
+    BIS_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    BIS_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    BIS_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * BIS_NUM_SCALARS));
+    BIS_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * BIS_NUM_SCALARS));
+    BIS_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * BIS_NUM_SCALARS));
+    BIS_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * BIS_MAX_RED * BIS_MAX_RED_BLOCKS));
+    BIS_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+    BIS_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int)));
+    BIS_CUDA(cudaMalloc(&c->d_errflag, sizeof(int)));
+    BIS_CUDA(cudaMemset(c->d_errflag, 0, sizeof(int)));
+    BIS_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int bis_context_create(int device, bis_context **ctx) {
+    BIS_REQUIRE(ctx, "bis_context_create: null output");
+    bis_context *c = new bis_context;
+    if (context_init(c, device) != 0) {
+        delete c;
+        return 1;
+    }
+    *ctx = c;
+    return 0;
+}
+
+extern "C" int bis_nccl_unique_id(void *out, size_t bytes) {
+    BIS_REQUIRE(out && bytes >= sizeof(ncclUniqueId), "bis_nccl_unique_id: need %zu bytes",
+                sizeof(ncclUniqueId));
+    ncclUniqueId id;
+    BIS_NCCL(ncclGetUniqueId(&id));
+    memcpy(out, &id, sizeof id);
+    return 0;
+}
+
+extern "C" int bis_context_create_distributed(int device, int rank, int nranks,
+                                              const void *nccl_id, size_t nccl_id_bytes,
+                                              bis_context **ctx) {
+    BIS_REQUIRE(ctx, "bis_context_create_distributed: null output");
+    BIS_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / nranks %d", rank, nranks);
+    bis_context *c = new bis_context;
+    if (context_init(c, device) != 0) {
+        delete c;
+        return 1;
+    }
+    c->rank = rank;
+    c->nranks = nranks;
+    if (nranks > 1) {
+        if (!nccl_id || nccl_id_bytes < sizeof(ncclUniqueId)) {
+            bis_set_error("bis_context_create_distributed: nccl_id must hold %zu bytes",
+                          sizeof(ncclUniqueId));
+            delete c;
+            return 2;
+        }
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof id);
+        ncclResult_t r = ncclCommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            bis_set_error("ncclCommInitRank failed: %s", ncclGetErrorString(r));
+            delete c;
+            return 1;
+        }
+        // a second communicator for the halo exchange so that send/recv on the
+        // comm stream never interleaves with the reductions on the main stream
+        r = ncclCommSplit(c->comm, 0, rank, &c->comm_halo, nullptr);
+        if (r != ncclSuccess) {
+            bis_set_error("ncclCommSplit failed: %s", ncclGetErrorString(r));
+            ncclCommDestroy(c->comm);
+            delete c;
+            return 1;
+        }
+    }
+    *ctx = c;
+    return 0;
+}
+
+extern "C" int bis_context_destroy(bis_context *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm_halo) ncclCommDestroy(c->comm_halo);
+    if (c->comm) ncclCommDestroy(c->comm);
+    cudaFree(c->d_scalars);
+    cudaFreeHost(c->h_scalars);
+    cudaFree(c->d_partials);
+    cudaFree(c->d_counter);
+    cudaFree(c->d_errflag);
+    cudaFree(c->d_flush);
+    cudaEventDestroy(c->ev_timer0);
+    cudaEventDestroy(c->ev_timer1);
+    cudaEventDestroy(c->ev_main);
+    cudaEventDestroy(c->ev_comm);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->comm_stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int bis_context_synchronize(bis_context *c) {
+    BIS_REQUIRE(c, "null context");
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    int flag = 0;
+    BIS_CUDA(cudaMemcpy(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(c->d_errflag, 0, sizeof(int));
+        bis_set_error("device watchdog fired (code %d): a level-scheduled triangular solve did "
+                      "not make progress", flag);
+        return 3;
+    }
+    return 0;
+}
+
+extern "C" int bis_context_rank(const bis_context *c, int *rank, int *nranks) {
+    BIS_REQUIRE(c, "null context");
+    if (rank) *rank = c->rank;
+    if (nranks) *nranks = c->nranks;
+    return 0;
+}
+
+extern "C" int bis_context_info(bis_context *c, int64_t info[8]) {
+    BIS_REQUIRE(c && info, "null argument");
+    size_t fr = 0, tot = 0;
+    BIS_CUDA(cudaSetDevice(c->device));
+    BIS_CUDA(cudaMemGetInfo(&fr, &tot));
+    for (int i = 0; i < 8; ++i) info[i] = 0;
+    info[0] = c->sm_count;
+    info[1] = (int64_t)fr;
+    info[2] = (int64_t)tot;
+    info[3] = c->launches;
+    info[4] = (int64_t)c->l2_bytes;
+    return 0;
+}
+
+extern "C" int bis_timer_start(bis_context *c) {
+    BIS_REQUIRE(c, "null context");
+    BIS_CUDA(cudaEventRecord(c->ev_timer0, c->stream));
+    return 0;
+}
+
+extern "C" int bis_timer_stop(bis_context *c, double *elapsed_ms) {
+    BIS_REQUIRE(c && elapsed_ms, "null argument");
+    BIS_CUDA(cudaEventRecord(c->ev_timer1, c->stream));
+    BIS_CUDA(cudaEventSynchronize(c->ev_timer1));
+    float ms = 0.f;
+    BIS_CUDA(cudaEventElapsedTime(&ms, c->ev_timer0, c->ev_timer1));
+    *elapsed_ms = (double)ms;
+    return 0;
+}
+
+extern "C" int bis_flush_l2(bis_context *c) {
+    BIS_REQUIRE(c, "null context");
+    if (!c->d_flush) {
+        c->flush_bytes = c->l2_bytes ? 2 * c->l2_bytes : ((size_t)256 << 20);
+        BIS_CUDA(cudaMalloc(&c->d_flush, c->flush_bytes));
+    }
+    BIS_CUDA(cudaMemsetAsync(c->d_flush, 1, c->flush_bytes, c->stream));
+    return 0;
+}
+
+extern "C" int bis_context_set_option(bis_context *c, const char *key, int value) {
+    BIS_REQUIRE(c && key, "null argument");
+    std::string k(key);
+    if (k == "spmv_variant") c->opt_spmv_variant = value;
+    else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
+    else if (k == "trsv_variant") c->opt_trsv_variant = value;
+    else {
+        bis_set_error("unknown option '%s'", key);
+        return 2;
+    }
+    return 0;
+}
+
+// ---- vectors ----------------------------------------------------------------
+extern "C" int bis_vector_alloc(bis_context *c, int64_t n, double **v) {
+    BIS_REQUIRE(c && v && n >= 0, "bis_vector_alloc: bad argument");
+    BIS_CUDA(cudaSetDevice(c->device));
+    size_t bytes = sizeof(double) * (size_t)(n > 0 ? n : 1);
+    BIS_CUDA(cudaMalloc(v, bytes));
+    BIS_CUDA(cudaMemsetAsync(*v, 0, bytes, c->stream));
+    return 0;
+}
+
+extern "C" int bis_vector_free(bis_context *c, double *v) {
+    BIS_REQUIRE(c, "null context");
+    if (!v) return 0;
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    BIS_CUDA(cudaFree(v));
+    return 0;
+}
+
+extern "C" int bis_vector_upload(bis_context *c, double *dst, const double *src, int64_t n) {
+    BIS_REQUIRE(c && (n == 0 || (dst && src)), "bis_vector_upload: null pointer");
+    if (n == 0) return 0;
+    BIS_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));   // src is never retained
+    return 0;
+}
+
+extern "C" int bis_vector_download(bis_context *c, double *dst, const double *src, int64_t n) {
+    BIS_REQUIRE(c && (n == 0 || (dst && src)), "bis_vector_download: null pointer");
+    if (n == 0) return 0;
+    BIS_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- device scalars -----------------------------------------------------------
+extern "C" int bis_scalar_set(bis_context *c, int slot, double value) {
+    BIS_REQUIRE(c && slot >= 0 && slot < BIS_NUM_SCALARS, "bis_scalar_set: bad slot %d", slot);
+    // stream-ordered 8-byte write from pageable memory is staged by the driver
+    BIS_CUDA(cudaMemcpyAsync(c->d_scalars + slot, &value, sizeof(double), cudaMemcpyHostToDevice,
+                             c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int bis_scalar_get(bis_context *c, int first_slot, int count, double *values) {
+    BIS_REQUIRE(c && values && first_slot >= 0 && count >= 0 &&
+                    first_slot + count <= BIS_NUM_SCALARS,
+                "bis_scalar_get: bad range [%d,+%d)", first_slot, count);
+    if (count == 0) return 0;
+    BIS_CUDA(cudaMemcpyAsync(c->h_scalars + first_slot, c->d_scalars + first_slot,
+                             sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(values, c->h_scalars + first_slot, sizeof(double) * count);
+    return 0;
+}
+
+extern "C" int bis_scalar_copy(bis_context *c, int dst_slot, int src_slot) {
+    BIS_REQUIRE(c && dst_slot >= 0 && dst_slot < BIS_NUM_SCALARS && src_slot >= 0 &&
+                    src_slot < BIS_NUM_SCALARS,
+                "bis_scalar_copy: bad slot");
+    BIS_CUDA(cudaMemcpyAsync(c->d_scalars + dst_slot, c->d_scalars + src_slot, sizeof(double),
+                             cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+// Called after a reduction kernel wrote its slot(s): sum over ranks.
+int bis_reduce_finish(bis_context *c, int slot_a, int slot_b) {
+    if (c->nranks <= 1) return 0;
+    if (slot_a >= 0 && slot_b == slot_a + 1) {
+        BIS_NCCL(ncclAllReduce(c->d_scalars + slot_a, c->d_scalars + slot_a, 2, ncclDouble, ncclSum,
+                               c->comm, c->stream));
+        return 0;
+    }
+    if (slot_a >= 0)
+        BIS_NCCL(ncclAllReduce(c->d_scalars + slot_a, c->d_scalars + slot_a, 1, ncclDouble, ncclSum,
+                               c->comm, c->stream));
+    if (slot_b >= 0)
+        BIS_NCCL(ncclAllReduce(c->d_scalars + slot_b, c->d_scalars + slot_b, 1, ncclDouble, ncclSum,
+                               c->comm, c->stream));
+    return 0;
+}
+
+RedArgs bis_red_args(bis_context *c, int slot_a, int slot_b) {
+    RedArgs ra;
+    ra.partials = c->d_partials;
+    ra.counter = c->d_counter;
+    ra.scalars = c->d_scalars;
+    ra.slot[0] = slot_a;
+    ra.slot[1] = slot_b;
+    ra.block_offset = 0;
+    ra.total_blocks = 0;
+    ra.finalize = 1;
+    return ra;
+}

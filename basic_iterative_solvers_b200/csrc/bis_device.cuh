@@ -1,0 +1,76 @@
+// bis_device.cuh -- device-side helpers: pinned-rounding arithmetic and the
+// deterministic block/grid reduction used by every fused kernel.
+#pragma once
+
+#include "bis_internal.cuh"
+
+// The library is compiled with --fmad=false: a*b+c is two roundings unless
+// written as fma().  The helpers below name the intent at the call sites.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// streaming loads/stores: matrix data is read exactly once per SpMV
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of NRED accumulators, then the grid-wide deterministic
+// finish.  Must be called by ALL threads of the block (blockDim.x <= 1024,
+// multiple of 32).
+template <int NRED>
+__device__ __forceinline__ void block_reduce_finish(double (&acc)[NRED], const RedArgs &ra) {
+    __shared__ double s_part[NRED][32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < NRED; ++q) {
+        double v = warp_sum(acc[q]);
+        if (lane == 0) s_part[q][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < NRED; ++q) {
+            double v = (lane < nwarp) ? s_part[q][lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0)
+                ra.partials[q * BIS_MAX_RED_BLOCKS + ra.block_offset + blockIdx.x] = v;
+        }
+    }
+    if (!ra.finalize) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int ticket = atomicAdd(ra.counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: fixed-order sum of all partials
+#pragma unroll
+    for (int q = 0; q < NRED; ++q) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < ra.total_blocks; i += blockDim.x)
+            v += __ldcg(&ra.partials[q * BIS_MAX_RED_BLOCKS + i]);
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) s_part[q][warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double t = (lane < nwarp) ? s_part[q][lane] : 0.0;
+            t = warp_sum(t);
+            if (lane == 0 && ra.slot[q] >= 0) ra.scalars[ra.slot[q]] = t;
+        }
+    }
+    if (threadIdx.x == 0) *ra.counter = 0u;
+}

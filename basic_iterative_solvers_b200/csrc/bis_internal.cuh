@@ -1,0 +1,169 @@
+// bis_internal.cuh -- shared declarations of the sm_100a implementation behind
+// include/bis_b200.h.  Nothing here is part of the ABI.
+#pragma once
+
+#include "bis_b200.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+// ---- error plumbing -------------------------------------------------------
+void bis_set_error(const char *fmt, ...);
+
+#define BIS_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) {                                               \
+            bis_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,   \
+                          cudaGetErrorString(_e));                             \
+            return 1;                                                          \
+        }                                                                      \
+    } while (0)
+
+#define BIS_NCCL(call)                                                         \
+    do {                                                                       \
+        ncclResult_t _r = (call);                                              \
+        if (_r != ncclSuccess) {                                               \
+            bis_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,   \
+                          ncclGetErrorString(_r));                             \
+            return 1;                                                          \
+        }                                                                      \
+    } while (0)
+
+#define BIS_CHECK(expr)                                                        \
+    do {                                                                       \
+        int _rc = (expr);                                                      \
+        if (_rc != 0)                                                          \
+            return _rc;                                                        \
+    } while (0)
+
+#define BIS_REQUIRE(cond, ...)                                                 \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            bis_set_error(__VA_ARGS__);                                        \
+            return 2;                                                          \
+        }                                                                      \
+    } while (0)
+
+#define BIS_LAUNCH_CHECK(ctx)                                                  \
+    do {                                                                       \
+        (ctx)->launches++;                                                     \
+        cudaError_t _e = cudaGetLastError();                                   \
+        if (_e != cudaSuccess) {                                               \
+            bis_set_error("%s:%d: kernel launch failed: %s", __FILE__,         \
+                          __LINE__, cudaGetErrorString(_e));                   \
+            return 1;                                                          \
+        }                                                                      \
+    } while (0)
+
+// ---- reductions -----------------------------------------------------------
+// Deterministic two-stage reduction: every block writes one partial per
+// reduced quantity; the last block to arrive (ticket counter) adds the
+// partials in a fixed order and writes the device scalar slot(s).
+constexpr int BIS_MAX_RED_BLOCKS = 8192;   // partials per quantity
+constexpr int BIS_MAX_RED = 2;             // quantities per kernel
+
+struct RedArgs {
+    double *partials;        // [BIS_MAX_RED][BIS_MAX_RED_BLOCKS]
+    unsigned int *counter;   // ticket, self-resetting
+    double *scalars;         // device scalar bank
+    int slot[BIS_MAX_RED];   // target slots (-1: unused)
+    int block_offset;        // first partial index written by this launch
+    int total_blocks;        // partials to add when finalising
+    int finalize;            // 0: only write partials (a later launch finalises)
+};
+
+struct bis_context {
+    int device = 0;
+    int rank = 0;
+    int nranks = 1;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_timer0 = nullptr, ev_timer1 = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+    double *d_scalars = nullptr;         // BIS_NUM_SCALARS
+    double *h_scalars = nullptr;         // pinned staging
+    double *d_partials = nullptr;
+    unsigned int *d_counter = nullptr;
+    int *d_errflag = nullptr;            // set by kernels on watchdog expiry
+    void *d_flush = nullptr;
+    size_t flush_bytes = 0;
+    ncclComm_t comm = nullptr;           // reductions (main stream)
+    ncclComm_t comm_halo = nullptr;      // halo exchange (comm stream)
+    int64_t launches = 0;
+    // options
+    int opt_spmv_variant = 0;
+    int opt_spmv_lanes = 0;
+    int opt_trsv_variant = 0;
+};
+
+struct LevelSets {
+    int n_levels = 0;
+    int64_t n_slots = 0;              // == n_rows: position in the level-ordered row list
+    int *d_slot_row = nullptr;        // [n_slots] original row
+    int *d_slot_level = nullptr;      // [n_slots] level of that row (non-decreasing)
+    int *d_level_size = nullptr;      // [n_levels] rows per level
+    std::vector<int64_t> level_start; // [n_levels+1] host copy (per-level launch variant)
+    unsigned int *d_level_done = nullptr;   // [n_levels] completion counters
+    unsigned int *d_ticket = nullptr; // chunk ticket
+    // level-ordered copy of the strict factor (rows stored in slot order)
+    int64_t *d_rp = nullptr;          // [n_slots+1]
+    int *d_col = nullptr;
+    double *d_val = nullptr;
+};
+
+struct HaloPlan {
+    int64_t n_ghost = 0;                 // ghost elements appended after owned
+    double *d_ghost = nullptr;           // [n_ghost] received values
+    double *d_sendbuf = nullptr;         // [n_send]
+    int *d_send_idx = nullptr;           // [n_send] local row indices to pack
+    int *d_ghost_global = nullptr;       // [n_ghost] global column id of each ghost (sorted)
+    int64_t n_send = 0;
+    std::vector<int64_t> recv_off;       // [nranks+1] segments of d_ghost
+    std::vector<int64_t> send_off;       // [nranks+1] segments of d_sendbuf
+    int64_t interior_begin = 0, interior_end = 0;   // rows without ghosts
+};
+
+struct bis_matrix {
+    int64_t n_rows = 0;        // local rows
+    int64_t n_cols = 0;        // local owned columns (== n_rows when square)
+    int64_t n_rows_global = 0;
+    int64_t row_begin = 0;     // first global row
+    int64_t nnz = 0;           // local nnz
+    int64_t nnz_global = 0;
+    int rp_bytes = 4;          // 4 or 8
+    void *d_rp = nullptr;      // int32_t or int64_t [n_rows+1]
+    int *d_col = nullptr;      // local column ids (ghosts >= n_cols)
+    double *d_val = nullptr;
+    int triangular = 0;        // 0 general, 1 strictly lower, 2 strictly upper
+    double mean_row = 0.0;
+    int max_row = 0;
+    LevelSets lv;
+    HaloPlan halo;
+    bool distributed = false;
+};
+
+// ---- internal entry points shared between translation units ---------------
+int bis_reduce_finish(bis_context *ctx, int slot_a, int slot_b);
+RedArgs bis_red_args(bis_context *ctx, int slot_a, int slot_b);
+int bis_halo_exchange_begin(bis_context *ctx, const bis_matrix *A, const double *x);
+int bis_halo_exchange_end(bis_context *ctx, const bis_matrix *A);
+int bis_matrix_finalize_distributed(bis_context *ctx, bis_matrix *A,
+                                    int *d_col_global_in_place);
+int bis_build_levels_device(bis_context *ctx, bis_matrix *T);
+int bis_matrix_stats(bis_context *ctx, bis_matrix *A);
+
+static inline int bis_blocks_for(int64_t n, int per_block, int cap) {
+    int64_t b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}

@@ -1,0 +1,624 @@
+// bis_matrix.cu -- device CRS containers (MatrixCRS, sparse_matrix.hpp:59-179),
+// level sets for the strictly triangular factors, device-side synthetic
+// generators, row partitioning + halo index lists.
+#include "bis_device.cuh"
+
+#include <thrust/copy.h>
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/scan.h>
+#include <thrust/sort.h>
+#include <thrust/unique.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace {
+
+template <typename T> int dev_alloc(T **p, size_t count) {
+    BIS_CUDA(cudaMalloc(p, sizeof(T) * (count > 0 ? count : 1)));
+    return 0;
+}
+
+void free_matrix_storage(bis_matrix *A) {
+    cudaFree(A->d_rp);
+    cudaFree(A->d_col);
+    cudaFree(A->d_val);
+    cudaFree(A->lv.d_slot_row);
+    cudaFree(A->lv.d_slot_level);
+    cudaFree(A->lv.d_level_size);
+    cudaFree(A->lv.d_level_done);
+    cudaFree(A->lv.d_ticket);
+    cudaFree(A->lv.d_rp);
+    cudaFree(A->lv.d_col);
+    cudaFree(A->lv.d_val);
+    cudaFree(A->halo.d_ghost);
+    cudaFree(A->halo.d_sendbuf);
+    cudaFree(A->halo.d_send_idx);
+    cudaFree(A->halo.d_ghost_global);
+}
+
+template <typename RP>
+int upload_common(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz, const RP *rp,
+                  const int32_t *col, const double *val, bis_matrix **out) {
+    BIS_REQUIRE(c && out && rp, "matrix upload: null argument");
+    BIS_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "matrix upload: negative size");
+    BIS_REQUIRE(nnz == 0 || (col && val), "matrix upload: null col/val");
+    BIS_REQUIRE((int64_t)rp[n_rows] == nnz, "matrix upload: row_ptr[n_rows]=%lld != nnz=%lld",
+                (long long)rp[n_rows], (long long)nnz);
+    BIS_REQUIRE(n_rows < INT32_MAX && n_cols < INT32_MAX, "matrix upload: more than 2^31-1 rows");
+    BIS_CUDA(cudaSetDevice(c->device));
+    bis_matrix *A = new bis_matrix;
+    A->n_rows = n_rows;
+    A->n_cols = n_cols;
+    A->n_rows_global = n_rows;
+    A->nnz = A->nnz_global = nnz;
+    A->rp_bytes = (int)sizeof(RP);
+    int max_row = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t len = (int64_t)rp[r + 1] - (int64_t)rp[r];
+        if (len < 0) {
+            bis_set_error("matrix upload: row_ptr not monotone at row %lld", (long long)r);
+            delete A;
+            return 2;
+        }
+        if (len > max_row) max_row = (int)len;
+    }
+    A->max_row = max_row;
+    A->mean_row = n_rows ? (double)nnz / (double)n_rows : 0.0;
+    RP *d_rp = nullptr;
+    if (dev_alloc(&d_rp, (size_t)n_rows + 1) || dev_alloc(&A->d_col, (size_t)nnz) ||
+        dev_alloc(&A->d_val, (size_t)nnz)) {
+        A->d_rp = d_rp;
+        free_matrix_storage(A);
+        delete A;
+        return 1;
+    }
+    A->d_rp = d_rp;
+    BIS_CUDA(cudaMemcpyAsync(d_rp, rp, sizeof(RP) * ((size_t)n_rows + 1), cudaMemcpyHostToDevice, c->stream));
+    if (nnz) {
+        BIS_CUDA(cudaMemcpyAsync(A->d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+        BIS_CUDA(cudaMemcpyAsync(A->d_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    }
+    BIS_CUDA(cudaStreamSynchronize(c->stream));   // host arrays are never retained
+    *out = A;
+    return 0;
+}
+
+} // namespace
+
+extern "C" int bis_matrix_upload_crs(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                     const int32_t *rp, const int32_t *col, const double *val,
+                                     bis_matrix **A) {
+    BIS_REQUIRE(!c || c->nranks == 1,
+                "bis_matrix_upload_crs: distributed context; use bis_matrix_upload_crs_distributed");
+    return upload_common<int32_t>(c, n_rows, n_cols, nnz, rp, col, val, A);
+}
+
+extern "C" int bis_matrix_upload_crs64(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                       const int64_t *rp, const int32_t *col, const double *val,
+                                       bis_matrix **A) {
+    BIS_REQUIRE(!c || c->nranks == 1,
+                "bis_matrix_upload_crs64: distributed context; use bis_matrix_upload_crs_distributed");
+    return upload_common<int64_t>(c, n_rows, n_cols, nnz, rp, col, val, A);
+}
+
+extern "C" int bis_matrix_upload_crs_distributed(bis_context *c, int64_t row_begin,
+                                                 int64_t n_rows_local, int64_t n_rows_global,
+                                                 int64_t nnz_local, const int64_t *rp,
+                                                 const int32_t *col, const double *val,
+                                                 bis_matrix **out) {
+    BIS_REQUIRE(c && out, "null argument");
+    bis_matrix *A = nullptr;
+    BIS_CHECK(upload_common<int64_t>(c, n_rows_local, n_rows_local, nnz_local, rp, col, val, &A));
+    A->n_rows_global = n_rows_global;
+    A->row_begin = row_begin;
+    if (bis_matrix_finalize_distributed(c, A, A->d_col) != 0) {
+        free_matrix_storage(A);
+        delete A;
+        return 1;
+    }
+    *out = A;
+    return 0;
+}
+
+// ---- level sets ---------------------------------------------------------------
+extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t nnz,
+                                            const int32_t *rp, const int32_t *col,
+                                            const double *val, int upper, bis_matrix **out) {
+    BIS_REQUIRE(c && out, "null argument");
+    BIS_REQUIRE(c->nranks == 1, "triangular factors are single-GPU only (they do not shard)");
+    bis_matrix *T = nullptr;
+    BIS_CHECK(upload_common<int32_t>(c, n, n, nnz, rp, col, val, &T));
+    T->triangular = upper ? 2 : 1;
+    // level(r) = 1 + max level over the rows it reads (host, one pass in
+    // dependency order; the device-side analysis is SURVEY.md 8(f) "next")
+    std::vector<int> level((size_t)n, 0);
+    int n_levels = n > 0 ? 1 : 0;
+    auto fail = [&](const char *msg, int64_t r) {
+        bis_set_error("bis_matrix_upload_triangular: %s at row %lld", msg, (long long)r);
+        free_matrix_storage(T);
+        delete T;
+        return 2;
+    };
+    if (!upper) {
+        for (int64_t r = 0; r < n; ++r) {
+            int lv = 0;
+            for (int32_t k = rp[r]; k < rp[r + 1]; ++k) {
+                int32_t cc = col[k];
+                if (cc < 0 || cc >= r) return fail("entry not strictly below the diagonal", r);
+                lv = std::max(lv, level[cc] + 1);
+            }
+            level[r] = lv;
+            n_levels = std::max(n_levels, lv + 1);
+        }
+    } else {
+        for (int64_t r = n - 1; r >= 0; --r) {
+            int lv = 0;
+            for (int32_t k = rp[r]; k < rp[r + 1]; ++k) {
+                int32_t cc = col[k];
+                if (cc <= r || cc >= n) return fail("entry not strictly above the diagonal", r);
+                lv = std::max(lv, level[cc] + 1);
+            }
+            level[r] = lv;
+            n_levels = std::max(n_levels, lv + 1);
+        }
+    }
+    // counting sort by level, ascending row inside a level
+    std::vector<int64_t> start((size_t)n_levels + 1, 0);
+    for (int64_t r = 0; r < n; ++r) start[level[r] + 1]++;
+    std::vector<int> level_size((size_t)std::max(n_levels, 1), 0);
+    for (int l = 0; l < n_levels; ++l) {
+        level_size[l] = (int)start[l + 1];
+        start[l + 1] += start[l];
+    }
+    std::vector<int> slot_row((size_t)n), slot_level((size_t)n);
+    {
+        std::vector<int64_t> cur(start.begin(), start.end() - 1);
+        for (int64_t r = 0; r < n; ++r) {
+            int64_t s = cur[level[r]]++;
+            slot_row[s] = (int)r;
+            slot_level[s] = level[r];
+        }
+    }
+    std::vector<int64_t> rp2((size_t)n + 1, 0);
+    std::vector<int32_t> col2((size_t)nnz);
+    std::vector<double> val2((size_t)nnz);
+    for (int64_t s = 0; s < n; ++s) {
+        int r = slot_row[s];
+        int32_t len = rp[r + 1] - rp[r];
+        rp2[s + 1] = rp2[s] + len;
+        if (len) {
+            memcpy(&col2[rp2[s]], &col[rp[r]], sizeof(int32_t) * len);
+            memcpy(&val2[rp2[s]], &val[rp[r]], sizeof(double) * len);
+        }
+    }
+    LevelSets &lv = T->lv;
+    lv.n_levels = n_levels;
+    lv.n_slots = n;
+    lv.level_start = start;
+    int rc = 0;
+    rc |= dev_alloc(&lv.d_slot_row, (size_t)n);
+    rc |= dev_alloc(&lv.d_slot_level, (size_t)n);
+    rc |= dev_alloc(&lv.d_level_size, (size_t)n_levels);
+    rc |= dev_alloc(&lv.d_level_done, (size_t)n_levels);
+    rc |= dev_alloc(&lv.d_ticket, 1);
+    rc |= dev_alloc(&lv.d_rp, (size_t)n + 1);
+    rc |= dev_alloc(&lv.d_col, (size_t)nnz);
+    rc |= dev_alloc(&lv.d_val, (size_t)nnz);
+    if (rc) {
+        free_matrix_storage(T);
+        delete T;
+        return 1;
+    }
+    auto h2d = [&](void *d, const void *h, size_t bytes) {
+        return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+    };
+    BIS_CUDA(h2d(lv.d_slot_row, slot_row.data(), sizeof(int) * (size_t)n));
+    BIS_CUDA(h2d(lv.d_slot_level, slot_level.data(), sizeof(int) * (size_t)n));
+    BIS_CUDA(h2d(lv.d_level_size, level_size.data(), sizeof(int) * (size_t)n_levels));
+    BIS_CUDA(h2d(lv.d_rp, rp2.data(), sizeof(int64_t) * ((size_t)n + 1)));
+    BIS_CUDA(h2d(lv.d_col, col2.data(), sizeof(int32_t) * (size_t)nnz));
+    BIS_CUDA(h2d(lv.d_val, val2.data(), sizeof(double) * (size_t)nnz));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    *out = T;
+    return 0;
+}
+
+// ---- synthetic generators ---------------------------------------------------------
+namespace {
+
+// number of stencil points along one axis at coordinate k (3-point, clipped)
+__host__ __device__ inline int64_t cnt3(int64_t k, int64_t n) {
+    return 1 + (k > 0 ? 1 : 0) + (k + 1 < n ? 1 : 0);
+}
+// sum of cnt3 over coordinates < k
+__host__ __device__ inline int64_t pre3(int64_t k, int64_t n) {
+    if (k <= 0) return 0;
+    if (n == 1) return 1;
+    // k rows: first has 2, interior 3, last (index n-1) 2
+    return 3 * k - 1 - (k >= n ? 1 : 0);
+}
+__host__ __device__ inline int64_t hpcg_prefix(int64_t row, int64_t nx, int64_t ny, int64_t nz) {
+    const int64_t sx = pre3(nx, nx), sy = pre3(ny, ny);
+    if (row >= nx * ny * nz) return sx * sy * pre3(nz, nz);
+    const int64_t x = row % nx, y = (row / nx) % ny, z = row / (nx * ny);
+    return pre3(z, nz) * sx * sy + cnt3(z, nz) * (pre3(y, ny) * sx + cnt3(y, ny) * pre3(x, nx));
+}
+
+template <typename RP>
+__global__ void hpcg_fill_kernel(int64_t row_begin, int64_t n_local, int64_t nx, int64_t ny,
+                                 int64_t nz, RP *rp, int *col, double *val) {
+    const int64_t base = hpcg_prefix(row_begin, nx, ny, nz);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_local;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = row_begin + i;
+        const int64_t p = hpcg_prefix(row, nx, ny, nz) - base;
+        rp[i] = (RP)p;
+        if (i == n_local) break;
+        const int64_t x = row % nx, y = (row / nx) % ny, z = row / (nx * ny);
+        int64_t k = p;
+        for (int dz = -1; dz <= 1; ++dz) {
+            if (z + dz < 0 || z + dz >= nz) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                if (y + dy < 0 || y + dy >= ny) continue;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (x + dx < 0 || x + dx >= nx) continue;
+                    col[k] = (int)(row + (dz * ny + dy) * nx + dx);
+                    val[k] = (dx == 0 && dy == 0 && dz == 0) ? 26.0 : -1.0;
+                    ++k;
+                }
+            }
+        }
+    }
+}
+
+__host__ __device__ inline double splitmix_unit(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct AndersonP {
+    int64_t lx, ly, lz;
+    double ranpot, t;
+    uint64_t seed;
+    int periodic;
+};
+
+// neighbour list of one site in ascending column order; returns the count
+__device__ inline int anderson_row(const AndersonP &p, int64_t row, int64_t *cols, double *vals) {
+    const int64_t x = row % p.lx, y = (row / p.lx) % p.ly, z = row / (p.lx * p.ly);
+    const int dxs[7] = {0, 0, -1, 0, 1, 0, 0};
+    const int dys[7] = {0, -1, 0, 0, 0, 1, 0};
+    const int dzs[7] = {-1, 0, 0, 0, 0, 0, 1};
+    int n = 0;
+    for (int k = 0; k < 7; ++k) {
+        int64_t xx = x + dxs[k], yy = y + dys[k], zz = z + dzs[k];
+        bool ok = true;
+        if (p.periodic) {
+            if (dxs[k] && p.lx <= 2) ok = ok && xx >= 0 && xx < p.lx;
+            if (dys[k] && p.ly <= 2) ok = ok && yy >= 0 && yy < p.ly;
+            if (dzs[k] && p.lz <= 2) ok = ok && zz >= 0 && zz < p.lz;
+            xx = (xx + p.lx) % p.lx;
+            yy = (yy + p.ly) % p.ly;
+            zz = (zz + p.lz) % p.lz;
+        } else {
+            ok = xx >= 0 && xx < p.lx && yy >= 0 && yy < p.ly && zz >= 0 && zz < p.lz;
+        }
+        if (!ok) continue;
+        cols[n] = (zz * p.ly + yy) * p.lx + xx;
+        // 2u - 1 and the scaling are exact-rounded ops, identical in numpy
+        vals[n] = (k == 3) ? mul_rn(p.ranpot, sub_rn(mul_rn(2.0, splitmix_unit(p.seed, (uint64_t)row)), 1.0))
+                           : -p.t;
+        ++n;
+    }
+    // periodic wrap can break the ascending order: insertion sort (<= 7 items)
+    for (int i = 1; i < n; ++i) {
+        int64_t cc = cols[i];
+        double vv = vals[i];
+        int j = i - 1;
+        while (j >= 0 && cols[j] > cc) {
+            cols[j + 1] = cols[j];
+            vals[j + 1] = vals[j];
+            --j;
+        }
+        cols[j + 1] = cc;
+        vals[j + 1] = vv;
+    }
+    return n;
+}
+
+__global__ void anderson_count_kernel(AndersonP p, int64_t row_begin, int64_t n_local, int64_t *rp) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t cols[7];
+        double vals[7];
+        rp[i] = anderson_row(p, row_begin + i, cols, vals);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) rp[n_local] = 0;
+}
+
+__global__ void anderson_fill_kernel(AndersonP p, int64_t row_begin, int64_t n_local,
+                                     const int64_t *rp, int *col, double *val) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t cols[7];
+        double vals[7];
+        int n = anderson_row(p, row_begin + i, cols, vals);
+        int64_t k = rp[i];
+        for (int j = 0; j < n; ++j) {
+            col[k + j] = (int)cols[j];
+            val[k + j] = vals[j];
+        }
+    }
+}
+
+void slab(int64_t n, int rank, int nranks, int64_t plane, int64_t *begin, int64_t *end) {
+    // contiguous row blocks; whole planes per rank when the plane count allows
+    // it (z-slabs), otherwise plain row blocks
+    int64_t planes = plane > 0 ? n / plane : 0;
+    if (plane > 0 && planes >= nranks) {
+        int64_t q = planes / nranks, r = planes % nranks;
+        int64_t b = rank * q + std::min<int64_t>(rank, r);
+        int64_t e = b + q + (rank < r ? 1 : 0);
+        *begin = b * plane;
+        *end = e * plane;
+    } else {
+        int64_t q = n / nranks, r = n % nranks;
+        *begin = rank * q + std::min<int64_t>(rank, r);
+        *end = *begin + q + (rank < r ? 1 : 0);
+    }
+}
+
+int finish_generated(bis_context *c, bis_matrix *A, bis_matrix **out) {
+    if (c->nranks > 1) {
+        if (bis_matrix_finalize_distributed(c, A, A->d_col) != 0) {
+            free_matrix_storage(A);
+            delete A;
+            return 1;
+        }
+    }
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    *out = A;
+    return 0;
+}
+
+} // namespace
+
+extern "C" int bis_matrix_generate_hpcg(bis_context *c, int nx, int ny, int nz, bis_matrix **out) {
+    BIS_REQUIRE(c && out, "null argument");
+    BIS_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1, "bis_matrix_generate_hpcg: bad grid %dx%dx%d", nx, ny, nz);
+    const int64_t n = (int64_t)nx * ny * nz;
+    BIS_REQUIRE(n < INT32_MAX, "bis_matrix_generate_hpcg: %lld rows exceed 32-bit column ids", (long long)n);
+    BIS_CUDA(cudaSetDevice(c->device));
+    int64_t rb = 0, re = n;
+    slab(n, c->rank, c->nranks, (int64_t)nx * ny, &rb, &re);
+    const int64_t n_local = re - rb;
+    const int64_t nnz_local = hpcg_prefix(re, nx, ny, nz) - hpcg_prefix(rb, nx, ny, nz);
+    bis_matrix *A = new bis_matrix;
+    A->n_rows = A->n_cols = n_local;
+    A->n_rows_global = n;
+    A->row_begin = rb;
+    A->nnz = nnz_local;
+    A->nnz_global = hpcg_prefix(n, nx, ny, nz);
+    A->max_row = (int)(std::min(nx, 3) * std::min(ny, 3) * std::min(nz, 3));
+    A->mean_row = n_local ? (double)nnz_local / (double)n_local : 0.0;
+    const bool wide = nnz_local >= (int64_t)INT32_MAX;
+    A->rp_bytes = wide ? 8 : 4;
+    int rc = 0;
+    if (wide) rc |= dev_alloc(reinterpret_cast<int64_t **>(&A->d_rp), (size_t)n_local + 1);
+    else rc |= dev_alloc(reinterpret_cast<int32_t **>(&A->d_rp), (size_t)n_local + 1);
+    rc |= dev_alloc(&A->d_col, (size_t)nnz_local);
+    rc |= dev_alloc(&A->d_val, (size_t)nnz_local);
+    if (rc) {
+        free_matrix_storage(A);
+        delete A;
+        return 1;
+    }
+    const int blocks = c->sm_count * 8;
+    if (wide)
+        hpcg_fill_kernel<int64_t><<<blocks, 256, 0, c->stream>>>(rb, n_local, nx, ny, nz,
+                                                                static_cast<int64_t *>(A->d_rp), A->d_col, A->d_val);
+    else
+        hpcg_fill_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(rb, n_local, nx, ny, nz,
+                                                                static_cast<int32_t *>(A->d_rp), A->d_col, A->d_val);
+    BIS_LAUNCH_CHECK(c);
+    return finish_generated(c, A, out);
+}
+
+extern "C" int bis_matrix_generate_anderson(bis_context *c, int lx, int ly, int lz, double ranpot,
+                                            double t, uint64_t seed, int periodic, bis_matrix **out) {
+    BIS_REQUIRE(c && out, "null argument");
+    BIS_REQUIRE(lx >= 1 && ly >= 1 && lz >= 1, "bis_matrix_generate_anderson: bad lattice");
+    const int64_t n = (int64_t)lx * ly * lz;
+    BIS_REQUIRE(n < INT32_MAX / 8, "bis_matrix_generate_anderson: lattice too large for 32-bit ids");
+    BIS_CUDA(cudaSetDevice(c->device));
+    int64_t rb = 0, re = n;
+    slab(n, c->rank, c->nranks, (int64_t)lx * ly, &rb, &re);
+    const int64_t n_local = re - rb;
+    AndersonP p{lx, ly, lz, ranpot, t, seed, periodic};
+    int64_t *d_rp64 = nullptr;
+    BIS_CHECK(dev_alloc(&d_rp64, (size_t)n_local + 1));
+    const int blocks = c->sm_count * 8;
+    anderson_count_kernel<<<blocks, 256, 0, c->stream>>>(p, rb, n_local, d_rp64);
+    BIS_LAUNCH_CHECK(c);
+    thrust::exclusive_scan(thrust::cuda::par.on(c->stream), thrust::device_pointer_cast(d_rp64),
+                           thrust::device_pointer_cast(d_rp64) + n_local + 1,
+                           thrust::device_pointer_cast(d_rp64));
+    int64_t nnz_local = 0;
+    BIS_CUDA(cudaMemcpyAsync(&nnz_local, d_rp64 + n_local, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    bis_matrix *A = new bis_matrix;
+    A->n_rows = A->n_cols = n_local;
+    A->n_rows_global = n;
+    A->row_begin = rb;
+    A->nnz = nnz_local;
+    A->nnz_global = nnz_local;   // fixed below for nranks > 1
+    A->max_row = 7;
+    A->mean_row = n_local ? (double)nnz_local / (double)n_local : 0.0;
+    A->rp_bytes = 8;
+    A->d_rp = d_rp64;
+    if (dev_alloc(&A->d_col, (size_t)nnz_local) || dev_alloc(&A->d_val, (size_t)nnz_local)) {
+        free_matrix_storage(A);
+        delete A;
+        return 1;
+    }
+    anderson_fill_kernel<<<blocks, 256, 0, c->stream>>>(p, rb, n_local, d_rp64, A->d_col, A->d_val);
+    BIS_LAUNCH_CHECK(c);
+    return finish_generated(c, A, out);
+}
+
+extern "C" int bis_matrix_free(bis_context *c, bis_matrix *A) {
+    if (!A) return 0;
+    if (c) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->comm_stream);
+    }
+    free_matrix_storage(A);
+    delete A;
+    return 0;
+}
+
+extern "C" int bis_matrix_info(const bis_matrix *A, int64_t info[8]) {
+    BIS_REQUIRE(A && info, "null argument");
+    info[0] = A->n_rows;
+    info[1] = A->n_rows_global;
+    info[2] = A->nnz;
+    info[3] = A->nnz_global;
+    info[4] = A->rp_bytes;
+    info[5] = A->lv.n_levels;
+    info[6] = A->halo.n_ghost;
+    info[7] = A->row_begin;
+    return 0;
+}
+
+namespace {
+__global__ void cols_to_global_kernel(int64_t nnz, const int *col, int64_t n_owned, int64_t row_begin,
+                                      const int *ghost_global, int *out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        int cc = col[k];
+        out[k] = cc < n_owned ? (int)(cc + row_begin) : ghost_global[cc - n_owned];
+    }
+}
+template <typename RP> __global__ void rp_to_i64_kernel(int64_t n1, const RP *rp, int64_t *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int64_t)rp[i];
+}
+} // namespace
+
+extern "C" int bis_matrix_download_crs(bis_context *c, const bis_matrix *A, int64_t *rp, int32_t *col,
+                                       double *val) {
+    BIS_REQUIRE(c && A && rp, "null argument");
+    BIS_CUDA(cudaSetDevice(c->device));
+    int64_t *d_rp64 = nullptr;
+    BIS_CHECK(dev_alloc(&d_rp64, (size_t)A->n_rows + 1));
+    if (A->rp_bytes == 8)
+        rp_to_i64_kernel<int64_t><<<256, 256, 0, c->stream>>>(A->n_rows + 1, static_cast<const int64_t *>(A->d_rp), d_rp64);
+    else
+        rp_to_i64_kernel<int32_t><<<256, 256, 0, c->stream>>>(A->n_rows + 1, static_cast<const int32_t *>(A->d_rp), d_rp64);
+    BIS_LAUNCH_CHECK(c);
+    BIS_CUDA(cudaMemcpyAsync(rp, d_rp64, sizeof(int64_t) * ((size_t)A->n_rows + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (A->nnz && col) {
+        int *d_tmp = nullptr;
+        BIS_CHECK(dev_alloc(&d_tmp, (size_t)A->nnz));
+        cols_to_global_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(A->nnz, A->d_col, A->n_cols, A->row_begin,
+                                                                    A->halo.d_ghost_global, d_tmp);
+        BIS_LAUNCH_CHECK(c);
+        BIS_CUDA(cudaMemcpyAsync(col, d_tmp, sizeof(int32_t) * (size_t)A->nnz, cudaMemcpyDeviceToHost, c->stream));
+        BIS_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(d_tmp);
+    }
+    if (A->nnz && val)
+        BIS_CUDA(cudaMemcpyAsync(val, A->d_val, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_rp64);
+    return 0;
+}
+
+namespace {
+template <typename RP>
+__global__ void extract_diag_kernel(int64_t n, const RP *rp, const int *col, const double *val,
+                                    double *D, double *D_inv, int *missing) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        bool found = false;
+        for (RP k = rp[r]; k < rp[r + 1]; ++k) {
+            if (col[k] == r) {   // local column id == local row id on the diagonal
+                double d = val[k];
+                D[r] = d;
+                if (D_inv) D_inv[r] = div_rn(1.0, d);
+                found = true;   // peel_diag_crs_new keeps the LAST match (LU_factors.hpp:836-850)
+            }
+        }
+        if (!found) atomicExch(missing, (int)(r + 1 > 0x7fffffff ? 0x7fffffff : r + 1));
+    }
+}
+} // namespace
+
+extern "C" int bis_matrix_extract_diagonal(bis_context *c, const bis_matrix *A, double *D, double *D_inv) {
+    BIS_REQUIRE(c && A && D, "null argument");
+    BIS_CUDA(cudaSetDevice(c->device));
+    int *d_missing = nullptr;
+    BIS_CHECK(dev_alloc(&d_missing, 1));
+    BIS_CUDA(cudaMemsetAsync(d_missing, 0, sizeof(int), c->stream));
+    const int blocks = bis_blocks_for(A->n_rows, 256, c->sm_count * 8);
+    if (A->rp_bytes == 8)
+        extract_diag_kernel<int64_t><<<blocks, 256, 0, c->stream>>>(A->n_rows, static_cast<const int64_t *>(A->d_rp), A->d_col, A->d_val, D, D_inv, d_missing);
+    else
+        extract_diag_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(A->n_rows, static_cast<const int32_t *>(A->d_rp), A->d_col, A->d_val, D, D_inv, d_missing);
+    BIS_LAUNCH_CHECK(c);
+    int missing = 0;
+    BIS_CUDA(cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_missing);
+    // SanityChecker::no_diag (common.hpp:393-396) is fatal in the reference
+    BIS_REQUIRE(missing == 0, "No diagonal to extract at row index %d", missing - 1);
+    return 0;
+}
+
+// split_LU_new (LU_factors.hpp:122-309), strict parts.  Host round trip for
+// now (device-side split + level analysis is SURVEY.md 8(f) "next").
+extern "C" int bis_matrix_split_triangular(bis_context *c, const bis_matrix *A, bis_matrix **L,
+                                           bis_matrix **U) {
+    BIS_REQUIRE(c && A && L && U, "null argument");
+    BIS_REQUIRE(!A->distributed && c->nranks == 1, "bis_matrix_split_triangular: single-GPU only");
+    BIS_REQUIRE(A->nnz < INT32_MAX, "bis_matrix_split_triangular: nnz exceeds 32-bit row_ptr");
+    const int64_t n = A->n_rows;
+    std::vector<int64_t> rp((size_t)n + 1);
+    std::vector<int32_t> col((size_t)A->nnz);
+    std::vector<double> val((size_t)A->nnz);
+    BIS_CHECK(bis_matrix_download_crs(c, A, rp.data(), col.data(), val.data()));
+    std::vector<int32_t> lrp((size_t)n + 1, 0), urp((size_t)n + 1, 0);
+    for (int64_t r = 0; r < n; ++r) {
+        int32_t nl = 0, nu = 0;
+        for (int64_t k = rp[r]; k < rp[r + 1]; ++k) {
+            if (col[k] < r) ++nl;
+            else if (col[k] > r) ++nu;
+        }
+        lrp[r + 1] = lrp[r] + nl;
+        urp[r + 1] = urp[r] + nu;
+    }
+    std::vector<int32_t> lcol((size_t)lrp[n]), ucol((size_t)urp[n]);
+    std::vector<double> lval((size_t)lrp[n]), uval((size_t)urp[n]);
+    for (int64_t r = 0; r < n; ++r) {
+        int32_t pl = lrp[r], pu = urp[r];
+        for (int64_t k = rp[r]; k < rp[r + 1]; ++k) {
+            if (col[k] < r) { lcol[pl] = col[k]; lval[pl++] = val[k]; }
+            else if (col[k] > r) { ucol[pu] = col[k]; uval[pu++] = val[k]; }
+        }
+    }
+    BIS_CHECK(bis_matrix_upload_triangular(c, n, lrp[n], lrp.data(), lcol.data(), lval.data(), 0, L));
+    if (bis_matrix_upload_triangular(c, n, urp[n], urp.data(), ucol.data(), uval.data(), 1, U) != 0) {
+        bis_matrix_free(c, *L);
+        *L = nullptr;
+        return 1;
+    }
+    return 0;
+}

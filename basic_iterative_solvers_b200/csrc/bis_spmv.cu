@@ -1,0 +1,269 @@
+// bis_spmv.cu -- CRS sparse matrix-vector product (native_spmv,
+// kernels.hpp:22-42) and its fused forms:
+//   y = A x                                   bis_spmv            kernels.hpp:44-52
+//   y = A x ; (y,w) ; (y,y)                   bis_spmv_dot        cg.hpp:16-23, bicgstab.hpp:30-34,48-51
+//   tmp = A x ; r = b - tmp ; (r,r)           bis_spmv_residual   kernels.hpp:155-162 + 194-203
+//   x_new = (b - (A x_old - D x_old)) / D     bis_spmv_jacobi     jacobi.hpp:27-52
+//   out = b - T x                             bis_spmv_sub        gauss_seidel.hpp:30-34
+//
+// Roofline: HBM.  Algorithmic bytes per launch:
+//   12*nnz + sizeof(row_ptr)*(n+1) + 8*n (x once) + 8*n (y)   [+ 8*n per extra
+//   vector an epilogue reads or writes].
+//
+// Variant 1 ("vector CRS"): LPR lanes cooperate on one row (LPR = 2..32 chosen
+// from the mean row length), lanes read consecutive nonzeros (coalesced 8-byte
+// val / 4-byte col loads marked evict-first so that x stays cached), x is
+// gathered through the read-only path, partial sums are combined by a
+// fixed-shape shuffle tree (deterministic), and the epilogue runs on the
+// group's first lane.  The grid is persistent (SM count x resident blocks) with
+// a static row assignment so the fused dot products are bit-reproducible.
+//
+// Variant 2 (TMA-staged, thread-per-row) lives in bis_spmv_tma.cu.
+#include "bis_device.cuh"
+
+namespace {
+
+constexpr int SPMV_THREADS = 256;
+
+struct SpmvIn {
+    const void *rp;
+    const int *col;
+    const double *val;
+    const double *x;       // owned part, indexed by local column
+    const double *ghost;   // halo part, indexed by column - n_owned
+    int64_t n_owned;
+    // rows handled by this launch: [lo1, lo1+cnt1) then [lo2, lo2+cnt2)
+    int64_t lo1, cnt1, lo2, cnt2;
+};
+
+struct EpiStore {
+    static constexpr int NRED = 0;
+    double *y;
+    __device__ __forceinline__ void operator()(int64_t r, double s, double *) const { y[r] = s; }
+};
+struct EpiDot {
+    static constexpr int NRED = 2;
+    double *y;
+    const double *w;
+    __device__ __forceinline__ void operator()(int64_t r, double s, double *acc) const {
+        y[r] = s;
+        acc[0] = fma(s, w[r], acc[0]);
+        acc[1] = fma(s, s, acc[1]);
+    }
+};
+struct EpiResid {
+    static constexpr int NRED = 1;
+    const double *b;
+    double *res;
+    double *tmp;
+    __device__ __forceinline__ void operator()(int64_t r, double s, double *acc) const {
+        if (tmp) tmp[r] = s;
+        double v = sub_rn(b[r], s);   // subtract_vectors with scale 1.0
+        res[r] = v;
+        acc[0] = fma(v, v, acc[0]);
+    }
+};
+struct EpiJacobi {
+    static constexpr int NRED = 0;
+    const double *D, *b, *x_old;
+    double *x_new;
+    __device__ __forceinline__ void operator()(int64_t r, double s, double *) const {
+        double d = D[r];
+        double scaled = mul_rn(d, x_old[r]);
+        double adj = sub_rn(s, scaled);
+        x_new[r] = div_rn(sub_rn(b[r], adj), d);
+    }
+};
+struct EpiSub {
+    static constexpr int NRED = 0;
+    const double *b;
+    double *out;
+    __device__ __forceinline__ void operator()(int64_t r, double s, double *) const {
+        out[r] = sub_rn(b[r], s);
+    }
+};
+
+template <typename RP, int LPR, bool GHOST, class Epi>
+__global__ void __launch_bounds__(SPMV_THREADS)
+spmv_vec_kernel(SpmvIn in, Epi epi, RedArgs ra) {
+    constexpr int RPW = 32 / LPR;   // rows per warp per trip
+    const RP *__restrict__ rp = static_cast<const RP *>(in.rp);
+    const int *__restrict__ col = in.col;
+    const double *__restrict__ val = in.val;
+    const double *__restrict__ x = in.x;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
+    const int grp = lane / LPR;
+    const int64_t warp_global = (int64_t)blockIdx.x * (SPMV_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t total_warps = (int64_t)gridDim.x * (SPMV_THREADS / 32);
+    const int64_t total_rows = in.cnt1 + in.cnt2;
+
+    double acc[Epi::NRED > 0 ? Epi::NRED : 1];
+#pragma unroll
+    for (int q = 0; q < (Epi::NRED > 0 ? Epi::NRED : 1); ++q) acc[q] = 0.0;
+
+    for (int64_t v0 = warp_global * RPW; v0 < total_rows; v0 += total_warps * RPW) {
+        const int64_t v = v0 + grp;
+        const bool live = v < total_rows;
+        const int64_t r = live ? (v < in.cnt1 ? in.lo1 + v : in.lo2 + (v - in.cnt1)) : 0;
+        double sum = 0.0;
+        if (live) {
+            const RP s = rp[r], e = rp[r + 1];
+#pragma unroll 4
+            for (RP k = s + sub; k < e; k += LPR) {
+                const int c = ld_stream(col + k);
+                const double a = ld_stream(val + k);
+                double xv;
+                if (GHOST && c >= in.n_owned) xv = __ldg(in.ghost + (c - in.n_owned));
+                else xv = __ldg(x + c);
+                sum = fma(a, xv, sum);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, LPR);
+        if (live && sub == 0) epi(r, sum, acc);
+    }
+    if constexpr (Epi::NRED > 0) block_reduce_finish<Epi::NRED>(acc, ra);
+}
+
+template <typename RP, int LPR, bool GHOST, class Epi>
+int launch_one(bis_context *c, const SpmvIn &in, const Epi &epi, RedArgs &ra, int *blocks_out) {
+    static int occ = 0;
+    if (!occ) {
+        BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, spmv_vec_kernel<RP, LPR, GHOST, Epi>, SPMV_THREADS, 0));
+        if (occ < 1) occ = 1;
+    }
+    const int64_t rows = in.cnt1 + in.cnt2;
+    constexpr int rows_per_block = (SPMV_THREADS / 32) * (32 / LPR);
+    int cap = c->sm_count * occ;
+    if (cap > BIS_MAX_RED_BLOCKS / 2) cap = BIS_MAX_RED_BLOCKS / 2;
+    int blocks = bis_blocks_for(rows, rows_per_block, cap);
+    *blocks_out = blocks;
+    if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + blocks;
+    spmv_vec_kernel<RP, LPR, GHOST, Epi><<<blocks, SPMV_THREADS, 0, c->stream>>>(in, epi, ra);
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}
+
+template <typename RP, bool GHOST, class Epi>
+int launch_lanes(bis_context *c, int lanes, const SpmvIn &in, const Epi &epi, RedArgs &ra, int *nb) {
+    switch (lanes) {
+    case 2: return launch_one<RP, 2, GHOST, Epi>(c, in, epi, ra, nb);
+    case 4: return launch_one<RP, 4, GHOST, Epi>(c, in, epi, ra, nb);
+    case 8: return launch_one<RP, 8, GHOST, Epi>(c, in, epi, ra, nb);
+    case 16: return launch_one<RP, 16, GHOST, Epi>(c, in, epi, ra, nb);
+    default: return launch_one<RP, 32, GHOST, Epi>(c, in, epi, ra, nb);
+    }
+}
+
+int pick_lanes(const bis_context *c, const bis_matrix *A) {
+    if (c->opt_spmv_lanes >= 2) {
+        int l = 2;
+        while (l < c->opt_spmv_lanes && l < 32) l <<= 1;
+        return l;
+    }
+    // ~4 nonzeros per lane: 27/row -> 8 lanes, 7/row -> 2, 13/row -> 4
+    double m = A->mean_row;
+    int l = 2;
+    while (l < 32 && l * 4 < m) l <<= 1;
+    return l;
+}
+
+template <bool GHOST, class Epi>
+int launch_rp(bis_context *c, const bis_matrix *A, const SpmvIn &in, const Epi &epi, RedArgs &ra,
+              int *nb) {
+    const int lanes = pick_lanes(c, A);
+    if (A->rp_bytes == 8) return launch_lanes<int64_t, GHOST, Epi>(c, lanes, in, epi, ra, nb);
+    return launch_lanes<int32_t, GHOST, Epi>(c, lanes, in, epi, ra, nb);
+}
+
+} // namespace
+
+// Variant 2 entry (bis_spmv_tma.cu); returns -1 when it does not apply.
+int bis_spmv_tma_try(bis_context *c, const bis_matrix *A, const double *x, int epi_kind,
+                     const void *epi, int slot_a, int slot_b);
+
+// Shared driver: halo exchange (distributed) overlapped with the interior rows.
+template <class Epi>
+static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, const Epi &epi,
+                       int slot_a, int slot_b) {
+    BIS_REQUIRE(c && A && x, "spmv: null argument");
+    BIS_CUDA(cudaSetDevice(c->device));
+    RedArgs ra = bis_red_args(c, slot_a, slot_b);
+    SpmvIn in;
+    in.rp = A->d_rp;
+    in.col = A->d_col;
+    in.val = A->d_val;
+    in.x = x;
+    in.ghost = A->halo.d_ghost;
+    in.n_owned = A->n_cols;
+    int nb = 0;
+    if (!A->distributed || A->halo.n_ghost == 0) {
+        in.lo1 = 0; in.cnt1 = A->n_rows; in.lo2 = 0; in.cnt2 = 0;
+        BIS_CHECK((launch_rp<false, Epi>(c, A, in, epi, ra, &nb)));
+    } else {
+        // rows [interior_begin, interior_end) touch no ghost column: run them
+        // while the halo is in flight, then the two boundary strips.
+        BIS_CHECK(bis_halo_exchange_begin(c, A, x));
+        const int64_t ib = A->halo.interior_begin, ie = A->halo.interior_end;
+        int nb1 = 0;
+        if (ie > ib) {
+            in.lo1 = ib; in.cnt1 = ie - ib; in.lo2 = 0; in.cnt2 = 0;
+            ra.finalize = 0;
+            BIS_CHECK((launch_rp<false, Epi>(c, A, in, epi, ra, &nb1)));
+        }
+        BIS_CHECK(bis_halo_exchange_end(c, A));
+        in.lo1 = 0; in.cnt1 = (ie > ib) ? ib : A->n_rows;
+        in.lo2 = ie; in.cnt2 = (ie > ib) ? A->n_rows - ie : 0;
+        ra.finalize = 1;
+        ra.block_offset = nb1;
+        BIS_CHECK((launch_rp<true, Epi>(c, A, in, epi, ra, &nb)));
+    }
+    if (Epi::NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));
+    return 0;
+}
+
+extern "C" int bis_spmv(bis_context *c, const bis_matrix *A, const double *x, double *y) {
+    BIS_REQUIRE(y, "bis_spmv: null y");
+    EpiStore e{y};
+    return spmv_driver(c, A, x, e, -1, -1);
+}
+
+extern "C" int bis_spmv_dot(bis_context *c, const bis_matrix *A, const double *x, double *y,
+                            const double *w, int slot_yw, int slot_yy) {
+    BIS_REQUIRE(y && w, "bis_spmv_dot: null argument");
+    BIS_REQUIRE(slot_yw >= 0 && slot_yw < BIS_NUM_SCALARS && slot_yy < BIS_NUM_SCALARS,
+                "bis_spmv_dot: bad slot");
+    EpiDot e{y, w};
+    return spmv_driver(c, A, x, e, slot_yw, slot_yy);
+}
+
+extern "C" int bis_spmv_residual(bis_context *c, const bis_matrix *A, const double *x,
+                                 const double *b, double *r, double *tmp, int slot_rr) {
+    BIS_REQUIRE(b && r, "bis_spmv_residual: null argument");
+    BIS_REQUIRE(slot_rr >= 0 && slot_rr < BIS_NUM_SCALARS, "bis_spmv_residual: bad slot");
+    EpiResid e{b, r, tmp};
+    return spmv_driver(c, A, x, e, slot_rr, -1);
+}
+
+extern "C" int bis_spmv_jacobi(bis_context *c, const bis_matrix *A, const double *D,
+                               const double *b, const double *x_old, double *x_new) {
+    BIS_REQUIRE(D && b && x_new, "bis_spmv_jacobi: null argument");
+    EpiJacobi e{D, b, x_old, x_new};
+    return spmv_driver(c, A, x_old, e, -1, -1);
+}
+
+extern "C" int bis_spmv_sub(bis_context *c, const bis_matrix *T, const double *x, const double *b,
+                            double *out) {
+    BIS_REQUIRE(b && out, "bis_spmv_sub: null argument");
+    EpiSub e{b, out};
+    return spmv_driver(c, T, x, e, -1, -1);
+}
+
+// compute_residual, kernels.hpp:155-162 (tmp is materialised as the reference does)
+extern "C" int bis_compute_residual(bis_context *c, const bis_matrix *A, const double *x,
+                                    const double *b, double *residual, double *tmp) {
+    BIS_REQUIRE(tmp, "bis_compute_residual: null tmp");
+    return bis_spmv_residual(c, A, x, b, residual, tmp, BIS_NUM_SCALARS - 2);
+}

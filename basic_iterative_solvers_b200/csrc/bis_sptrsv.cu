@@ -1,0 +1,226 @@
+// bis_sptrsv.cu -- forward / backward sparse triangular solves
+// (native_sptrsv kernels.hpp:54-76, native_bsptrsv kernels.hpp:88-107) and
+// apply_preconditioner (kernels.hpp:336-414).
+//
+// The reference walks the rows strictly in sequence.  The value of a row does
+// not depend on the schedule, only on its own summation order, so the rows are
+// processed here in LEVEL order (level(r) = 1 + max level of the rows it reads)
+// by ONE launch: a thread owns a row, adds its products left to right in
+// storage order with unfused multiply/add (bit-identical to the reference's
+// scalar loop), and a warp starts a level once the completion
+// counter of the previous level has reached that level's size.  Blocks take
+// their chunk of the level-ordered row list from a ticket counter, so a block
+// only ever waits for blocks that already run: no co-residency assumption, no
+// grid barrier, no deadlock.  The factor is stored a second time in level order
+// (LevelSets::d_rp/d_col/d_val) so that consecutive threads stream consecutive
+// rows; each thread prefetches its row into registers BEFORE it waits, which
+// takes the HBM latency off the level-to-level critical path.
+//
+// Roofline: HBM for the bytes (12*nnz + 4*n level ids + 4*n row ids +
+// sizeof(rp)*n + 24*n for b, D, x), but the run time is bounded below by
+// n_levels x (L2 round trip + fence): latency-bound for stencil orderings
+// (HPCG-n has 7n-6 levels).
+#include "bis_device.cuh"
+
+namespace {
+
+constexpr int TRSV_THREADS = 256;
+constexpr int TRSV_PF = 16;   // nonzeros prefetched into registers per row
+
+struct TrsvArgs {
+    int64_t n_slots;
+    const int *slot_row;
+    const int *slot_level;
+    const int64_t *rp;      // level-ordered
+    const int *col;
+    const double *val;
+    const int *level_size;
+    unsigned int *level_done;
+    unsigned int *ticket;
+    int *errflag;
+    double *x;
+    const double *D;
+    const double *b;
+};
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
+    return *reinterpret_cast<const volatile unsigned int *>(p);
+}
+
+__global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) {
+    __shared__ unsigned int s_chunk;
+    if (threadIdx.x == 0) s_chunk = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t slot = (int64_t)s_chunk * TRSV_THREADS + threadIdx.x;
+    const bool live = slot < a.n_slots;
+
+    int row = 0, lvl = 0x7fffffff;
+    int64_t s = 0, e = 0;
+    double bb = 0.0, dd = 1.0;
+    if (live) {
+        row = a.slot_row[slot];
+        lvl = a.slot_level[slot];
+        s = a.rp[slot];
+        e = a.rp[slot + 1];
+        bb = a.b[row];
+        dd = a.D[row];
+    }
+    // prefetch the head of the row while earlier levels are still running
+    double av[TRSV_PF];
+    int cv[TRSV_PF];
+#pragma unroll
+    for (int j = 0; j < TRSV_PF; ++j) {
+        const bool ok = s + j < e;
+        av[j] = ok ? __ldcs(a.val + s + j) : 0.0;
+        cv[j] = ok ? __ldcs(a.col + s + j) : 0;
+    }
+    // levels present in this warp (rows are sorted by level)
+    int lv_lo = lvl, lv_hi = live ? lvl : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lv_lo = min(lv_lo, __shfl_xor_sync(0xffffffffu, lv_lo, o));
+        lv_hi = max(lv_hi, __shfl_xor_sync(0xffffffffu, lv_hi, o));
+    }
+    for (int lv = lv_lo; lv <= lv_hi; ++lv) {
+        if (lv > 0) {
+            if (lane == 0) {
+                const unsigned int need = (unsigned int)a.level_size[lv - 1];
+                long long t0 = clock64();
+                unsigned int spins = 0;
+                while (ld_volatile_u32(a.level_done + (lv - 1)) < need) {
+                    if ((++spins & 1023u) == 0) {
+                        if (*reinterpret_cast<volatile int *>(a.errflag)) break;
+                        if (clock64() - t0 > 6000000000LL) {   // ~3 s: something is broken
+                            atomicExch(a.errflag, 1);
+                            break;
+                        }
+                    }
+                }
+                __threadfence();   // acquire: order the x loads after the counter read
+            }
+            __syncwarp();
+        }
+        const bool mine = live && lvl == lv;
+        if (mine) {
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < TRSV_PF; ++j)
+                if (s + j < e) sum = add_rn(sum, mul_rn(av[j], __ldcg(a.x + cv[j])));
+            for (int64_t k = s + TRSV_PF; k < e; ++k)
+                sum = add_rn(sum, mul_rn(a.val[k], __ldcg(a.x + a.col[k])));
+            __stcg(a.x + row, div_rn(sub_rn(bb, sum), dd));
+            __threadfence();   // release: x[row] visible before the counter moves
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0 && m) atomicAdd(a.level_done + lv, (unsigned int)__popc(m));
+    }
+}
+
+// Safety-net variant: one launch per level (opt "trsv_variant" = 1).
+__global__ void __launch_bounds__(TRSV_THREADS)
+sptrsv_one_level_kernel(TrsvArgs a, int64_t slot_begin, int64_t slot_end) {
+    const int64_t slot = slot_begin + (int64_t)blockIdx.x * TRSV_THREADS + threadIdx.x;
+    if (slot >= slot_end) return;
+    const int row = a.slot_row[slot];
+    const int64_t s = a.rp[slot], e = a.rp[slot + 1];
+    double sum = 0.0;
+    for (int64_t k = s; k < e; ++k) sum = add_rn(sum, mul_rn(a.val[k], __ldcg(a.x + a.col[k])));
+    a.x[row] = div_rn(sub_rn(a.b[row], sum), a.D[row]);
+}
+
+} // namespace
+
+static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const double *D,
+                      const double *b, int want_kind) {
+    BIS_REQUIRE(c && T && x && D && b, "sptrsv: null argument");
+    BIS_REQUIRE(T->triangular == want_kind,
+                "sptrsv: matrix is not the %s strictly-triangular factor this call needs",
+                want_kind == 1 ? "lower" : "upper");
+    BIS_REQUIRE(!T->distributed, "sptrsv: triangular sweeps do not shard (single-GPU only)");
+    BIS_CUDA(cudaSetDevice(c->device));
+    const LevelSets &lv = T->lv;
+    if (T->n_rows == 0) return 0;
+    TrsvArgs a;
+    a.n_slots = lv.n_slots;
+    a.slot_row = lv.d_slot_row;
+    a.slot_level = lv.d_slot_level;
+    a.rp = lv.d_rp;
+    a.col = lv.d_col;
+    a.val = lv.d_val;
+    a.level_size = lv.d_level_size;
+    a.level_done = lv.d_level_done;
+    a.ticket = lv.d_ticket;
+    a.errflag = c->d_errflag;
+    a.x = x;
+    a.D = D;
+    a.b = b;
+    if (c->opt_trsv_variant == 1) {
+        const std::vector<int64_t> &ls = lv.level_start;
+        for (int l = 0; l < lv.n_levels; ++l) {
+            int64_t cnt = ls[l + 1] - ls[l];
+            int blocks = (int)((cnt + TRSV_THREADS - 1) / TRSV_THREADS);
+            sptrsv_one_level_kernel<<<blocks, TRSV_THREADS, 0, c->stream>>>(a, ls[l], ls[l + 1]);
+            BIS_LAUNCH_CHECK(c);
+        }
+        return 0;
+    }
+    BIS_CUDA(cudaMemsetAsync(lv.d_level_done, 0, sizeof(unsigned int) * (size_t)lv.n_levels, c->stream));
+    BIS_CUDA(cudaMemsetAsync(lv.d_ticket, 0, sizeof(unsigned int), c->stream));
+    const int64_t blocks = (lv.n_slots + TRSV_THREADS - 1) / TRSV_THREADS;
+    sptrsv_level_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a);
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}
+
+extern "C" int bis_sptrsv(bis_context *c, const bis_matrix *L, double *x, const double *D,
+                          const double *b) {
+    return trsv_solve(c, L, x, D, b, 1);
+}
+extern "C" int bis_bsptrsv(bis_context *c, const bis_matrix *U, double *x, const double *D,
+                           const double *b) {
+    return trsv_solve(c, U, x, D, b, 2);
+}
+
+// apply_preconditioner, kernels.hpp:336-414 with PRECOND_OUTER_ITERS = 1 and
+// PRECOND_INNER_ITERS = 0 (CMakeLists.txt:24-25).
+extern "C" int bis_apply_preconditioner(bis_context *c, int precond, int64_t n,
+                                        const bis_matrix *L, const bis_matrix *U,
+                                        const double *A_D, const double *A_D_inv,
+                                        const double *L_D, const double *U_D, double *out,
+                                        double *in, double *tmp, double *work) {
+    BIS_REQUIRE(c && out && in, "bis_apply_preconditioner: null argument");
+    switch (precond) {
+    case BIS_PRECOND_JACOBI:
+        return bis_elemwise_div_vectors(c, out, in, A_D, n, 1.0);
+    case BIS_PRECOND_GS:
+        return bis_sptrsv(c, L, out, A_D, in);
+    case BIS_PRECOND_BGS:
+        return bis_bsptrsv(c, U, out, A_D, in);
+    case BIS_PRECOND_SGS:
+        BIS_REQUIRE(tmp, "bis_apply_preconditioner: sgs needs tmp");
+        BIS_CHECK(bis_sptrsv(c, L, tmp, A_D, in));                  // tmp <- (L+D)^-1 in
+        BIS_CHECK(bis_elemwise_mult_vectors(c, tmp, tmp, A_D, n, 1.0));   // tmp <- D tmp
+        return bis_bsptrsv(c, U, out, A_D, tmp);                    // out <- (D+U)^-1 tmp
+    case BIS_PRECOND_2ST:
+        BIS_REQUIRE(work && A_D_inv, "bis_apply_preconditioner: 2st needs work and A_D_inv");
+        BIS_CHECK(bis_elemwise_mult_vectors(c, work, A_D_inv, in, n, 1.0));
+        return bis_copy_vector(c, out, work, n);
+    case BIS_PRECOND_S2ST:
+        BIS_REQUIRE(work && A_D_inv, "bis_apply_preconditioner: s2st needs work and A_D_inv");
+        BIS_CHECK(bis_elemwise_mult_vectors(c, work, A_D_inv, in, n, 1.0));
+        BIS_CHECK(bis_copy_vector(c, out, work, n));
+        BIS_CHECK(bis_elemwise_mult_vectors(c, out, out, A_D, n, 1.0));
+        BIS_CHECK(bis_elemwise_mult_vectors(c, work, A_D_inv, out, n, 1.0));
+        return bis_copy_vector(c, out, work, n);
+    case BIS_PRECOND_ILU0:
+        BIS_REQUIRE(tmp, "bis_apply_preconditioner: ilu0 needs tmp");
+        BIS_CHECK(bis_sptrsv(c, L, tmp, L_D, in));   // tmp <- L^-1 in (L_D == 1)
+        return bis_bsptrsv(c, U, out, U_D, tmp);     // out <- U^-1 tmp
+    case BIS_PRECOND_NONE:
+        return bis_copy_vector(c, out, in, n);
+    default:
+        bis_set_error("bis_apply_preconditioner: unknown preconditioner %d", precond);
+        return 2;
+    }
+}
