@@ -1,0 +1,65 @@
+// host/run.hpp -- run(): build the Solver for the chosen method, obtain A,
+// preprocess, solve, postprocess (reference main.cpp:17-70).  Shared by the CLI
+// (main.cpp) and the C entry point used by the tests (host_capi.cpp).
+#pragma once
+
+#include "methods/bicgstab.hpp"
+#include "methods/cg.hpp"
+#include "methods/gauss_seidel.hpp"
+#include "methods/gmres.hpp"
+#include "methods/jacobi.hpp"
+#include "postprocessing.hpp"
+#include "preprocessing.hpp"
+#include "solver_harness.hpp"
+#include "utilities.hpp"
+
+inline std::unique_ptr<Solver> make_solver(const Args *cli_args, Interface *dev) {
+    switch (cli_args->method) {
+    case SolverType::Jacobi: return std::make_unique<JacobiSolver>(cli_args, dev);
+    case SolverType::GaussSeidel: return std::make_unique<GaussSeidelSolver>(cli_args, dev);
+    case SolverType::SymmetricGaussSeidel: return std::make_unique<SymmetricGaussSeidelSolver>(cli_args, dev);
+    case SolverType::ConjugateGradient: return std::make_unique<ConjugateGradientSolver>(cli_args, dev);
+    case SolverType::GMRES: return std::make_unique<GMRESSolver>(cli_args, dev);
+    case SolverType::BiCGSTAB: return std::make_unique<BiCGSTABSolver>(cli_args, dev);
+    }
+    bis_fatal("Error: Unknown or unsupported solver type.");
+}
+
+// Matrix by name: built-in generators or a MatrixMarket file.  Matrices whose
+// factors are needed, or that fit the host container, are built on the host;
+// HPCG sizes beyond 32-bit nnz are generated on the device (Jacobi/none only).
+inline void obtain_matrix(const Args *cli_args, Interface *dev, bool need_host,
+                          std::unique_ptr<MatrixCRS> &A, std::unique_ptr<DeviceCRS> &dA) {
+    const MatrixSpec spec = parse_matrix_spec(cli_args->matrix_file_name);
+    if (spec.kind == MatrixSpec::File) {
+        MatrixCOO coo;
+        coo.read_from_mtx(spec.path);
+        A = std::make_unique<MatrixCRS>();
+        convert_coo_to_crs(&coo, A.get());
+        return;
+    }
+    if (need_host) {
+        A = spec.kind == MatrixSpec::Hpcg ? generate_hpcg(spec.nx, spec.ny, spec.nz)
+                                          : generate_anderson(spec.nx, spec.ny, spec.nz, spec.ranpot, spec.t,
+                                                              spec.seed, spec.periodic);
+        return;
+    }
+    dA = std::make_unique<DeviceCRS>();
+    dA->dev = dev;
+    if (spec.kind == MatrixSpec::Hpcg)
+        BIS_OK(bis_matrix_generate_hpcg(dev, spec.nx, spec.ny, spec.nz, &dA->handle));
+    else
+        BIS_OK(bis_matrix_generate_anderson(dev, spec.nx, spec.ny, spec.nz, spec.ranpot, spec.t, spec.seed,
+                                            spec.periodic ? 1 : 0, &dA->handle));
+    dA->refresh_info();
+}
+
+inline void run(Args *cli_args, Timers *timers, Interface *dev) {
+    std::unique_ptr<Solver> solver = make_solver(cli_args, dev);
+    std::unique_ptr<MatrixCRS> A;
+    std::unique_ptr<DeviceCRS> dA;
+    obtain_matrix(cli_args, dev, solver->needs_triangular_factors(), A, dA);
+    TIME(timers->preprocessing, preprocessing(cli_args, solver.get(), timers, A, std::move(dA)))
+    TIME(timers->solve, solve(cli_args, solver.get(), timers))
+    TIME(timers->postprocessing, postprocessing(cli_args, solver.get(), timers))
+}

@@ -1,0 +1,170 @@
+// host/solver.hpp -- the Solver base class of the reference (solver.hpp:9-193)
+// with device-resident state: every `double *` vector member is a DEVICE
+// address, the matrices are device CRS handles, and the residual history stays
+// on the host.  Virtual interface, member names, stopping logic
+// (solver.hpp:173-191) and history bookkeeping (solver.hpp:148-171) are the
+// reference's.
+#pragma once
+
+#include "common.hpp"
+#include "kernels.hpp"
+#include "sparse_matrix.hpp"
+
+#include <cfloat>
+
+// device scalar slots shared by the methods (include/bis_b200.h "device scalars")
+enum Slot : int {
+    S_RR = 0,        // (r,r) of the newest residual
+    S_RZ_NEW = 1,    // adjacent to S_RR: one allreduce of 2
+    S_RZ = 2,
+    S_PAP = 3,
+    S_R0V = 4,
+    S_ZS = 5,
+    S_ZZ = 6,        // adjacent to S_ZS
+    S_RHO_NEW = 7,
+    S_RR_BI = 8,     // adjacent to S_RHO_NEW
+    S_RHO_OLD = 9,
+    S_BETA2 = 10,
+    S_HN = 11,
+    S_H = 16         // S_H + j, j = 0..m  (GMRES Hessenberg column)
+};
+
+class Solver {
+  public:
+    SolverType method;
+    PrecondType preconditioner = PrecondType::None;
+    Interface *dev = nullptr;   // the device context (the reference's `smax` slot)
+
+    // host copy of A (only kept while preprocessing needs it) and device mirrors
+    std::unique_ptr<MatrixCRS> A;
+    std::unique_ptr<DeviceCRS> dA, dL_strict, dU_strict;
+    int64_t N = 0;          // local rows
+    int64_t N_global = 0;
+
+    double stopping_criteria = 0.0;
+    int iter_count = 0;
+    int collected_residual_norms_count = 0;
+    double residual_norm = DBL_MAX;
+    int max_iters = MAX_ITERS;
+    double tolerance = TOL;
+    int residual_check_len = RES_CHECK_LEN;
+    int gmres_restart_len = 0;
+    int gmres_restart_count = 0;
+    bool num_scale = false;
+
+    // common vectors [dev]
+    double *x_star = nullptr, *x_0 = nullptr, *b = nullptr, *tmp = nullptr, *work = nullptr;
+    double *residual = nullptr, *residual_0 = nullptr;
+    double *A_D = nullptr, *A_D_inv = nullptr, *L_D = nullptr, *U_D = nullptr;
+
+    // bookkeeping [host]
+    double *collected_residual_norms = nullptr;
+    double *time_per_iteration = nullptr;
+
+    bool convergence_flag = false;
+    bool gmres_restarted = false;
+
+    Solver(const Args *cli_args, Interface *device)
+        : method(cli_args->method), preconditioner(cli_args->preconditioner), dev(device),
+          gmres_restart_len(cli_args->restart_length), num_scale(cli_args->num_scale) {
+        collected_residual_norms = new double[max_iters * 2]();
+        time_per_iteration = new double[max_iters * 2]();
+    }
+
+    virtual void iterate(Timers *) = 0;
+    virtual void exchange() = 0;
+
+    bool needs_triangular_factors() const {
+        return method == SolverType::GaussSeidel || method == SolverType::SymmetricGaussSeidel ||
+               preconditioner == PrecondType::GaussSeidel ||
+               preconditioner == PrecondType::BackwardsGaussSeidel ||
+               preconditioner == PrecondType::SymmetricGaussSeidel ||
+               preconditioner == PrecondType::ILU0;
+    }
+
+    // solver.hpp:82-110: x_star = 0, x_0 = INIT_X_VAL, b = B_VAL, diagonals = 1
+    virtual void allocate_structs(const int64_t n) {
+        N = n;
+        x_star = dev_new(dev, n);
+        x_0 = dev_new(dev, n);
+        b = dev_new(dev, n);
+        tmp = dev_new(dev, n);
+        work = dev_new(dev, n);
+        residual = dev_new(dev, n);
+        residual_0 = dev_new(dev, n);
+        A_D = dev_new(dev, n);
+        A_D_inv = dev_new(dev, n);
+        L_D = dev_new(dev, n);
+        U_D = dev_new(dev, n);
+        if (!gmres_restarted) {
+            init_vector(dev, x_star, 0.0, n);
+            init_vector(dev, x_0, INIT_X_VAL, n);
+            init_vector(dev, b, B_VAL, n);
+            init_vector(dev, A_D, 1.0, n);
+            init_vector(dev, A_D_inv, 0.0, n);
+            init_vector(dev, L_D, 1.0, n);
+            init_vector(dev, U_D, 1.0, n);
+        }
+    }
+
+    // solver.hpp:112-120
+    virtual void init_structs(const int64_t n) {
+        init_vector(dev, tmp, 0.0, n);
+        init_vector(dev, work, 0.0, n);
+        init_vector(dev, residual, 0.0, n);
+        init_vector(dev, residual_0, 0.0, n);
+    }
+
+    virtual void check_restart(Timers *) {}
+    virtual void get_explicit_x() {}
+
+    virtual ~Solver() {
+        for (double **p : {&x_star, &x_0, &b, &tmp, &work, &residual, &residual_0, &A_D, &A_D_inv, &L_D, &U_D})
+            dev_delete(dev, *p);
+        delete[] collected_residual_norms;
+        delete[] time_per_iteration;
+    }
+
+    // solver.hpp:148-151
+    virtual void init_residual() {
+        copy_vector(dev, residual_0, residual, N);
+        collected_residual_norms[collected_residual_norms_count++] = residual_norm;
+    }
+
+    // solver.hpp:153-159: true residual of x_star, parked at [count + 1]
+    virtual void save_x_star() {
+        BIS_OK(bis_spmv_residual(dev, dA->handle, x_star, b, residual, tmp, S_RR));
+        residual_norm = std::sqrt(scalar(dev, S_RR));
+        if (collected_residual_norms_count + 1 < 2 * max_iters)
+            collected_residual_norms[collected_residual_norms_count + 1] = residual_norm;
+    }
+
+    virtual void record_residual_norm() {
+        collected_residual_norms[collected_residual_norms_count++] = residual_norm;
+    }
+
+    void sample_residual(Stopwatch *per_iteration_time) {
+        if (iter_count % residual_check_len == 0) {
+            record_residual_norm();
+            time_per_iteration[collected_residual_norms_count] = per_iteration_time->check();
+        }
+    }
+
+    void init_stopping_criteria() { stopping_criteria = tolerance * residual_norm; }
+
+    bool check_stopping_criteria() {
+        bool norm_convergence = std::abs(residual_norm) < stopping_criteria;
+        bool over_max_iters = iter_count >= (max_iters - gmres_restart_count);
+        bool divergence = std::abs(residual_norm) > DBL_MAX || std::isnan(residual_norm);
+        return norm_convergence || over_max_iters || divergence;
+    }
+
+  protected:
+    void precondition(double *out, double *in) {
+        apply_preconditioner(dev, preconditioner, N, dL_strict.get(), dU_strict.get(), A_D, A_D_inv,
+                             L_D, U_D, out, in, tmp, work);
+    }
+    bool fused_precond() const {
+        return preconditioner == PrecondType::None || preconditioner == PrecondType::Jacobi;
+    }
+};
