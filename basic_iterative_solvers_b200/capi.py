@@ -104,6 +104,22 @@ def declared_symbols() -> list[str]:
     return sorted(set(re.findall(r"\b(bis_[a-z0-9_]+)\s*\(", txt)))
 
 
+def _preload_nccl() -> None:
+    """libbis_b200.so needs libnccl.so.2.  PyTorch bundles a newer NCCL under the same SONAME
+    than the system one; whichever is loaded first serves the whole process, so load the
+    bundled one first (when present) to keep a later `import torch` working."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            return
+
+
 def load() -> C.CDLL:
     global _lib
     if _lib is not None:
@@ -111,6 +127,7 @@ def load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise BisError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
                        f"g.build()'` (there is no CPU fallback)")
+    _preload_nccl()
     lib = C.CDLL(LIB_PATH)
     lib.bis_last_error.restype = C.c_char_p
     lib.bis_last_error.argtypes = []

@@ -1,0 +1,126 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference compiled in the build
+container (oracle/_ref/libbis_ref.so, built from /root/reference by oracle/Makefile).
+
+Run from the repo root:  python tests/golden/make_golden.py
+
+The fixtures pin the oracle (oracle/port) and the CUDA path to outputs of the real
+reference: residual histories, iteration counts, final true residuals, triangular
+factors, ILU(0) factors and kernel outputs.  All reference runs use ONE OpenMP thread
+(the reference's reductions are thread-count dependent) and the stock
+flavour of the build (-O3 -fopenmp, -march=x86-64-v3).  ILU(0) uses factor_ILU0_old
+(LU_factors.hpp:320-539): factor_ILU0_new needs the absent SMAX library.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import matgen, refshim  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+REF_DATA = "/root/reference/data/matrices"
+
+SOLVES = [("j", "none"), ("gs", "none"), ("sgs", "none"), ("cg", "none"), ("gm", "none"), ("bi", "none"),
+          ("cg", "j"), ("cg", "gs"), ("cg", "sgs"), ("cg", "ilu0"),
+          ("gm", "j"), ("gm", "gs"), ("gm", "bgs"), ("gm", "sgs"), ("gm", "ilu0"),
+          ("bi", "j"), ("bi", "gs"), ("bi", "bgs"), ("bi", "sgs"), ("bi", "ilu0")]
+
+
+def solves(rp, col, val, which, restart_len=10):
+    out = {}
+    for method, pre in which:
+        r = refshim.solve(rp, col, val, method, pre, restart_len=restart_len, threads=1)
+        key = f"{method}__{pre}"
+        out[key + "__history"] = r.history
+        out[key + "__meta"] = np.array([r.iter_count, int(r.converged), r.restarts], np.int64)
+        out[key + "__final"] = np.array([r.final_true_residual, r.stopping_criteria])
+        out[key + "__x"] = r.x_star
+        print(f"  {key:14s} its={r.iter_count:4d} conv={int(r.converged)} restarts={r.restarts} "
+              f"r0={r.history[0]:.16e} final={r.final_true_residual:.3e}")
+    return out
+
+
+def kernels(rp, col, val, seed):
+    """Kernel-level outputs of the reference on seeded inputs."""
+    rng = np.random.default_rng(seed)
+    n = rp.size - 1
+    x = rng.uniform(-1.0, 1.0, n)
+    v = rng.uniform(-1.0, 1.0, n)
+    out = {"x": x, "v": v}
+    out["spmv"] = refshim.spmv(rp, col, val, x)
+    fac = refshim.factor(rp, col, val, "sgs")
+    for k in ("l_rp", "l_col", "l_val", "u_rp", "u_col", "u_val", "A_D", "A_D_inv"):
+        out["split__" + k] = getattr(fac, k)
+    out["sptrsv"] = refshim.sptrsv(fac.l_rp, fac.l_col, fac.l_val, fac.A_D, x)
+    out["bsptrsv"] = refshim.sptrsv(fac.u_rp, fac.u_col, fac.u_val, fac.A_D, x, backward=True)
+    out["sptrsv_inplace"] = refshim.sptrsv_inplace(fac.l_rp, fac.l_col, fac.l_val, fac.A_D, x)
+    for pre in ("none", "j", "gs", "bgs", "sgs"):
+        out["precond__" + pre] = refshim.apply_preconditioner(pre, fac, x)
+    ilu = refshim.factor(rp, col, val, "ilu0", ilu0_old=True)
+    for k in ("l_rp", "l_col", "l_val", "u_rp", "u_col", "u_val", "L_D", "U_D"):
+        out["ilu0__" + k] = getattr(ilu, k)
+    out["precond__ilu0"] = refshim.apply_preconditioner("ilu0", ilu, x)
+    lib = refshim.load()
+    for name in ("subtract_vectors", "sum_vectors", "elemwise_mult_vectors", "elemwise_div_vectors"):
+        o = np.zeros(n)
+        getattr(lib, "ref_" + name)(o, x, v + 2.0, n, 0.37)
+        out[name] = o
+    o = np.zeros(n)
+    lib.ref_scale(o, x, -1.25, n)
+    out["scale"] = o
+    out["dot"] = np.array([lib.ref_dot(x, v, n)])
+    out["norm"] = np.array([lib.ref_euclidean_vec_norm(x, n)])
+    xn = refshim.spmv(rp, col, val, x)
+    lib.ref_normalize_x(xn, x, fac.A_D, v, n)
+    out["normalize_x"] = xn
+    return out
+
+
+def main():
+    assert refshim.available(), "build oracle/_ref first: make -C oracle ref"
+    refshim.load().ref_omp_set_threads(1)
+
+    for fname, key in (("FDM-2d-16.mtx", "fdm2d16"), ("matrix_band_klein.mtx", "band_klein")):
+        print(key)
+        rp, col, val = refshim.read_mtx(os.path.join(REF_DATA, fname))
+        d = {"rp": rp, "col": col, "val": val}
+        d.update(solves(rp, col, val, SOLVES))
+        d.update({"k__" + k: v for k, v in kernels(rp, col, val, 7).items()})
+        np.savez_compressed(os.path.join(OUT, key + ".npz"), **d)
+
+    print("hpcg16")
+    rp, col, val = matgen.hpcg(16)
+    d = solves(rp, col, val, SOLVES)
+    d.update({"k__" + k: v for k, v in kernels(rp, col, val, 11).items()
+              if not k.startswith(("split__", "ilu0__l_", "ilu0__u_r", "ilu0__u_c"))})
+    np.savez_compressed(os.path.join(OUT, "hpcg16.npz"), **d)
+
+    print("hpcg32 (headline configs at reduced size)")
+    rp, col, val = matgen.hpcg(32)
+    d = solves(rp, col, val, [("cg", "none"), ("cg", "sgs"), ("bi", "j"), ("gm", "sgs")])
+    # histories only (x_star of 32768 rows x 4 is small enough too)
+    np.savez_compressed(os.path.join(OUT, "hpcg32.npz"), **d)
+
+    print("anderson 12x10x8 ranpot=5 seed=1 open BC (config 4 at reduced size)")
+    rp, col, val = matgen.anderson(12, 10, 8, ranpot=5.0, t=1.0, seed=1, periodic=False)
+    d = {"rp": rp.astype(np.int32), "col": col, "val": val}
+    d.update(solves(rp, col, val, [("gm", "ilu0"), ("gm", "j"), ("bi", "ilu0")]))
+    np.savez_compressed(os.path.join(OUT, "anderson_12_10_8.npz"), **d)
+
+    # diagonally dominant Anderson (ranpot shifts the spectrum): a well-conditioned ILU(0) case
+    print("anderson-dd 12x10x8 (diagonal + 8)")
+    val2 = val.copy()
+    n = rp.size - 1
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    val2[rows == col] += 8.0
+    d = {"rp": rp.astype(np.int32), "col": col, "val": val2}
+    d.update(solves(rp, col, val2, [("gm", "ilu0"), ("cg", "ilu0"), ("bi", "ilu0")]))
+    np.savez_compressed(os.path.join(OUT, "anderson_dd_12_10_8.npz"), **d)
+
+
+if __name__ == "__main__":
+    main()

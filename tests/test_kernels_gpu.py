@@ -1,0 +1,479 @@
+"""GPU parity tests, kernel level: every kernels.hpp entry of the C-ABI (include/bis_b200.h)
+against the oracle (oracle/port) and the fixtures produced by the compiled reference.
+
+Bit-exact: triangular solves, every preconditioner built from them, the axpby family, scale,
+copy, init, normalize_x given the same SpMV input, ILU(0) applies, generators, diagonal peel.
+Tolerance 1e-13 relative (order of summation is the kernel's, not the reference's, which the
+reference itself leaves to OpenMP/SIMD): SpMV, dot, norm and everything fused
+with them.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import matgen, port
+
+from basic_iterative_solvers_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+RED_TOL = 1e-13
+
+
+def rel(a, b):
+    s = max(np.max(np.abs(b)), 1e-300)
+    return np.max(np.abs(a - b)) / s
+
+
+def i32(*a):
+    return np.array(a, np.int32)
+
+
+def f64(*a):
+    return np.array(a, np.float64)
+
+
+def run_spmv(ctx, rp, col, val, x, lanes=0):
+    A = ctx.upload_crs(rp, col, val)
+    ctx.set_option("spmv_lanes", lanes)
+    dx, dy = ctx.upload(x), ctx.alloc(len(rp) - 1)
+    ctx.call("bis_spmv", A.h, dx, dy)
+    y = ctx.download(dy, len(rp) - 1)
+    ctx.set_option("spmv_lanes", 0)
+    ctx.free(dx), ctx.free(dy), A.free()
+    return y
+
+
+# ---- reference KATs through the C-ABI (tests/test_kernels.cpp) -------------------------------
+def test_kat_spmv(ctx):
+    assert np.array_equal(run_spmv(ctx, i32(0, 1, 2, 3), i32(0, 1, 2), f64(2, 3, 4), f64(1, 2, 3)), f64(2, 6, 12))
+    y = run_spmv(ctx, i32(0, 3, 6, 9), i32(0, 1, 2, 0, 1, 2, 0, 1, 2), f64(*range(1, 10)), f64(1, 2, 3))
+    assert np.array_equal(y, f64(14, 32, 50))
+
+
+def test_kat_sptrsv(ctx):
+    L = ctx.upload_triangular(i32(0, 0, 1, 3), i32(0, 0, 1), f64(1, -2, 1), upper=False)
+    U = ctx.upload_triangular(i32(0, 2, 3, 3), i32(1, 2, 2), f64(1, -2, 1), upper=True)
+    D = ctx.upload(f64(2, 3, 4))
+    x = ctx.alloc(3)
+    b = ctx.upload(f64(2, 7, 12))
+    ctx.call("bis_sptrsv", L.h, x, D, b)
+    assert np.allclose(ctx.download(x, 3), f64(1, 2, 3), atol=1e-9)
+    ctx.upload(f64(-2, 9, 12), b)
+    ctx.call("bis_bsptrsv", U.h, x, D, b)
+    assert np.allclose(ctx.download(x, 3), f64(1, 2, 3), atol=1e-9)
+    # wrong factor kind is an error, not a silent wrong answer
+    with pytest.raises(capi.BisError):
+        ctx.call("bis_sptrsv", U.h, x, D, b)
+    L.free(), U.free()
+
+
+def test_kat_vector_ops(ctx):
+    a, b, out = ctx.upload(f64(1, 2, 3)), ctx.upload(f64(4, 5, 6)), ctx.alloc(3)
+    ctx.call("bis_sum_vectors", out, a, b, 3, 2.0)
+    assert np.array_equal(ctx.download(out, 3), f64(9, 12, 15))
+    ctx.call("bis_subtract_vectors", out, a, b, 3, 2.0)
+    assert np.array_equal(ctx.download(out, 3), f64(-7, -8, -9))
+    ctx.call("bis_elemwise_mult_vectors", out, a, b, 3, 1.0)
+    assert np.array_equal(ctx.download(out, 3), f64(4, 10, 18))
+    ctx.call("bis_elemwise_div_vectors", out, b, a, 3, 1.0)
+    assert np.array_equal(ctx.download(out, 3), f64(4, 2.5, 2))
+    c = ctx.upload(f64(2, 4, 5))
+    assert ctx.dot(a, c, 3) == 25.0
+    ctx.call("bis_scale", out, a, 3.0, 3)
+    assert np.array_equal(ctx.download(out, 3), f64(3, 6, 9))
+    d = ctx.upload(f64(3, 4))
+    assert ctx.norm(d, 2) == 5.0
+    assert ctx.norm(d, 0) == 0.0          # tests/test_utilities.cpp:55-62 (empty vector)
+    ctx.call("bis_init_vector", out, 7.5, 3)
+    assert np.array_equal(ctx.download(out, 3), f64(7.5, 7.5, 7.5))
+    ctx.call("bis_copy_vector", out, a, 3)
+    assert np.array_equal(ctx.download(out, 3), f64(1, 2, 3))
+
+
+# ---- SpMV ------------------------------------------------------------------------------
+@pytest.mark.parametrize("lanes", [0, 2, 4, 8, 16, 32])
+def test_spmv_hpcg_vs_oracle(ctx, lanes):
+    rp, col, val = matgen.hpcg(24, 20, 17)
+    x = np.random.default_rng(1).uniform(-1, 1, len(rp) - 1)
+    assert rel(run_spmv(ctx, rp, col, val, x, lanes), port.spmv(rp, col, val, x)) <= RED_TOL
+
+
+def test_spmv_ragged_empty_rows_and_64bit_rowptr(ctx):
+    rng = np.random.default_rng(2)
+    n = 5000
+    lens = rng.integers(0, 70, n)
+    lens[::7] = 0
+    lens[13] = 900                     # one very long row
+    rp = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    col = rng.integers(0, n, rp[-1]).astype(np.int32)
+    val = rng.uniform(-1, 1, rp[-1])
+    x = rng.uniform(-1, 1, n)
+    want = port.spmv(rp.astype(np.int32), col, val, x)
+    for r in (rp, rp.astype(np.int32)):
+        got = run_spmv(ctx, r, col, val, x)
+        assert rel(got, want) <= RED_TOL
+        assert np.all(got[lens == 0] == 0.0)
+    # empty matrix
+    A = ctx.upload_crs(i32(0), i32(), f64())
+    assert A.info()["n_rows"] == 0
+    A.free()
+
+
+@pytest.mark.parametrize("name", ["fdm2d16", "band_klein", "hpcg16"])
+def test_spmv_and_fused_forms_vs_reference_fixture(ctx, name):
+    g = golden(name)
+    rp, col, val = matgen.hpcg(16) if name == "hpcg16" else (g["rp"], g["col"], g["val"])
+    x, v = g["k__x"], g["k__v"]
+    n = x.size
+    assert rel(run_spmv(ctx, rp, col, val, x), g["k__spmv"]) <= RED_TOL
+    A = ctx.upload_crs(rp, col, val)
+    dx, dv, dy, dr = ctx.upload(x), ctx.upload(v), ctx.alloc(n), ctx.alloc(n)
+    y_ref = port.spmv(rp, col, val, x)
+    # spmv + dots
+    ctx.call("bis_spmv_dot", A.h, dx, dy, dv, 20, 21)
+    s = ctx.scalars(20, 2)
+    assert rel(ctx.download(dy, n), y_ref) <= RED_TOL
+    assert abs(s[0] - y_ref @ v) <= 1e-12 * np.linalg.norm(y_ref) * np.linalg.norm(v)
+    assert abs(s[1] - y_ref @ y_ref) <= 1e-12 * (y_ref @ y_ref)
+    # residual + squared norm (compute_residual, kernels.hpp:155-162)
+    ctx.call("bis_spmv_residual", A.h, dx, dv, dr, dy, 22)
+    r_ref = v - y_ref
+    assert rel(ctx.download(dr, n), r_ref) <= RED_TOL * 10
+    assert abs(ctx.scalars(22)[0] - r_ref @ r_ref) <= 1e-12 * (r_ref @ r_ref)
+    ctx.call("bis_compute_residual", A.h, dx, dv, dr, dy)
+    assert rel(ctx.download(dr, n), r_ref) <= RED_TOL * 10
+    # Jacobi sweep == spmv then normalize_x (jacobi.hpp:27-52); fused and unfused agree bit for bit
+    f = port.factor(rp, col, val, "sgs")
+    dD, dxn = ctx.upload(f.A_D), ctx.alloc(n)
+    ctx.call("bis_spmv_jacobi", A.h, dD, dv, dx, dxn)
+    fused = ctx.download(dxn, n)
+    ctx.call("bis_spmv", A.h, dx, dxn)
+    ctx.call("bis_normalize_x", dxn, dx, dD, dv, n)
+    assert np.array_equal(fused, ctx.download(dxn, n))
+    assert rel(fused, g["k__normalize_x"]) <= 1e-12
+    # b - T x on a strictly triangular factor (gauss_seidel.hpp:30-34)
+    U = ctx.upload_triangular(f.u_rp, f.u_col, f.u_val, upper=True)
+    ctx.call("bis_spmv_sub", U.h, dx, dv, dr)
+    assert rel(ctx.download(dr, n), v - port.spmv(f.u_rp, f.u_col, f.u_val, x)) <= RED_TOL * 10
+    U.free(), A.free()
+
+
+# ---- triangular solves and preconditioners: bit-exact ------------------------------------------
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", ["fdm2d16", "band_klein", "hpcg16"])
+def test_triangular_solves_bit_exact(ctx, name, variant):
+    g = golden(name)
+    rp, col, val = matgen.hpcg(16) if name == "hpcg16" else (g["rp"], g["col"], g["val"])
+    x = g["k__x"]
+    n = x.size
+    f = port.factor(rp, col, val, "sgs")
+    fi = port.factor(rp, col, val, "ilu0")
+    ctx.set_option("trsv_variant", variant)
+    try:
+        L = ctx.upload_triangular(f.l_rp, f.l_col, f.l_val, upper=False)
+        U = ctx.upload_triangular(f.u_rp, f.u_col, f.u_val, upper=True)
+        dD, db, dx = ctx.upload(f.A_D), ctx.upload(x), ctx.alloc(n)
+        ctx.call("bis_sptrsv", L.h, dx, dD, db)
+        assert np.array_equal(ctx.download(dx, n), g["k__sptrsv"])
+        ctx.call("bis_bsptrsv", U.h, dx, dD, db)
+        assert np.array_equal(ctx.download(dx, n), g["k__bsptrsv"])
+        # in place: x aliases b (gmres.hpp:288-291, bicgstab.hpp:157-160)
+        ctx.call("bis_copy_vector", dx, db, n)
+        ctx.call("bis_sptrsv", L.h, dx, dD, dx)
+        assert np.array_equal(ctx.download(dx, n), g["k__sptrsv_inplace"])
+        dAi, dLD, dUD = ctx.upload(f.A_D_inv), ctx.upload(np.ones(n)), ctx.upload(np.ones(n))
+        dtmp, dwork, dout = ctx.alloc(n), ctx.alloc(n), ctx.alloc(n)
+        for pre in ("none", "j", "gs", "bgs", "sgs"):
+            ctx.call("bis_apply_preconditioner", capi.PRECOND[pre], n, L.h, U.h, dD, dAi, dLD, dUD,
+                     dout, db, dtmp, dwork)
+            assert np.array_equal(ctx.download(dout, n), g["k__precond__" + pre]), pre
+        # in-place application (gmres.hpp:173-176)
+        ctx.call("bis_copy_vector", dout, db, n)
+        ctx.call("bis_apply_preconditioner", capi.PRECOND["sgs"], n, L.h, U.h, dD, dAi, dLD, dUD,
+                 dout, dout, dtmp, dwork)
+        assert np.array_equal(ctx.download(dout, n), g["k__precond__sgs"])
+        # two-stage GS with PRECOND_INNER_ITERS = 0 (kernels.hpp:375-385) against the oracle
+        for pre in ("2st", "s2st"):
+            ctx.call("bis_apply_preconditioner", capi.PRECOND[pre], n, L.h, U.h, dD, dAi, dLD, dUD,
+                     dout, db, dtmp, dwork)
+            assert np.array_equal(ctx.download(dout, n), port.apply_preconditioner(pre, f, x)), pre
+        L.free(), U.free()
+        # ILU(0): L_D == 1, U_D from the factorisation
+        L = ctx.upload_triangular(fi.l_rp, fi.l_col, fi.l_val, upper=False)
+        U = ctx.upload_triangular(fi.u_rp, fi.u_col, fi.u_val, upper=True)
+        ctx.upload(fi.L_D, dLD), ctx.upload(fi.U_D, dUD)
+        ctx.call("bis_apply_preconditioner", capi.PRECOND["ilu0"], n, L.h, U.h, dD, dAi, dLD, dUD,
+                 dout, db, dtmp, dwork)
+        assert np.array_equal(ctx.download(dout, n), g["k__precond__ilu0"])
+        L.free(), U.free()
+    finally:
+        ctx.set_option("trsv_variant", 0)
+    ctx.sync()
+
+
+def test_triangular_solve_long_rows_and_many_levels(ctx):
+    """Rows longer than the register prefetch window, a pure chain (n levels) and a diagonal
+    matrix (one level): the schedule never changes the bits."""
+    rng = np.random.default_rng(4)
+    n = 3000
+    cols, rp = [], [0]
+    for r in range(n):
+        k = min(r, int(rng.integers(0, 40)))
+        c = np.sort(rng.choice(r, k, replace=False)) if k else np.zeros(0, int)
+        if r > 0 and r % 3 == 0 and (r - 1) not in c:
+            c = np.sort(np.append(c, r - 1))       # long dependency chains
+        cols.append(c)
+        rp.append(rp[-1] + len(c))
+    col = np.concatenate(cols).astype(np.int32)
+    rp = np.array(rp, np.int32)
+    val = rng.uniform(-0.05, 0.05, col.size)
+    D = rng.uniform(1, 2, n)
+    b = rng.uniform(-1, 1, n)
+    L = ctx.upload_triangular(rp, col, val, upper=False)
+    assert L.info()["n_levels"] > 100
+    dD, db, dx = ctx.upload(D), ctx.upload(b), ctx.alloc(n)
+    ctx.call("bis_sptrsv", L.h, dx, dD, db)
+    assert np.array_equal(ctx.download(dx, n), port.sptrsv(rp, col, val, D, b))
+    L.free()
+    # mirrored into an upper factor
+    dense_rows = np.repeat(np.arange(n), np.diff(rp))
+    order = np.lexsort((dense_rows, col))          # transpose: sort by (col, row)
+    urp = np.zeros(n + 1, np.int32)
+    np.add.at(urp, col + 1, 1)
+    urp = np.cumsum(urp).astype(np.int32)
+    ucol, uval = dense_rows[order].astype(np.int32), val[order]
+    U = ctx.upload_triangular(urp, ucol, uval, upper=True)
+    ctx.call("bis_bsptrsv", U.h, dx, dD, db)
+    assert np.array_equal(ctx.download(dx, n), port.sptrsv(urp, ucol, uval, D, b, backward=True))
+    U.free()
+    # chain: n levels of one row
+    m = 2000
+    crp = np.arange(0, m, dtype=np.int32)
+    crp = np.concatenate([[0], crp]).astype(np.int32)
+    ccol = np.arange(0, m - 1, dtype=np.int32)
+    cval = np.full(m - 1, -0.5)
+    C = ctx.upload_triangular(crp, ccol, cval, upper=False)
+    assert C.info()["n_levels"] == m
+    dD2, db2, dx2 = ctx.upload(np.full(m, 1.5)), ctx.upload(np.ones(m)), ctx.alloc(m)
+    ctx.call("bis_sptrsv", C.h, dx2, dD2, db2)
+    assert np.array_equal(ctx.download(dx2, m), port.sptrsv(crp, ccol, cval, np.full(m, 1.5), np.ones(m)))
+    C.free()
+    # diagonal only: empty strict factor
+    E = ctx.upload_triangular(np.zeros(m + 1, np.int32), i32(), f64(), upper=False)
+    ctx.call("bis_sptrsv", E.h, dx2, dD2, db2)
+    assert np.array_equal(ctx.download(dx2, m), np.ones(m) / 1.5)
+    E.free()
+    # entries on the wrong side of the diagonal are rejected at upload
+    with pytest.raises(capi.BisError):
+        ctx.upload_triangular(i32(0, 1, 1), i32(1), f64(1.0), upper=False)
+    ctx.sync()
+
+
+# ---- BLAS-1 and fused vector kernels -----------------------------------------------------
+def test_axpby_family_bit_exact_with_aliasing(ctx):
+    g = golden("hpcg16")
+    x, v = g["k__x"], g["k__v"]
+    n = x.size
+    dx, dv, out = ctx.upload(x), ctx.upload(v + 2.0), ctx.alloc(n)
+    for fn in ("subtract_vectors", "sum_vectors", "elemwise_mult_vectors", "elemwise_div_vectors"):
+        ctx.call("bis_" + fn, out, dx, dv, n, 0.37)
+        assert np.array_equal(ctx.download(out, n), g["k__" + fn]), fn
+        # out aliases a, then out aliases b (gauss_seidel.hpp:34, gmres.hpp:25, kernels.hpp:369)
+        ctx.call("bis_copy_vector", out, dx, n)
+        ctx.call("bis_" + fn, out, out, dv, n, 0.37)
+        assert np.array_equal(ctx.download(out, n), g["k__" + fn]), fn + " out=a"
+        ctx.call("bis_copy_vector", out, dv, n)
+        ctx.call("bis_" + fn, out, dx, out, n, 0.37)
+        assert np.array_equal(ctx.download(out, n), g["k__" + fn]), fn + " out=b"
+    ctx.call("bis_scale", out, dx, -1.25, n)
+    assert np.array_equal(ctx.download(out, n), g["k__scale"])
+    dvv = ctx.upload(v)
+    assert abs(ctx.dot(dx, dvv, n) - g["k__dot"][0]) <= RED_TOL * np.sqrt(n)
+    assert abs(ctx.norm(dx, n) - g["k__norm"][0]) <= RED_TOL * g["k__norm"][0]
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, 4097, 1 << 20, (1 << 22) + 3])
+def test_reductions_deterministic_and_accurate(ctx, n):
+    rng = np.random.default_rng(n)
+    a, b = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    da, db = ctx.upload(a), ctx.upload(b)
+    d1, d2 = ctx.dot(da, db, n), ctx.dot(da, db, n)
+    assert d1 == d2                                   # fixed launch shape => bit-reproducible
+    exact = float(np.sum(a.astype(np.longdouble) * b.astype(np.longdouble)))
+    assert abs(d1 - exact) <= 1e-13 * np.sqrt(n) + 1e-15 * n ** 0.5
+    nv = ctx.norm(da, n)
+    assert abs(nv - np.linalg.norm(a)) <= 1e-13 * nv
+    ctx.free(da), ctx.free(db)
+
+
+def test_cg_fused_kernels_match_unfused_sequence(ctx):
+    """bis_cg_update / bis_cg_direction against the reference's sequence of separate kernels
+    (cg.hpp:19-52) run through the same C-ABI: identical per-element arithmetic => identical bits
+    for the vectors; the fused reductions agree with separate dots to rounding."""
+    rng = np.random.default_rng(9)
+    n = 100003
+    h = {k: rng.uniform(-1, 1, n) for k in ("x", "p", "r", "Ap")}
+    D = rng.uniform(1, 2, n)
+    d = {k: ctx.upload(v) for k, v in h.items()}
+    dD = ctx.upload(D)
+    xn, rn, zn, pn, t = (ctx.alloc(n) for _ in range(5))
+    rz, pAp = 0.731, 1.93
+    alpha = rz / pAp
+    for pre in ("none", "j", "sgs"):
+        ctx.call("bis_scalar_set", 2, rz)
+        ctx.call("bis_scalar_set", 3, pAp)
+        ctx.call("bis_cg_update", capi.PRECOND[pre], n, xn, d["x"], d["p"], rn, d["r"], d["Ap"], zn, dD,
+                 2, 3, 0, 1)
+        got_x, got_r = ctx.download(xn, n), ctx.download(rn, n)
+        ctx.call("bis_sum_vectors", t, d["x"], d["p"], n, alpha)
+        assert np.array_equal(got_x, ctx.download(t, n))
+        ctx.call("bis_subtract_vectors", t, d["r"], d["Ap"], n, alpha)
+        want_r = ctx.download(t, n)
+        assert np.array_equal(got_r, want_r)
+        s = ctx.scalars(0, 2)
+        assert abs(s[0] - want_r @ want_r) <= 1e-12 * (want_r @ want_r)
+        if pre == "none":
+            assert np.array_equal(ctx.download(zn, n), want_r) and s[1] == s[0]
+        if pre == "j":
+            ctx.call("bis_elemwise_div_vectors", t, rn, dD, n, 1.0)
+            want_z = ctx.download(t, n)
+            assert np.array_equal(ctx.download(zn, n), want_z)
+            assert abs(s[1] - want_r @ want_z) <= 1e-12 * abs(want_r @ want_z)
+    ctx.call("bis_scalar_set", 1, 0.9)
+    ctx.call("bis_scalar_set", 2, 0.4)
+    ctx.call("bis_cg_direction", n, pn, zn, d["p"], 1, 2)
+    ctx.call("bis_sum_vectors", t, zn, d["p"], n, 0.9 / 0.4)
+    assert np.array_equal(ctx.download(pn, n), ctx.download(t, n))
+
+
+def test_bicgstab_and_gmres_fused_kernels(ctx):
+    rng = np.random.default_rng(10)
+    n = 50021
+    names = ("x", "y", "st", "s", "z", "r0", "r", "v", "p")
+    h = {k: rng.uniform(-1, 1, n) for k in names}
+    d = {k: ctx.upload(v) for k, v in h.items()}
+    D = rng.uniform(1, 2, n)
+    dD = ctx.upload(D)
+    o1, o2, o3, t = (ctx.alloc(n) for _ in range(4))
+    rho_old, r0v, zs, zz = 0.83, 1.7, 0.61, 2.3
+    for slot, v in ((9, rho_old), (4, r0v), (5, zs), (6, zz)):
+        ctx.call("bis_scalar_set", slot, v)
+    alpha, omega = rho_old / r0v, zs / zz
+    # s = r - alpha v ; s_tmp = s / D
+    ctx.call("bis_bicgstab_s", capi.PRECOND["j"], n, o1, o2, d["r"], d["v"], dD, 9, 4)
+    ctx.call("bis_subtract_vectors", t, d["r"], d["v"], n, alpha)
+    s_want = ctx.download(t, n)
+    assert np.array_equal(ctx.download(o1, n), s_want)
+    ctx.call("bis_elemwise_div_vectors", t, o1, dD, n, 1.0)
+    assert np.array_equal(ctx.download(o2, n), ctx.download(t, n))
+    # x_new = (x + alpha y) + omega s_tmp ; r_new = s - omega z ; (r0,r_new) ; (r_new,r_new)
+    ctx.call("bis_bicgstab_xr", n, o3, o1, d["x"], d["y"], d["st"], o2, d["s"], d["z"], d["r0"],
+             9, 4, 5, 6, 7, 8)
+    ctx.call("bis_sum_vectors", t, d["x"], d["y"], n, alpha)
+    assert np.array_equal(ctx.download(o3, n), ctx.download(t, n))
+    ctx.call("bis_sum_vectors", t, t, d["st"], n, omega)
+    assert np.array_equal(ctx.download(o1, n), ctx.download(t, n))
+    ctx.call("bis_subtract_vectors", t, d["s"], d["z"], n, omega)
+    r_new = ctx.download(t, n)
+    assert np.array_equal(ctx.download(o2, n), r_new)
+    s = ctx.scalars(7, 2)
+    assert abs(s[0] - h["r0"] @ r_new) <= 1e-12 * np.linalg.norm(r_new) * np.linalg.norm(h["r0"])
+    assert abs(s[1] - r_new @ r_new) <= 1e-12 * (r_new @ r_new)
+    # p_new = r_new + beta (p - omega v) ; y_next = p_new / D
+    rho_new = s[0]
+    beta = (rho_new / rho_old) * (alpha / omega)
+    ctx.call("bis_bicgstab_p", capi.PRECOND["j"], n, o3, o1, d["p"], d["v"], o2, t, dD, 7, 9, 4, 5, 6)
+    y_next = ctx.download(t, n)
+    ctx.call("bis_subtract_vectors", t, d["p"], d["v"], n, omega)
+    assert np.array_equal(ctx.download(o3, n), ctx.download(t, n))
+    ctx.call("bis_sum_vectors", t, o2, t, n, beta)
+    assert np.array_equal(ctx.download(o1, n), ctx.download(t, n))
+    ctx.call("bis_elemwise_div_vectors", t, o1, dD, n, 1.0)
+    assert np.array_equal(y_next, ctx.download(t, n))
+    # MGS step: w -= h v_j ; (w, v_next)
+    ctx.call("bis_scalar_set", 16, 0.37)
+    ctx.call("bis_copy_vector", o1, d["x"], n)
+    ctx.call("bis_mgs_step", n, o1, d["y"], d["z"], 16, 17)
+    ctx.call("bis_subtract_vectors", t, d["x"], d["y"], n, 0.37)
+    w = ctx.download(t, n)
+    assert np.array_equal(ctx.download(o1, n), w)
+    assert abs(ctx.scalars(17)[0] - w @ h["z"]) <= 1e-12 * np.linalg.norm(w) * np.linalg.norm(h["z"])
+    ctx.call("bis_mgs_step", n, o1, d["y"], None, 16, 11)
+    ctx.call("bis_subtract_vectors", t, t, d["y"], n, 0.37)
+    w = ctx.download(t, n)
+    assert abs(ctx.scalars(11)[0] - w @ w) <= 1e-12 * (w @ w)
+    # basis normalisation: out = w * (1 / sqrt(sumsq))  (gmres.hpp:36-45)
+    ctx.call("bis_scale_inv_norm", n, o2, o1, 11)
+    ctx.call("bis_scale", t, o1, 1.0 / np.sqrt(ctx.scalars(11)[0]), n)
+    assert np.array_equal(ctx.download(o2, n), ctx.download(t, n))
+    # get_explicit_x: x = x_old + sum_j V_j y_j, left to right (gmres.hpp:326-375)
+    k = 5
+    V = rng.uniform(-1, 1, (k + 1, n))
+    yv = rng.uniform(-1, 1, k)
+    dV = ctx.upload(V.ravel())
+    ctx.call("bis_gmres_update_x", n, k, dV, yv.ctypes.data, o1, d["x"], o2)
+    acc = np.zeros(n)
+    for j in range(k):
+        acc = acc + V[j] * yv[j]
+    assert np.array_equal(ctx.download(o2, n), acc)
+    assert np.array_equal(ctx.download(o1, n), h["x"] + acc)
+
+
+# ---- matrices: generators, diagonal, split -------------------------------------------------
+def test_device_generators_match_numpy(ctx):
+    for dims in ((16, 16, 16), (9, 7, 5), (1, 1, 1), (2, 1, 3), (33, 8, 4)):
+        A = ctx.generate_hpcg(*dims)
+        rp, col, val = A.download()
+        w = matgen.hpcg(*dims, index_dtype=np.int64)
+        assert np.array_equal(rp, w[0]) and np.array_equal(col, w[1]) and np.array_equal(val, w[2]), dims
+        assert A.info()["nnz"] == matgen.hpcg_nnz(*dims)
+        A.free()
+    for periodic in (False, True):
+        for dims in ((10, 8, 6), (3, 2, 1), (2, 2, 2)):
+            A = ctx.generate_anderson(*dims, ranpot=5.0, t=1.0, seed=42, periodic=periodic)
+            rp, col, val = A.download()
+            w = matgen.anderson(*dims, 5.0, 1.0, 42, periodic)
+            assert np.array_equal(rp, w[0]) and np.array_equal(col, w[1]) and np.array_equal(val, w[2])
+            A.free()
+
+
+def test_extract_diagonal_and_split(ctx):
+    rp, col, val = matgen.anderson(9, 8, 7, 5.0, 1.0, 3, True)
+    n = len(rp) - 1
+    A = ctx.upload_crs(rp.astype(np.int32), col, val)
+    f = port.factor(rp.astype(np.int32), col, val, "sgs")
+    dD, dDi = ctx.alloc(n), ctx.alloc(n)
+    ctx.call("bis_matrix_extract_diagonal", A.h, dD, dDi)
+    assert np.array_equal(ctx.download(dD, n), f.A_D)
+    assert np.array_equal(ctx.download(dDi, n), f.A_D_inv)
+    L, U = ctx.split_triangular(A)
+    lrp, lcol, lval = L.download()
+    urp, ucol, uval = U.download()
+    assert np.array_equal(lrp, f.l_rp) and np.array_equal(lcol, f.l_col) and np.array_equal(lval, f.l_val)
+    assert np.array_equal(urp, f.u_rp) and np.array_equal(ucol, f.u_col) and np.array_equal(uval, f.u_val)
+    L.free(), U.free(), A.free()
+    # a missing diagonal is fatal in the reference (common.hpp:393-396)
+    B = ctx.upload_crs(i32(0, 1, 2), i32(1, 0), f64(1, 1))
+    with pytest.raises(capi.BisError):
+        ctx.call("bis_matrix_extract_diagonal", B.h, dD, None)
+    B.free()
+
+
+def test_hpcg_levels_follow_wavefront(ctx):
+    # HPCG natural ordering: level(x,y,z) = x + 2y + 4z  =>  7n - 6 levels
+    n = 12
+    A = ctx.generate_hpcg(n)
+    L, U = ctx.split_triangular(A)
+    assert L.info()["n_levels"] == 7 * n - 6 and U.info()["n_levels"] == 7 * n - 6
+    L.free(), U.free(), A.free()
+
+
+def test_bad_arguments_fail_loudly(ctx):
+    with pytest.raises(capi.BisError):
+        ctx.call("bis_dot_to_slot", None, None, 4, 4096)
+    with pytest.raises(capi.BisError):
+        ctx.upload_crs(i32(0, 2, 1), i32(0, 0), f64(1, 1))     # row_ptr not monotone / != nnz
+    with pytest.raises(capi.BisError):
+        ctx.set_option("no_such_option", 1)

@@ -1,0 +1,157 @@
+"""GPU parity tests, solver level: whole solves through the C++ host stack
+(host/solver_harness.hpp, host/methods/*.hpp) and the C-ABI, compared with
+
+ - the fixtures produced by the compiled, unmodified reference (tests/golden/*.npz), and
+ - the oracle (oracle/port) run here on the same seeded inputs.
+
+The bar is north_star's: iteration counts identical and max_k |r_k - r_k^ref| <= 1e-10 * ||r0||
+(fp64).  The reference's own tests only pin 3x3 solutions to 1e-7 (tests/test_solvers.cpp);
+those are reproduced through the device path as well.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import matgen, port
+
+from basic_iterative_solvers_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+HIST_TOL = 1e-10
+
+UNSTABLE = {("fdm2d16", "cg__gs"), ("band_klein", "cg__gs"), ("hpcg16", "cg__gs"),
+            ("anderson_12_10_8", "gm__ilu0"), ("anderson_12_10_8", "gm__j"),
+            ("anderson_12_10_8", "bi__ilu0")}
+
+
+def i32(*a):
+    return np.array(a, np.int32)
+
+
+def f64(*a):
+    return np.array(a, np.float64)
+
+
+def check(got, want_hist, its, conv, restarts, final, unstable=False):
+    r0 = want_hist[0]
+    if unstable:
+        k = min(4, want_hist.size, got.history.size)
+        assert np.max(np.abs(got.history[:k] - want_hist[:k]) / np.maximum(np.abs(want_hist[:k]), r0)) <= 1e-9
+        return
+    assert got.iter_count == its, (got.iter_count, its)
+    assert got.converged == bool(conv) and got.restarts == restarts
+    assert got.history.size == want_hist.size
+    err = np.max(np.abs(got.history - want_hist)) / r0
+    assert err <= HIST_TOL, err
+    assert abs(got.final_true_residual - final) <= HIST_TOL * r0
+
+
+def _matrix(name, g):
+    if name == "hpcg16":
+        return matgen.hpcg(16)
+    if name == "hpcg32":
+        return matgen.hpcg(32)
+    return g["rp"], g["col"], g["val"]
+
+
+def _keys(g):
+    return sorted(k[:-len("__history")] for k in g.files if k.endswith("__history"))
+
+
+CASES = [(n, k) for n in ("fdm2d16", "band_klein", "hpcg16", "hpcg32", "anderson_12_10_8", "anderson_dd_12_10_8")
+         for k in _keys(golden(n))]
+
+
+@pytest.mark.parametrize("name,key", CASES)
+def test_solve_matches_reference_fixture(ctx, name, key):
+    g = golden(name)
+    rp, col, val = _matrix(name, g)
+    method, pre = key.split("__")
+    got = host.solve(ctx, method, pre, crs=(rp, col, val))
+    its, conv, restarts = (int(v) for v in g[key + "__meta"])
+    check(got, g[key + "__history"], its, conv, restarts, g[key + "__final"][0], (name, key) in UNSTABLE)
+    if (name, key) not in UNSTABLE and conv:
+        x_ref = g[key + "__x"]
+        assert np.max(np.abs(got.x_star - x_ref)) <= 1e-9 * max(np.max(np.abs(x_ref)), 1.0)
+    assert got.launches > 0
+
+
+@pytest.mark.parametrize("method,pre", [("cg", "none"), ("cg", "j"), ("bi", "none"), ("bi", "j"),
+                                        ("j", "none"), ("gs", "none"), ("sgs", "none"), ("gm", "none"),
+                                        ("gm", "j")])
+def test_reference_3x3_solves(ctx, method, pre):
+    # tests/test_solvers.cpp:49-91,158-192 (GMRES is disabled there, :187-189; it passes here)
+    rp, col, val = i32(0, 2, 5, 7), i32(0, 1, 0, 1, 2, 1, 2), f64(2, -1, -1, 2, -1, -1, 2)
+    r = host.solve(ctx, method, pre, crs=(rp, col, val), b=f64(0, 0, 4), x0=f64(0, 0, 0))
+    assert r.converged and np.max(np.abs(r.x_star - f64(1, 2, 3))) <= 1e-7
+
+
+def test_reference_3x3_bicgstab_jacobi_diag10(ctx):
+    # tests/test_solvers.cpp:93-141
+    rp, col, val = i32(0, 2, 5, 7), i32(0, 1, 0, 1, 2, 1, 2), f64(10, -1, -1, 10, -1, -1, 10)
+    xt = f64(1, 2, 3)
+    r = host.solve(ctx, "bi", "j", crs=(rp, col, val), b=port.spmv(rp, col, val, xt), x0=f64(0, 0, 0))
+    assert r.converged and np.max(np.abs(r.x_star - xt)) <= 1e-7
+
+
+@pytest.mark.parametrize("method,pre,restart", [("cg", "sgs", 10), ("bi", "j", 10), ("cg", "none", 10),
+                                                ("gm", "ilu0", 10), ("gm", "sgs", 25), ("bi", "ilu0", 10),
+                                                ("cg", "2st", 10), ("gm", "s2st", 10)])
+def test_solve_matches_oracle_hpcg_nonuniform(ctx, method, pre, restart):
+    """Seeded inputs, non-cubic grid, random rhs / initial guess: GPU vs oracle run here."""
+    rp, col, val = matgen.hpcg(20, 14, 11)
+    rng = np.random.default_rng(21)
+    n = len(rp) - 1
+    b, x0 = rng.uniform(0.5, 1.5, n), rng.uniform(-0.1, 0.1, n)
+    want = port.solve(rp, col, val, method, pre, restart_len=restart, b=b, x0=x0)
+    got = host.solve(ctx, method, pre, crs=(rp, col, val), restart_len=restart, b=b, x0=x0)
+    check(got, want.history, want.iter_count, want.converged, want.restarts, want.final_true_residual)
+
+
+def test_stationary_sweeps_match_oracle(ctx):
+    rp, col, val = matgen.hpcg(12)
+    for method in ("j", "gs", "sgs"):
+        want = port.solve(rp, col, val, method, "none")
+        got = host.solve(ctx, method, "none", crs=(rp, col, val))
+        check(got, want.history, want.iter_count, want.converged, want.restarts, want.final_true_residual)
+
+
+def test_device_generated_matrix_equals_uploaded(ctx):
+    """`HPCG-<n>` names are generated on the device for methods that need no factors; the
+    history must be bit-identical to the same solve on the uploaded host CRS."""
+    rp, col, val = matgen.hpcg(24)
+    for method, pre in (("cg", "none"), ("bi", "j"), ("j", "none")):
+        a = host.solve(ctx, method, pre, crs=(rp, col, val), max_iters=60)
+        b = host.solve(ctx, method, pre, matrix_name="HPCG-24", max_iters=60, want_x=False)
+        assert a.iter_count == b.iter_count and np.array_equal(a.history, b.history)
+
+
+def test_run_to_run_determinism(ctx):
+    rp, col, val = matgen.hpcg(20)
+    for method, pre in (("cg", "sgs"), ("gm", "ilu0"), ("bi", "j")):
+        a = host.solve(ctx, method, pre, crs=(rp, col, val))
+        b = host.solve(ctx, method, pre, crs=(rp, col, val))
+        assert np.array_equal(a.history, b.history) and np.array_equal(a.x_star, b.x_star)
+
+
+def test_size_independent_properties_at_scale(ctx):
+    """HPCG-128 (BASELINE config 1/2 size), no oracle run: (a) the final TRUE residual of the
+    returned x_star, recomputed by the harness, is below the stopping threshold region;
+    (b) CG on an SPD matrix: the recurrence residual tracks the true residual;
+    (c) the published reference numbers for this size."""
+    r = host.solve(ctx, "cg", "none", matrix_name="HPCG-128", want_x=False)
+    assert abs(r.history[0] - 1.4148190838408811e+03) <= 1e-10 * r.history[0]
+    assert abs(r.history[1] - 9.4222420031314541e+03) <= 1e-10 * r.history[0]
+    assert abs(r.history[100] - 4.1442144142479105e+00) <= 1e-10 * r.history[0]
+    assert r.converged and abs(r.iter_count - 289) <= 1      # reference: 289 (8 threads), F7: +-1
+    res3 = int(np.argmax(r.history / r.history[0] < 1e-3))
+    res6 = int(np.argmax(r.history / r.history[0] < 1e-6))
+    assert (res3, res6) == (107, 150)
+    assert r.final_true_residual <= 50 * r.stopping_criteria
+    b = host.solve(ctx, "bi", "j", matrix_name="HPCG-128", want_x=False)
+    assert abs(b.history[1] - 2.4190103171406172e+03) <= 1e-10 * b.history[0]
+    assert b.converged and abs(b.iter_count - 189) <= 1
+    j = host.solve(ctx, "j", "none", matrix_name="HPCG-128", want_x=False)
+    assert not j.converged and j.iter_count == 1000
+    assert abs(j.history[1000] - 5.8007937268987325e+02) <= 1e-10 * j.history[0]
