@@ -43,6 +43,8 @@ _SIGS = {
     "bis_timer_start": ([c_ctx], cint),
     "bis_timer_stop": ([c_ctx, C.POINTER(dbl)], cint),
     "bis_flush_l2": ([c_ctx], cint),
+    "bis_profile_enable": ([c_ctx, cint], cint),
+    "bis_profile_read": ([c_ctx, C.c_char_p, C.POINTER(dbl), C.POINTER(i64)], cint),
     "bis_context_set_option": ([c_ctx, C.c_char_p, cint], cint),
     "bis_vector_alloc": ([c_ctx, i64, C.POINTER(c_dev)], cint),
     "bis_vector_free": ([c_ctx, c_dev], cint),
@@ -312,6 +314,14 @@ class Context:
         return r.value
 
     # timing ------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self.call("bis_profile_enable", int(on))
+
+    def profile_read(self, family: str):
+        ms, cnt = dbl(), i64()
+        self.call("bis_profile_read", family.encode(), C.byref(ms), C.byref(cnt))
+        return ms.value, int(cnt.value)
+
     def timer_start(self):
         self.call("bis_timer_start")
 

@@ -43,8 +43,10 @@ int launch_ew2(bis_context *c, int64_t n, P prep, F f, int slot_a = -1, int slot
     int blocks = bis_blocks_for(n, EW_THREADS * EW_UNROLL, cap);
     RedArgs ra = bis_red_args(c, slot_a, slot_b);
     ra.total_blocks = blocks;
+    BIS_CHECK(bis_prof_begin(c, BIS_PROF_VECTOR));
     ew_kernel<NRED, P, F><<<blocks, EW_THREADS, 0, c->stream>>>(n, prep, f, ra);
     BIS_LAUNCH_CHECK(c);
+    BIS_CHECK(bis_prof_end(c, BIS_PROF_VECTOR));
     if (NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));
     return 0;
 }

@@ -127,6 +127,8 @@ extern "C" int bis_context_destroy(bis_context *c) {
     cudaFree(c->d_counter);
     cudaFree(c->d_errflag);
     cudaFree(c->d_flush);
+    for (int i = 0; i < BIS_PROF_NTAGS; ++i)
+        for (cudaEvent_t e : c->prof[i].ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_timer0);
     cudaEventDestroy(c->ev_timer1);
     cudaEventDestroy(c->ev_main);
@@ -185,6 +187,65 @@ extern "C" int bis_timer_stop(bis_context *c, double *elapsed_ms) {
     float ms = 0.f;
     BIS_CUDA(cudaEventElapsedTime(&ms, c->ev_timer0, c->ev_timer1));
     *elapsed_ms = (double)ms;
+    return 0;
+}
+
+// ---- per-family kernel timing ---------------------------------------------------
+static int prof_flush(bis_context *c, ProfTag &t) {
+    if (t.used == 0) return 0;
+    BIS_CUDA(cudaEventSynchronize(t.ev[t.used - 1]));
+    for (size_t i = 0; i + 1 < t.used; i += 2) {
+        float ms = 0.f;
+        BIS_CUDA(cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]));
+        t.acc_ms += (double)ms;
+        t.count++;
+    }
+    t.used = 0;
+    (void)c;
+    return 0;
+}
+
+int bis_prof_begin(bis_context *c, int tag) {
+    if (!c->profile) return 0;
+    ProfTag &t = c->prof[tag];
+    if (t.used >= 16384) BIS_CHECK(prof_flush(c, t));   // bounded pool; a flush waits for the stream
+    while (t.ev.size() < t.used + 2) {
+        cudaEvent_t e;
+        BIS_CUDA(cudaEventCreate(&e));
+        t.ev.push_back(e);
+    }
+    BIS_CUDA(cudaEventRecord(t.ev[t.used], c->stream));
+    return 0;
+}
+
+int bis_prof_end(bis_context *c, int tag) {
+    if (!c->profile) return 0;
+    ProfTag &t = c->prof[tag];
+    BIS_CUDA(cudaEventRecord(t.ev[t.used + 1], c->stream));
+    t.used += 2;
+    return 0;
+}
+
+extern "C" int bis_profile_enable(bis_context *c, int on) {
+    BIS_REQUIRE(c, "null context");
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < BIS_PROF_NTAGS; ++i) {
+        BIS_CHECK(prof_flush(c, c->prof[i]));
+        c->prof[i].acc_ms = 0.0;
+        c->prof[i].count = 0;
+    }
+    c->profile = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int bis_profile_read(bis_context *c, const char *family, double *total_ms, int64_t *launches) {
+    BIS_REQUIRE(c && family && total_ms && launches, "null argument");
+    std::string f(family);
+    int tag = f == "spmv" ? BIS_PROF_SPMV : f == "sptrsv" ? BIS_PROF_SPTRSV : f == "vector" ? BIS_PROF_VECTOR : -1;
+    BIS_REQUIRE(tag >= 0, "bis_profile_read: unknown kernel family '%s' (spmv, sptrsv, vector)", family);
+    BIS_CHECK(prof_flush(c, c->prof[tag]));
+    *total_ms = c->prof[tag].acc_ms;
+    *launches = c->prof[tag].count;
     return 0;
 }
 

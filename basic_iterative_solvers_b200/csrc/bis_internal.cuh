@@ -79,6 +79,16 @@ struct RedArgs {
     int finalize;            // 0: only write partials (a later launch finalises)
 };
 
+// Optional per-kernel-family device timing (bis_profile_enable): cudaEvent pairs
+// recorded on the launching stream around every launch of the family.
+enum { BIS_PROF_SPMV = 0, BIS_PROF_SPTRSV = 1, BIS_PROF_VECTOR = 2, BIS_PROF_NTAGS = 3 };
+struct ProfTag {
+    std::vector<cudaEvent_t> ev;   // pairs: [2i] start, [2i+1] stop
+    size_t used = 0;               // events recorded since the last flush
+    double acc_ms = 0.0;
+    int64_t count = 0;
+};
+
 struct bis_context {
     int device = 0;
     int rank = 0;
@@ -103,6 +113,8 @@ struct bis_context {
     int opt_spmv_variant = 0;
     int opt_spmv_lanes = 0;
     int opt_trsv_variant = 0;
+    int profile = 0;
+    ProfTag prof[BIS_PROF_NTAGS];
 };
 
 struct LevelSets {
@@ -160,6 +172,8 @@ int bis_matrix_finalize_distributed(bis_context *ctx, bis_matrix *A,
                                     int *d_col_global_in_place);
 int bis_build_levels_device(bis_context *ctx, bis_matrix *T);
 int bis_matrix_stats(bis_context *ctx, bis_matrix *A);
+int bis_prof_begin(bis_context *ctx, int tag);
+int bis_prof_end(bis_context *ctx, int tag);
 
 static inline int bis_blocks_for(int64_t n, int per_block, int cap) {
     int64_t b = (n + per_block - 1) / per_block;

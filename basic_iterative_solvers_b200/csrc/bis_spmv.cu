@@ -199,6 +199,7 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     in.ghost = A->halo.d_ghost;
     in.n_owned = A->n_cols;
     int nb = 0;
+    BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPMV));
     if (!A->distributed || A->halo.n_ghost == 0) {
         in.lo1 = 0; in.cnt1 = A->n_rows; in.lo2 = 0; in.cnt2 = 0;
         BIS_CHECK((launch_rp<false, Epi>(c, A, in, epi, ra, &nb)));
@@ -220,6 +221,7 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
         ra.block_offset = nb1;
         BIS_CHECK((launch_rp<true, Epi>(c, A, in, epi, ra, &nb)));
     }
+    BIS_CHECK(bis_prof_end(c, BIS_PROF_SPMV));
     if (Epi::NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));
     return 0;
 }

@@ -155,6 +155,7 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.x = x;
     a.D = D;
     a.b = b;
+    BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPTRSV));
     if (c->opt_trsv_variant == 1) {
         const std::vector<int64_t> &ls = lv.level_start;
         for (int l = 0; l < lv.n_levels; ++l) {
@@ -163,14 +164,14 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
             sptrsv_one_level_kernel<<<blocks, TRSV_THREADS, 0, c->stream>>>(a, ls[l], ls[l + 1]);
             BIS_LAUNCH_CHECK(c);
         }
-        return 0;
+        return bis_prof_end(c, BIS_PROF_SPTRSV);
     }
     BIS_CUDA(cudaMemsetAsync(lv.d_level_done, 0, sizeof(unsigned int) * (size_t)lv.n_levels, c->stream));
     BIS_CUDA(cudaMemsetAsync(lv.d_ticket, 0, sizeof(unsigned int), c->stream));
     const int64_t blocks = (lv.n_slots + TRSV_THREADS - 1) / TRSV_THREADS;
     sptrsv_level_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a);
     BIS_LAUNCH_CHECK(c);
-    return 0;
+    return bis_prof_end(c, BIS_PROF_SPTRSV);
 }
 
 extern "C" int bis_sptrsv(bis_context *c, const bis_matrix *L, double *x, const double *D,

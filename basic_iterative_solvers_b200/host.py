@@ -46,6 +46,13 @@ def load() -> C.CDLL:
     lib.bis_host_gmres_update_g.restype = C.c_double
     lib.bis_host_solve.argtypes = ([C.c_void_p, C.c_char_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 3 +
                                    [C.c_void_p] * 2 + [C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 5)
+    lib.bis_host_bench_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.bis_host_bench_open.restype = C.c_void_p
+    lib.bis_host_bench_close.argtypes = [C.c_void_p]
+    lib.bis_host_bench_close.restype = None
+    lib.bis_host_bench_e2e.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    lib.bis_host_bench_prepare.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.bis_host_bench_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     _lib = lib
     return lib
 
@@ -184,3 +191,45 @@ def solve(ctx: capi.Context, method: str, precond: str = "none", *, crs=None, ma
     return SolveResult(hist[:cnt].copy(), float(od[1]), int(oi[0]), bool(oi[2]), int(oi[3]),
                        float(od[0]), xs, itime[1:cnt + 1].copy(), float(od[2]), float(od[3]),
                        float(od[4]), int(oi[4]))
+
+
+class BenchSession:
+    """Measurement session of bench.py (host/host_capi.cpp, "measurement sessions")."""
+
+    def __init__(self, ctx: capi.Context, matrix_name: str, method: str, precond: str = "none",
+                 restart_len: int = 10):
+        self.lib = load()
+        self.h = self.lib.bis_host_bench_open(ctx.h, matrix_name.encode(), METHOD[method], PRECOND[precond],
+                                              restart_len)
+        if not self.h:
+            raise capi.BisError(_err())
+
+    @staticmethod
+    def _info(arr):
+        return dict(zip(("n_rows", "n_rows_global", "nnz", "nnz_global", "rp_bytes"), (int(v) for v in arr[:5])))
+
+    def e2e(self, steps: int, b_ptr: int | None, x0_ptr: int | None, x_out_ptr: int | None):
+        out = (C.c_double * 8)()
+        info = (C.c_int64 * 8)()
+        if self.lib.bis_host_bench_e2e(self.h, steps, b_ptr, x0_ptr, x_out_ptr, out, info) != 0:
+            raise capi.BisError(_err())
+        return {"wall_ms": out[0], "iters": int(out[1]), "launches": int(out[2]), "res_last": out[3],
+                "res0": out[4], "res_true": out[5], **self._info(info)}
+
+    def prepare(self, warmup: int):
+        info = (C.c_int64 * 8)()
+        if self.lib.bis_host_bench_prepare(self.h, warmup, info) != 0:
+            raise capi.BisError(_err())
+        return self._info(info)
+
+    def run(self, steps: int):
+        out = (C.c_double * 8)()
+        if self.lib.bis_host_bench_run(self.h, steps, out) != 0:
+            raise capi.BisError(_err())
+        return {"device_ms": out[0], "wall_ms": out[1], "launches": int(out[2]), "res_last": out[3],
+                "res0": out[4]}
+
+    def close(self):
+        if self.h:
+            self.lib.bis_host_bench_close(self.h)
+            self.h = None

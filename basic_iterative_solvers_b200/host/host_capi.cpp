@@ -170,4 +170,158 @@ int bis_host_solve(bis_context *dev, const char *matrix_name, int n, const int *
     }
 }
 
+
+// ---- measurement sessions (bench.py) ----------------------------------------------
+// A session owns one Solver on one named matrix.  Two timed regions:
+//  * e2e: what a user of the host stack does -- host b / x0 arrays in,
+//    preprocessing() (allocate, upload, init_residual), solve() for exactly
+//    `steps` iterations (the harness reads the residual norm back every
+//    iteration), x_star downloaded to host memory.  Wall clock, device idle on
+//    both sides.  Matrix generation is outside (the matrix is the operator).
+//  * resident: state already in HBM; `warmup` untimed iterations of the
+//    harness loop body, then `steps` timed ones between two CUDA events on the
+//    context's stream.
+struct BenchSession {
+    Args args;
+    Timers timers;
+    std::unique_ptr<Solver> solver;
+    bis_context *dev = nullptr;
+};
+
+static void bench_make(BenchSession *s) {
+    s->solver = make_solver(&s->args, s->dev);
+}
+
+void *bis_host_bench_open(bis_context *dev, const char *matrix_name, int method, int precond,
+                          int restart_len) {
+    try {
+        auto s = std::make_unique<BenchSession>();
+        s->dev = dev;
+        s->args.matrix_file_name = matrix_name;
+        s->args.method = static_cast<SolverType>(method);
+        s->args.preconditioner = static_cast<PrecondType>(precond);
+        s->args.restart_length = restart_len;
+        s->args.quiet = true;
+        return s.release();
+    } catch (const std::exception &e) {
+        g_host_err = e.what();
+        return nullptr;
+    }
+}
+
+void bis_host_bench_close(void *h) { delete static_cast<BenchSession *>(h); }
+
+// info: [0] local rows, [1] global rows, [2] local nnz, [3] global nnz, [4] row_ptr bytes
+static void bench_fill_info(Solver *solver, int64_t *info) {
+    int64_t mi[8];
+    BIS_OK(bis_matrix_info(solver->dA->handle, mi));
+    info[0] = mi[0]; info[1] = mi[1]; info[2] = mi[2]; info[3] = mi[3]; info[4] = mi[4];
+}
+
+// out: [0] wall ms of the whole region, [1] iterations done, [2] kernel launches,
+//      [3] last residual norm, [4] ||r0||, [5] final true residual
+int bis_host_bench_e2e(void *h, int steps, const double *b_host, const double *x0_host,
+                       double *x_star_host, double *out, int64_t *info) {
+    auto *s = static_cast<BenchSession *>(h);
+    try {
+        if (steps < 1 || steps > MAX_ITERS) bis_fatal("bench: steps outside [1, MAX_ITERS]");
+        bench_make(s);
+        Solver *solver = s->solver.get();
+        solver->max_iters = steps;
+        solver->tolerance = 0.0;   // never stop early: exactly `steps` iterations
+        std::unique_ptr<MatrixCRS> A;
+        std::unique_ptr<DeviceCRS> dA;
+        obtain_matrix(&s->args, s->dev, solver->needs_triangular_factors(), A, dA);
+        BIS_OK(bis_context_synchronize(s->dev));
+        int64_t i0[8], i1[8];
+        BIS_OK(bis_context_info(s->dev, i0));
+        Stopwatch w;
+        w.start();
+        preprocessing(&s->args, solver, &s->timers, A, std::move(dA), b_host, x0_host);
+        solve(&s->args, solver, &s->timers);
+        if (x_star_host) BIS_OK(bis_vector_download(s->dev, x_star_host, solver->x_star, solver->N));
+        BIS_OK(bis_context_synchronize(s->dev));
+        out[0] = w.check() * 1e3;
+        BIS_OK(bis_context_info(s->dev, i1));
+        out[1] = solver->iter_count;
+        out[2] = (double)(i1[3] - i0[3]);
+        out[3] = solver->collected_residual_norms[solver->collected_residual_norms_count - 1];
+        out[4] = solver->collected_residual_norms[0];
+        out[5] = solver->residual_norm;
+        bench_fill_info(solver, info);
+        s->solver.reset();
+        return 0;
+    } catch (const std::exception &e) {
+        g_host_err = e.what();
+        s->solver.reset();
+        return 1;
+    }
+}
+
+// Untimed: build the solver, obtain the matrix, preprocessing, `warmup` iterations.
+int bis_host_bench_prepare(void *h, int warmup, int64_t *info) {
+    auto *s = static_cast<BenchSession *>(h);
+    try {
+        bench_make(s);
+        Solver *solver = s->solver.get();
+        solver->tolerance = 0.0;
+        std::unique_ptr<MatrixCRS> A;
+        std::unique_ptr<DeviceCRS> dA;
+        obtain_matrix(&s->args, s->dev, solver->needs_triangular_factors(), A, dA);
+        preprocessing(&s->args, solver, &s->timers, A, std::move(dA));
+        for (int i = 0; i < warmup; ++i) {
+            s->timers.per_iteration_time.start();
+            solver->iterate(&s->timers);
+            ++solver->iter_count;
+            solver->sample_residual(&s->timers.per_iteration_time);
+            solver->exchange();
+            solver->check_restart(&s->timers);
+        }
+        BIS_OK(bis_context_synchronize(s->dev));
+        bench_fill_info(solver, info);
+        return 0;
+    } catch (const std::exception &e) {
+        g_host_err = e.what();
+        s->solver.reset();
+        return 1;
+    }
+}
+
+// Timed: exactly `steps` iterations of the harness loop body (solver_harness.hpp:17-50).
+// out: [0] device ms (CUDA events on the context's stream), [1] wall ms, [2] kernel
+// launches, [3] residual norm after the last iteration, [4] ||r0||
+int bis_host_bench_run(void *h, int steps, double *out) {
+    auto *s = static_cast<BenchSession *>(h);
+    try {
+        Solver *solver = s->solver.get();
+        if (!solver) bis_fatal("bench: prepare first");
+        if (solver->iter_count + steps + 1 >= MAX_ITERS) bis_fatal("bench: warmup + steps exceed MAX_ITERS");
+        int64_t i0[8], i1[8];
+        BIS_OK(bis_context_info(s->dev, i0));
+        Stopwatch w;
+        w.start();
+        BIS_OK(bis_timer_start(s->dev));
+        for (int i = 0; i < steps; ++i) {
+            s->timers.per_iteration_time.start();
+            solver->iterate(&s->timers);
+            ++solver->iter_count;
+            solver->sample_residual(&s->timers.per_iteration_time);
+            solver->exchange();
+            solver->check_restart(&s->timers);
+        }
+        double ms = 0.0;
+        BIS_OK(bis_timer_stop(s->dev, &ms));
+        out[1] = w.check() * 1e3;
+        out[0] = ms;
+        BIS_OK(bis_context_info(s->dev, i1));
+        out[2] = (double)(i1[3] - i0[3]);
+        out[3] = solver->residual_norm;
+        out[4] = solver->collected_residual_norms[0];
+        return 0;
+    } catch (const std::exception &e) {
+        g_host_err = e.what();
+        return 1;
+    }
+}
+
 } // extern "C"

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: PCG time/iteration and SpMV HBM GB/s vs roofline on HPCG-512.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 512]
+
+A "step" is ONE iteration of the solver harness loop (solver_harness.hpp:17-50 of the
+reference: iterate, residual-norm sample read back by the host, pointer exchange) of
+Jacobi-preconditioned CG (`-cg -p j`) on the HPCG-n 27-point matrix (default n = 512:
+134 M rows, 3.6 G nonzeros, device-generated, 64-bit row_ptr), b = 1, x0 = 0.1.
+For N > 1 (launched by torchrun, one rank per GPU) the rows are partitioned into N z-slabs
+(strong scaling: the global problem is fixed); NCCL carries the halo planes and the dot-product
+allreduces.  `value` is milliseconds per iteration with all state resident in HBM (CUDA events,
+max over ranks); `e2e` is the same metric through the host stack from HOST buffers (b, x0 uploaded,
+x_star downloaded, residual norm read back every iteration); `roofline` is the SpMV kernel
+(the dominant kernel) against the measured HBM peak; `cpu_baseline` is the unmodified reference
+(oracle/_ref) timed on the host cores on a bounded sample.
+
+`--impl reference` times the reference's own CPU implementation of the same path (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pcg_time_per_iteration_hpcg"
+UNIT = "ms/iter"
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def slab_rows(n: int, nz_planes: int, plane: int, rank: int, nranks: int):
+    """Row block of `rank`: whole z-planes (csrc/bis_matrix.cu: slab())."""
+    if nz_planes >= nranks:
+        q, r = divmod(nz_planes, nranks)
+        b = rank * q + min(rank, r)
+        e = b + q + (1 if rank < r else 0)
+        return b * plane, e * plane
+    q, r = divmod(n, nranks)
+    b = rank * q + min(rank, r)
+    return b, b + q + (1 if rank < r else 0)
+
+
+# ---------------------------------------------------------------------------------------------
+def reference_leg(n_sample: int, iters: int, threads: int | None, n_target: int):
+    """The UNMODIFIED reference (oracle/_ref/libbis_ref.so: /root/reference compiled behind an
+    extern-C shim) running `-cg -p j` on HPCG-<n_sample> with all host threads, `iters`
+    iterations.  Returns ms/iter scaled to HPCG-<n_target> by the row ratio (every kernel on the
+    path is linear in the rows), plus the description."""
+    from oracle import refshim
+    from basic_iterative_solvers_b200 import host
+    if not refshim.available():
+        raise RuntimeError("oracle/_ref/libbis_ref.so is missing (built by __graft_entry__.build() where "
+                           "/root/reference exists)")
+    lib = refshim.load()
+    cores = threads or os.cpu_count() or 1
+    try:
+        cores = min(cores, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    lib.ref_omp_set_threads(int(cores))
+    rp, col, val = host.matrix(f"HPCG-{n_sample}")      # host generator: identical CRS to the device one
+    lib.ref_set_max_iters(int(iters))
+    t0 = time.time()
+    r = refshim.solve(rp, col, val, "cg", "j")
+    wall = time.time() - t0
+    lib.ref_set_max_iters(0)
+    its = max(r.iter_count, 1)
+    ms_iter = 1e3 * r.iterate_time / its                 # the reference's own "iterate" stopwatch
+    spmv_ms = 1e3 * r.spmv_time / its                    # its "SpMV time" timer / SpMV count
+    scale = (n_target / n_sample) ** 3
+    nnz = int(rp[-1])
+    nrow = rp.size - 1
+    spmv_bytes = 12 * nnz + 4 * (nrow + 1) + 16 * nrow
+    return {
+        "value": ms_iter * scale, "unit": UNIT, "cores": int(cores), "kind": "reference",
+        "sample": (f"HPCG-{n_sample} -cg -p j, {its} iterations of the reference's solve() at {cores} OpenMP "
+                   f"threads: {ms_iter:.2f} ms/iter measured (SpMV {spmv_ms:.2f} ms = "
+                   f"{spmv_bytes / spmv_ms / 1e6:.1f} GB/s), x{scale:.0f} row ratio to HPCG-{n_target}; "
+                   f"{wall:.1f} s of CPU work incl. its preprocessing"),
+        "measured_ms_per_iter": ms_iter, "spmv_ms": spmv_ms, "spmv_gbs": spmv_bytes / spmv_ms / 1e6,
+    }
+
+
+def pick_cpu_sample(n_target: int) -> int:
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 0
+    n = 256 if avail > 48 << 30 else 128
+    return min(n, n_target)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="HPCG grid edge (BASELINE: 512)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="HPCG edge of the CPU sample (0: auto)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+    n = args.n
+    workload = f"HPCG-{n} -cg -p j (27-point, {n**3} rows, {(3*n-2)**3} nnz, fp64 CRS, b=1, x0=0.1)"
+    config = {"workload": workload, "rows": n ** 3, "nnz": (3 * n - 2) ** 3,
+              "partition": f"{world} z-slab(s), NCCL halo + allreduce" if world > 1 else "single GPU",
+              "l2": "inputs larger than L2 (no flush): CRS alone is %.1f GB per GPU" %
+                    (12 * (3 * n - 2) ** 3 / world / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_s = args.cpu_sample or pick_cpu_sample(n)
+        vals = []
+        leg = None
+        for _ in range(1):   # one bounded solve: warm-up iterations are inside it (steps + warmup iterations)
+            leg = reference_leg(n_s, args.steps + args.warmup, None, n)
+            vals.append(leg["value"])
+        out = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["value"],
+               "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": config,
+               "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+               "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "spmv_gbs": leg["spmv_gbs"]}
+        print(json.dumps(out), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from basic_iterative_solvers_b200 import capi, host
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(capi.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = capi.Context(local_rank, rank, world, nccl_id)
+    K, W = args.steps, args.warmup
+    name = f"HPCG-{n}"
+    r_lo, r_hi = slab_rows(n ** 3, n, n * n, rank, world)
+    n_local = r_hi - r_lo
+
+    # ---- e2e: host buffers in, host buffer out (pinned), through the host stack -----------------
+    b_h = torch.full((n_local,), 1.0, dtype=torch.float64).pin_memory()
+    x0_h = torch.full((n_local,), 0.1, dtype=torch.float64).pin_memory()
+    xs_h = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    sess = host.BenchSession(ctx, name, "cg", "j")
+    sess.e2e(W, b_h.data_ptr(), x0_h.data_ptr(), xs_h.data_ptr())          # warm-up pass (allocators, NCCL)
+    barrier()
+    e = sess.e2e(K, b_h.data_ptr(), x0_h.data_ptr(), xs_h.data_ptr())
+    barrier()
+    e2e_ms = max_over_ranks(e["wall_ms"]) / K
+    assert e["iters"] == K and e["n_rows"] == n_local
+    e2e_check = float(xs_h[:4].sum())
+    sess.close()
+
+    # ---- resident: K timed iterations between CUDA events ------------------------------------------
+    sess = host.BenchSession(ctx, name, "cg", "j")
+    info = sess.prepare(W)
+    ctx.profile_enable(True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    r = sess.run(K)
+    barrier()
+    clk = clocks.stop()
+    dev_ms = max_over_ranks(r["device_ms"])
+    spmv_ms_total, spmv_cnt = ctx.profile_read("spmv")
+    vec_ms_total, vec_cnt = ctx.profile_read("vector")
+    ctx.profile_enable(False)
+    launches = r["launches"]
+    sess.close()
+    ms_iter = dev_ms / K
+    spmv_ms = spmv_ms_total / max(spmv_cnt, 1)
+    spmv_bytes = 12 * info["nnz"] + info["rp_bytes"] * (info["n_rows"] + 1) + 16 * info["n_rows"]
+    achieved = spmv_bytes / spmv_ms / 1e6            # GB/s, this rank's SpMV (per GPU)
+    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except (OSError, KeyError, ValueError):
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
+            t = json.load(f)
+            if t.get("workload_n") == n and world == 1:
+                traffic = t["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
+
+    # ---- BiCGSTAB + Jacobi on the same matrix (BASELINE configs[4]) ---------------------------
+    sess = host.BenchSession(ctx, name, "bi", "j")
+    sess.prepare(W)
+    barrier()
+    rb = sess.run(K)
+    barrier()
+    bi_ms = max_over_ranks(rb["device_ms"]) / K
+    sess.close()
+
+    out = {
+        "metric": METRIC, "value": ms_iter, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_iter, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_ms, "unit": UNIT,
+                "h2d_bytes_per_step": 16 * n_local / K, "d2h_bytes_per_step": 8 * n_local / K + 8,
+                "note": "preprocessing (allocate, upload b/x0 from pinned host memory, r0) + K harness "
+                        "iterations with the residual norm read back each + x_star download, / K",
+                "x_star_check": e2e_check},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "spmv_vec_kernel<EpiDot> (y = A p fused with (y,p))",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
+                     "launches_timed": spmv_cnt, "share_of_step": spmv_ms_total / dev_ms,
+                     "frac_of_nominal_8tbs": achieved / 8000.0},
+        "spmv_gbs": achieved,
+        "vector_kernels_ms_per_iter": vec_ms_total / K,
+        "residual_after_timed_steps": r["res_last"] / r["res0"],
+        "also": {"bicgstab_jacobi_ms_per_iter": bi_ms, "bicgstab_launches": rb["launches"]},
+    }
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        try:
+            n_s = args.cpu_sample or pick_cpu_sample(n)
+            leg = reference_leg(n_s, 30, None, n)
+            out["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                   "sample": f"unavailable: {ex}"}
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -80,6 +80,14 @@ int bis_context_info(bis_context *ctx, int64_t info[8]);
 /* Device timing on the context's stream (cudaEvent pair). */
 int bis_timer_start(bis_context *ctx);
 int bis_timer_stop(bis_context *ctx, double *elapsed_ms /* [host] */);
+/* Per-kernel-family device timing: cudaEvent pairs on the context's stream
+ * around every launch of the family ("spmv", "sptrsv", "vector").  Replaces
+ * the TIME(timers->spmv, ...) stopwatches and LIKWID regions of the reference
+ * (common.hpp:249-254, kernels.hpp:25-40), which cannot see asynchronous
+ * device work.  enable(on) resets the accumulators; read synchronises. */
+int bis_profile_enable(bis_context *ctx, int on);
+int bis_profile_read(bis_context *ctx, const char *family,
+                     double *total_ms /* [host] */, int64_t *launches /* [host] */);
 /* Write `bytes` of scratch to evict L2 between timed launches. */
 int bis_flush_l2(bis_context *ctx);
 /* Tuning knobs (all have defaults): key = "spmv_variant" (0 auto, 1 vector

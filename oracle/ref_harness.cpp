@@ -274,6 +274,11 @@ void ref_factor_fetch(int *l_rp, int *l_col, double *l_val, int *u_rp,
 // out_dbl[0]=stopping_criteria, out_dbl[1]=final residual_norm (true residual
 // from save_x_star), out_dbl[2]=iterate_time [s], out_dbl[3]=spmv_time [s],
 // out_dbl[4]=precond_time [s], out_dbl[5]=solve_time [s].
+// Bounded runs for bench.py's CPU-baseline leg: caps the public `max_iters`
+// member of the reference's Solver (solver.hpp:29); 0 restores MAX_ITERS.
+static int g_ref_max_iters = 0;
+void ref_set_max_iters(int max_iters) { g_ref_max_iters = max_iters; }
+
 int ref_solve(int n, int nnz, const int *rp, const int *col, const double *val,
               int method, int precond, int restart_len, int num_scale,
               int ilu0_old, int use_ref_preprocessing, const double *b,
@@ -293,6 +298,8 @@ int ref_solve(int n, int nnz, const int *rp, const int *col, const double *val,
     Solver *solver = make_solver(&args);
     if (!solver)
         return 1;
+    if (g_ref_max_iters > 0 && g_ref_max_iters <= MAX_ITERS)
+        solver->max_iters = g_ref_max_iters;
     std::unique_ptr<MatrixCRS> A = make_crs(n, n, nnz, rp, col, val);
 
     if (use_ref_preprocessing) {

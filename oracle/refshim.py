@@ -42,6 +42,7 @@ def load(det: bool = False) -> C.CDLL:
     crs = [C.c_int, C.c_int, _ip, _ip, _dp]
     lib.ref_omp_max_threads.restype = C.c_int
     lib.ref_omp_set_threads.argtypes = [C.c_int]
+    lib.ref_set_max_iters.argtypes = [C.c_int]
     lib.ref_spmv.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
     lib.ref_sptrsv.argtypes = crs + [_dp, _dp, _dp]
     lib.ref_bsptrsv.argtypes = crs + [_dp, _dp, _dp]

@@ -11,10 +11,9 @@ SpMV/dot/norm whose order the reference leaves to OpenMP/SIMD.
 import numpy as np
 import pytest
 
-from conftest import golden
+from conftest import HIST_TOL, check_against_fixture, golden
 from oracle import matgen, port, refshim
 
-HIST_TOL = 1e-10   # max_k |r_k - r_k^ref| / r_0, north_star
 RED_TOL = 1e-13    # relative, order-unspecified reductions
 
 
@@ -172,31 +171,6 @@ def _solve_keys(g):
     return sorted(k[:-len("__history")] for k in g.files if k.endswith("__history"))
 
 
-def check_history(got, g, key, unstable=False):
-    """The parity bar of north_star: same iteration count, max_k |r_k - r_k^ref| <= 1e-10 r0."""
-    want = g[key + "__history"]
-    its, conv, restarts = (int(v) for v in g[key + "__meta"])
-    r0 = want[0]
-    if unstable:
-        # diverging / stagnating runs amplify rounding differences without bound (SURVEY.md 7,
-        # "Config 4 numerics"; the reference's own 1-vs-8-thread histories differ by percents after
-        # 10 iterations there): pin the first iterations only
-        k = min(4, want.size, got.history.size)
-        assert np.max(np.abs(got.history[:k] - want[:k]) / np.maximum(np.abs(want[:k]), r0)) <= 1e-9
-        return
-    assert got.iter_count == its, (key, got.iter_count, its)
-    assert got.converged == bool(conv) and got.restarts == restarts
-    assert got.history.size == want.size
-    assert np.max(np.abs(got.history - want)) <= HIST_TOL * r0, key
-    fin = g[key + "__final"][0]
-    assert abs(got.final_true_residual - fin) <= HIST_TOL * r0
-
-
-UNSTABLE = {("fdm2d16", "cg__gs"), ("band_klein", "cg__gs"), ("hpcg16", "cg__gs"),
-            ("anderson_12_10_8", "gm__ilu0"), ("anderson_12_10_8", "gm__j"),
-            ("anderson_12_10_8", "bi__ilu0")}
-
-
 @pytest.mark.parametrize("name", ["fdm2d16", "band_klein", "hpcg16", "hpcg32", "anderson_12_10_8",
                                   "anderson_dd_12_10_8"])
 def test_golden_solves(name):
@@ -207,7 +181,7 @@ def test_golden_solves(name):
         if name == "hpcg16" and method in ("j", "gs", "sgs"):
             continue   # ~1000 serial sweeps each; covered by fdm2d16 / band_klein
         got = port.solve(rp, col, val, method, pre)
-        check_history(got, g, key, unstable=(name, key) in UNSTABLE)
+        check_against_fixture(got, g, key)
 
 
 # ---- (3) live against the compiled reference (build container only) -------------------------
