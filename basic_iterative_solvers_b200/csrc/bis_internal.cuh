@@ -113,6 +113,9 @@ struct bis_context {
     int opt_spmv_variant = 0;
     int opt_spmv_lanes = 0;
     int opt_trsv_variant = 0;
+    int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
+    int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
+    int opt_spmv_smem_kb = 0;   // TMA variant: shared-memory budget per CTA (0 auto)
     int profile = 0;
     ProfTag prof[BIS_PROF_NTAGS];
 };

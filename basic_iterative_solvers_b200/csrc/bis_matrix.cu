@@ -68,8 +68,8 @@ int upload_common(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz, c
     A->max_row = max_row;
     A->mean_row = n_rows ? (double)nnz / (double)n_rows : 0.0;
     RP *d_rp = nullptr;
-    if (dev_alloc(&d_rp, (size_t)n_rows + 1) || dev_alloc(&A->d_col, (size_t)nnz) ||
-        dev_alloc(&A->d_val, (size_t)nnz)) {
+    if (dev_alloc(&d_rp, (size_t)n_rows + 1) || dev_alloc(&A->d_col, (size_t)nnz + 4) ||
+        dev_alloc(&A->d_val, (size_t)nnz + 4)) {
         A->d_rp = d_rp;
         free_matrix_storage(A);
         delete A;
@@ -412,8 +412,8 @@ extern "C" int bis_matrix_generate_hpcg(bis_context *c, int nx, int ny, int nz, 
     int rc = 0;
     if (wide) rc |= dev_alloc(reinterpret_cast<int64_t **>(&A->d_rp), (size_t)n_local + 1);
     else rc |= dev_alloc(reinterpret_cast<int32_t **>(&A->d_rp), (size_t)n_local + 1);
-    rc |= dev_alloc(&A->d_col, (size_t)nnz_local);
-    rc |= dev_alloc(&A->d_val, (size_t)nnz_local);
+    rc |= dev_alloc(&A->d_col, (size_t)nnz_local + 4);
+    rc |= dev_alloc(&A->d_val, (size_t)nnz_local + 4);
     if (rc) {
         free_matrix_storage(A);
         delete A;
@@ -462,7 +462,7 @@ extern "C" int bis_matrix_generate_anderson(bis_context *c, int lx, int ly, int 
     A->mean_row = n_local ? (double)nnz_local / (double)n_local : 0.0;
     A->rp_bytes = 8;
     A->d_rp = d_rp64;
-    if (dev_alloc(&A->d_col, (size_t)nnz_local) || dev_alloc(&A->d_val, (size_t)nnz_local)) {
+    if (dev_alloc(&A->d_col, (size_t)nnz_local + 4) || dev_alloc(&A->d_val, (size_t)nnz_local + 4)) {
         free_matrix_storage(A);
         delete A;
         return 1;

@@ -20,6 +20,7 @@
 //
 // Variant 2 (TMA-staged, thread-per-row) lives in bis_spmv_tma.cu.
 #include "bis_device.cuh"
+#include "bis_spmv_tma.cuh"
 
 namespace {
 
@@ -137,7 +138,7 @@ int launch_one(bis_context *c, const SpmvIn &in, const Epi &epi, RedArgs &ra, in
     const int64_t rows = in.cnt1 + in.cnt2;
     constexpr int rows_per_block = (SPMV_THREADS / 32) * (32 / LPR);
     int cap = c->sm_count * occ;
-    if (cap > BIS_MAX_RED_BLOCKS / 2) cap = BIS_MAX_RED_BLOCKS / 2;
+    if (cap > BIS_MAX_RED_BLOCKS / 4) cap = BIS_MAX_RED_BLOCKS / 4;
     int blocks = bis_blocks_for(rows, rows_per_block, cap);
     *blocks_out = blocks;
     if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + blocks;
@@ -180,9 +181,86 @@ int launch_rp(bis_context *c, const bis_matrix *A, const SpmvIn &in, const Epi &
 
 } // namespace
 
-// Variant 2 entry (bis_spmv_tma.cu); returns -1 when it does not apply.
-int bis_spmv_tma_try(bis_context *c, const bis_matrix *A, const double *x, int epi_kind,
-                     const void *epi, int slot_a, int slot_b);
+// ---- variant 2 (TMA-staged, thread per row): plan + launch ------------------------------
+namespace {
+
+bool tma_plan(const bis_context *c, const bis_matrix *A, tma::Plan *p) {
+    if (c->opt_spmv_variant == 1) return false;
+    if (A->max_row < 1 || A->max_row > 96) return false;
+    const size_t budget = (size_t)(c->opt_spmv_smem_kb > 0 ? c->opt_spmv_smem_kb : 200) << 10;
+    for (int R : {256, 128, 64}) {
+        if (c->opt_spmv_rows > 0 && R != c->opt_spmv_rows) continue;
+        const int cap = (R * A->max_row + 8 + 3) & ~3;
+        const size_t stage = (size_t)cap * 12;
+        int nstage = (int)((budget - 128) / stage);
+        if (nstage > 4) nstage = 4;
+        if (c->opt_spmv_stages > 0 && nstage > c->opt_spmv_stages) nstage = c->opt_spmv_stages;
+        if (nstage < 2) continue;
+        p->threads = R;
+        p->cap = cap;
+        p->nstage = nstage;
+        p->smem_bytes = 128 + stage * nstage;
+        return true;
+    }
+    return false;
+}
+
+template <typename RP, bool GHOST, class Epi>
+int launch_tma(bis_context *c, const tma::Plan &p, SpmvTmaIn in, const Epi &epi, RedArgs &ra, int *nb) {
+    auto kern = spmv_tma_kernel<RP, GHOST, Epi>;
+    static size_t configured = 0;
+    if (configured < p.smem_bytes) {
+        BIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        configured = p.smem_bytes;
+    }
+    int occ = 1;
+    BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, p.threads, p.smem_bytes));
+    if (occ < 1) occ = 1;
+    const int64_t n_tiles = (in.cnt + p.threads - 1) / p.threads;
+    int64_t grid = (int64_t)c->sm_count * occ;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    in.tiles_per_cta = (n_tiles + grid - 1) / grid;
+    if (in.tiles_per_cta < 1) in.tiles_per_cta = 1;
+    in.cap = p.cap;
+    in.nstage = p.nstage;
+    *nb = (int)grid;
+    if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + (int)grid;
+    kern<<<(unsigned)grid, p.threads, p.smem_bytes, c->stream>>>(in, epi, ra);
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}
+
+struct Segment {
+    int64_t lo, cnt;
+    bool ghost;
+};
+
+// One contiguous row range with either variant.
+template <class Epi>
+int launch_segment(bis_context *c, const bis_matrix *A, const double *x, const Segment &sg, const Epi &epi,
+                   RedArgs &ra, int *nb) {
+    tma::Plan plan;
+    if (tma_plan(c, A, &plan)) {
+        SpmvTmaIn in;
+        in.rp = A->d_rp; in.col = A->d_col; in.val = A->d_val; in.x = x;
+        in.ghost = A->halo.d_ghost; in.n_owned = A->n_cols;
+        in.lo = sg.lo; in.cnt = sg.cnt;
+        in.tiles_per_cta = 1; in.cap = 0; in.nstage = 0;
+        if (A->rp_bytes == 8)
+            return sg.ghost ? launch_tma<int64_t, true, Epi>(c, plan, in, epi, ra, nb)
+                            : launch_tma<int64_t, false, Epi>(c, plan, in, epi, ra, nb);
+        return sg.ghost ? launch_tma<int32_t, true, Epi>(c, plan, in, epi, ra, nb)
+                        : launch_tma<int32_t, false, Epi>(c, plan, in, epi, ra, nb);
+    }
+    SpmvIn in;
+    in.rp = A->d_rp; in.col = A->d_col; in.val = A->d_val; in.x = x;
+    in.ghost = A->halo.d_ghost; in.n_owned = A->n_cols;
+    in.lo1 = sg.lo; in.cnt1 = sg.cnt; in.lo2 = 0; in.cnt2 = 0;
+    return sg.ghost ? launch_rp<true, Epi>(c, A, in, epi, ra, nb) : launch_rp<false, Epi>(c, A, in, epi, ra, nb);
+}
+
+} // namespace
 
 // Shared driver: halo exchange (distributed) overlapped with the interior rows.
 template <class Epi>
@@ -191,35 +269,31 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     BIS_REQUIRE(c && A && x, "spmv: null argument");
     BIS_CUDA(cudaSetDevice(c->device));
     RedArgs ra = bis_red_args(c, slot_a, slot_b);
-    SpmvIn in;
-    in.rp = A->d_rp;
-    in.col = A->d_col;
-    in.val = A->d_val;
-    in.x = x;
-    in.ghost = A->halo.d_ghost;
-    in.n_owned = A->n_cols;
-    int nb = 0;
     BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPMV));
-    if (!A->distributed || A->halo.n_ghost == 0) {
-        in.lo1 = 0; in.cnt1 = A->n_rows; in.lo2 = 0; in.cnt2 = 0;
-        BIS_CHECK((launch_rp<false, Epi>(c, A, in, epi, ra, &nb)));
+    Segment seg[3];
+    int nseg = 0;
+    bool halo = A->distributed && A->halo.n_ghost > 0;
+    if (!halo) {
+        seg[nseg++] = {0, A->n_rows, false};
     } else {
-        // rows [interior_begin, interior_end) touch no ghost column: run them
+        // rows [interior_begin, interior_end) touch no ghost column: they run
         // while the halo is in flight, then the two boundary strips.
         BIS_CHECK(bis_halo_exchange_begin(c, A, x));
         const int64_t ib = A->halo.interior_begin, ie = A->halo.interior_end;
-        int nb1 = 0;
         if (ie > ib) {
-            in.lo1 = ib; in.cnt1 = ie - ib; in.lo2 = 0; in.cnt2 = 0;
-            ra.finalize = 0;
-            BIS_CHECK((launch_rp<false, Epi>(c, A, in, epi, ra, &nb1)));
+            seg[nseg++] = {ib, ie - ib, false};
+            if (ib > 0) seg[nseg++] = {0, ib, true};
+            if (A->n_rows > ie) seg[nseg++] = {ie, A->n_rows - ie, true};
+        } else {
+            seg[nseg++] = {0, A->n_rows, true};
         }
-        BIS_CHECK(bis_halo_exchange_end(c, A));
-        in.lo1 = 0; in.cnt1 = (ie > ib) ? ib : A->n_rows;
-        in.lo2 = ie; in.cnt2 = (ie > ib) ? A->n_rows - ie : 0;
-        ra.finalize = 1;
-        ra.block_offset = nb1;
-        BIS_CHECK((launch_rp<true, Epi>(c, A, in, epi, ra, &nb)));
+    }
+    for (int i = 0; i < nseg; ++i) {
+        if (halo && seg[i].ghost && (i == 0 || !seg[i - 1].ghost)) BIS_CHECK(bis_halo_exchange_end(c, A));
+        int nb = 0;
+        ra.finalize = (i == nseg - 1) ? 1 : 0;
+        BIS_CHECK(launch_segment(c, A, x, seg[i], epi, ra, &nb));
+        ra.block_offset += nb;
     }
     BIS_CHECK(bis_prof_end(c, BIS_PROF_SPMV));
     if (Epi::NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));

@@ -62,6 +62,7 @@ def load() -> C.CDLL:
     lib.o_solve.argtypes = [C.c_int, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_void_p,
                             C.c_void_p, _dp, _dp, _ip, _dp]
     lib.o_solve.restype = C.c_int
+    lib.o_set_params.argtypes = [C.c_double, C.c_int]
     _lib = lib
     return lib
 
@@ -141,8 +142,10 @@ def apply_preconditioner(precond, fac: Factors, inp, inplace=False):
     return out
 
 
-def solve(rp, col, val, method, precond="none", restart_len=10, b=None, x0=None) -> SolveResult:
+def solve(rp, col, val, method, precond="none", restart_len=10, b=None, x0=None, tol=0.0,
+          max_iters=0) -> SolveResult:
     lib = load()
+    lib.o_set_params(float(tol), int(max_iters))
     rp, col, val = _crs(rp, col, val)
     n = rp.size - 1
     hist = np.zeros(2 * MAX_ITERS)

@@ -21,9 +21,12 @@
  *   - sum_vectors / subtract_vectors: one fused multiply-add (vfmadd/vfnmadd)
  *   - elemwise_mult / elemwise_div / scale / normalize_x: separately rounded
  *   - ILU(0) row update: fused (vfnmadd231sd)
- *   - SpMV, dot, norm: the reference's own order is unspecified (omp simd /
- *     omp reduction); the restatement uses storage order with fma for SpMV
- *     and plain left-to-right mul+add for dot/norm.  Tolerance only.
+ *   - SpMV: unfused multiply then add in storage order (GCC's in-order simd
+ *     reduction) -- bit-identical to the compiled reference at any thread count
+ *     (threads only split rows)
+ *   - dot, norm: left-to-right sum of separately rounded products; identical to
+ *     the reference at ONE OpenMP thread, tolerance only at more threads (the
+ *     cross-thread combine order is OpenMP's).
  */
 #include <math.h>
 #include <stdint.h>
@@ -39,6 +42,16 @@
 #define O_ILU0_PIVOT_TOL 1e-8     /* CMakeLists.txt:28 */
 #define O_ILU0_PIVOT_REPL 1e-4    /* CMakeLists.txt:29 */
 
+/* Solver::tolerance / Solver::max_iters are public members of the reference
+ * (solver.hpp:29-30) initialised from the macros above; tests may lower them
+ * (never above O_MAX_ITERS: the history arrays are sized by it). */
+static double o_tol = O_TOL;
+static int o_max_iters = O_MAX_ITERS;
+void o_set_params(double tol, int max_iters) {
+    o_tol = tol > 0.0 ? tol : O_TOL;
+    o_max_iters = (max_iters > 0 && max_iters <= O_MAX_ITERS) ? max_iters : O_MAX_ITERS;
+}
+
 /* common.hpp:38-56 */
 enum { P_NONE = 0, P_J = 1, P_GS = 2, P_BGS = 3, P_SGS = 4, P_2ST = 5, P_S2ST = 6, P_ILU0 = 7 };
 enum { M_J = 0, M_GS = 1, M_SGS = 2, M_GM = 3, M_CG = 4, M_BI = 5 };
@@ -53,13 +66,21 @@ typedef struct {
 
 /* ---- kernels.hpp --------------------------------------------------------- */
 
-/* kernels.hpp:22-42 native_spmv: y[r] = sum_k val[k] * x[col[k]] */
+/* kernels.hpp:22-42 native_spmv: y[r] = sum_k val[k] * x[col[k]].
+ * Order and rounding of the compiled reference (g++ 13.3, -O3 -fopenmp,
+ * x86-64-v3; established by single-row experiments against oracle/_ref, see
+ * DESIGN.md "summation orders"): GCC may not reassociate the `omp simd
+ * reduction(+)` without -ffast-math, so it vectorises the multiplies and adds
+ * the separately rounded products IN STORAGE ORDER (fold-left reduction):
+ * acc = acc + (val*x), two roundings per nonzero, no FMA. */
 void o_spmv(int n_rows, const int *rp, const int *col, const double *val,
             const double *x, double *y) {
     for (int r = 0; r < n_rows; ++r) {
         double acc = 0.0;
-        for (int k = rp[r]; k < rp[r + 1]; ++k)
-            acc = fma(val[k], x[col[k]], acc);
+        for (int k = rp[r]; k < rp[r + 1]; ++k) {
+            double p = val[k] * x[col[k]];
+            acc = acc + p;
+        }
         y[r] = acc;
     }
 }
@@ -590,7 +611,7 @@ static void o_exchange(osolver *S) {
 static void o_check_restart(osolver *S) {
     if (S->method != M_GM) return;
     int conv = S->residual_norm < S->stopping;
-    int over = S->iter_count > O_MAX_ITERS;
+    int over = S->iter_count > o_max_iters;
     int cycle = (S->iter_count % S->m == 0) && (S->iter_count != 0);
     if (!conv && !over && cycle) {
         S->restarted = 1;
@@ -605,7 +626,7 @@ static void o_check_restart(osolver *S) {
 /* solver.hpp:177-191 */
 static int o_stop(const osolver *S) {
     int conv = fabs(S->residual_norm) < S->stopping;
-    int over = S->iter_count >= (O_MAX_ITERS - S->restart_count);
+    int over = S->iter_count >= (o_max_iters - S->restart_count);
     int div = fabs(S->residual_norm) > DBL_MAX || isnan(S->residual_norm);
     return conv || over || div;
 }
@@ -681,7 +702,7 @@ int o_solve(int n, const int *rp, const int *col, const double *val, int method,
     }
 
     o_init_residual(&S);
-    S.stopping = O_TOL * S.residual_norm;   /* solver.hpp:173-175 */
+    S.stopping = o_tol * S.residual_norm;   /* solver.hpp:173-175 */
 
     /* solver_harness.hpp:15-51 */
     do {

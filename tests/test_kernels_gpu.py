@@ -3,9 +3,11 @@ against the oracle (oracle/port) and the fixtures produced by the compiled refer
 
 Bit-exact: triangular solves, every preconditioner built from them, the axpby family, scale,
 copy, init, normalize_x given the same SpMV input, ILU(0) applies, generators, diagonal peel.
-Tolerance 1e-13 relative (order of summation is the kernel's, not the reference's, which the
-reference itself leaves to OpenMP/SIMD): SpMV, dot, norm and everything fused
-with them.
+Also bit-exact: SpMV in its default variant (TMA-staged tiles, one thread per row, products added
+in storage order with separate roundings -- the order the compiled reference uses), and with it the
+Jacobi sweep, compute_residual and b - T x.
+Tolerance 1e-13 relative: dot and norm (the reference sums sequentially, a GPU cannot), and the
+vector-CRS SpMV variant kept for rows too long for a shared-memory tile.
 """
 import numpy as np
 import pytest
@@ -33,13 +35,21 @@ def f64(*a):
     return np.array(a, np.float64)
 
 
-def run_spmv(ctx, rp, col, val, x, lanes=0):
+def run_spmv(ctx, rp, col, val, x, lanes=0, **opts):
+    """lanes = 0: default variant (TMA-staged, thread per row, in-order sums: bit-exact);
+    lanes > 0: the vector-CRS variant with that many lanes per row (tolerance only)."""
     A = ctx.upload_crs(rp, col, val)
+    ctx.set_option("spmv_variant", 1 if lanes else 0)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
     ctx.set_option("spmv_lanes", lanes)
     dx, dy = ctx.upload(x), ctx.alloc(len(rp) - 1)
     ctx.call("bis_spmv", A.h, dx, dy)
     y = ctx.download(dy, len(rp) - 1)
     ctx.set_option("spmv_lanes", 0)
+    ctx.set_option("spmv_variant", 0)
+    for k in opts:
+        ctx.set_option(k, 0)
     ctx.free(dx), ctx.free(dy), A.free()
     return y
 
@@ -96,7 +106,31 @@ def test_kat_vector_ops(ctx):
 def test_spmv_hpcg_vs_oracle(ctx, lanes):
     rp, col, val = matgen.hpcg(24, 20, 17)
     x = np.random.default_rng(1).uniform(-1, 1, len(rp) - 1)
-    assert rel(run_spmv(ctx, rp, col, val, x, lanes), port.spmv(rp, col, val, x)) <= RED_TOL
+    got, want = run_spmv(ctx, rp, col, val, x, lanes), port.spmv(rp, col, val, x)
+    if lanes == 0:
+        assert np.array_equal(got, want)       # in-order sums: the reference's bits
+    else:
+        assert rel(got, want) <= RED_TOL
+
+
+@pytest.mark.parametrize("rows,stages,smem_kb", [(256, 2, 0), (128, 4, 0), (64, 3, 0), (256, 0, 170), (128, 2, 100), (64, 0, 50)])
+def test_spmv_tma_tile_shapes_bit_exact(ctx, rows, stages, smem_kb):
+    """Every tile shape / pipeline depth of the TMA-staged variant gives the same bits, on a
+    ragged matrix whose tiles start and end off the 16-byte copy alignment, with empty rows, an
+    empty leading tile and a row count that is not a multiple of the tile."""
+    rng = np.random.default_rng(12)
+    n = 70001
+    lens = rng.integers(0, 28, n)
+    lens[:600] = 0
+    lens[::11] = 0
+    for rp_dtype in (np.int32, np.int64):
+        rp = np.zeros(n + 1, rp_dtype)
+        np.cumsum(lens, out=rp[1:])
+        col = rng.integers(0, n, rp[-1]).astype(np.int32)
+        val = rng.uniform(-1, 1, rp[-1])
+        x = rng.uniform(-1, 1, n)
+        got = run_spmv(ctx, rp, col, val, x, 0, spmv_rows=rows, spmv_stages=stages, spmv_smem_kb=smem_kb)
+        assert np.array_equal(got, port.spmv(rp.astype(np.int32), col, val, x))
 
 
 def test_spmv_ragged_empty_rows_and_64bit_rowptr(ctx):
@@ -127,23 +161,23 @@ def test_spmv_and_fused_forms_vs_reference_fixture(ctx, name):
     rp, col, val = matgen.hpcg(16) if name == "hpcg16" else (g["rp"], g["col"], g["val"])
     x, v = g["k__x"], g["k__v"]
     n = x.size
-    assert rel(run_spmv(ctx, rp, col, val, x), g["k__spmv"]) <= RED_TOL
+    assert np.array_equal(run_spmv(ctx, rp, col, val, x), g["k__spmv"])     # the compiled reference's bits
     A = ctx.upload_crs(rp, col, val)
     dx, dv, dy, dr = ctx.upload(x), ctx.upload(v), ctx.alloc(n), ctx.alloc(n)
     y_ref = port.spmv(rp, col, val, x)
     # spmv + dots
     ctx.call("bis_spmv_dot", A.h, dx, dy, dv, 20, 21)
     s = ctx.scalars(20, 2)
-    assert rel(ctx.download(dy, n), y_ref) <= RED_TOL
+    assert np.array_equal(ctx.download(dy, n), y_ref)
     assert abs(s[0] - y_ref @ v) <= 1e-12 * np.linalg.norm(y_ref) * np.linalg.norm(v)
     assert abs(s[1] - y_ref @ y_ref) <= 1e-12 * (y_ref @ y_ref)
     # residual + squared norm (compute_residual, kernels.hpp:155-162)
     ctx.call("bis_spmv_residual", A.h, dx, dv, dr, dy, 22)
     r_ref = v - y_ref
-    assert rel(ctx.download(dr, n), r_ref) <= RED_TOL * 10
+    assert np.array_equal(ctx.download(dr, n), r_ref)
     assert abs(ctx.scalars(22)[0] - r_ref @ r_ref) <= 1e-12 * (r_ref @ r_ref)
     ctx.call("bis_compute_residual", A.h, dx, dv, dr, dy)
-    assert rel(ctx.download(dr, n), r_ref) <= RED_TOL * 10
+    assert np.array_equal(ctx.download(dr, n), r_ref) and np.array_equal(ctx.download(dy, n), y_ref)
     # Jacobi sweep == spmv then normalize_x (jacobi.hpp:27-52); fused and unfused agree bit for bit
     f = port.factor(rp, col, val, "sgs")
     dD, dxn = ctx.upload(f.A_D), ctx.alloc(n)
@@ -152,11 +186,11 @@ def test_spmv_and_fused_forms_vs_reference_fixture(ctx, name):
     ctx.call("bis_spmv", A.h, dx, dxn)
     ctx.call("bis_normalize_x", dxn, dx, dD, dv, n)
     assert np.array_equal(fused, ctx.download(dxn, n))
-    assert rel(fused, g["k__normalize_x"]) <= 1e-12
+    assert np.array_equal(fused, g["k__normalize_x"])
     # b - T x on a strictly triangular factor (gauss_seidel.hpp:30-34)
     U = ctx.upload_triangular(f.u_rp, f.u_col, f.u_val, upper=True)
     ctx.call("bis_spmv_sub", U.h, dx, dv, dr)
-    assert rel(ctx.download(dr, n), v - port.spmv(f.u_rp, f.u_col, f.u_val, x)) <= RED_TOL * 10
+    assert np.array_equal(ctx.download(dr, n), v - port.spmv(f.u_rp, f.u_col, f.u_val, x))
     U.free(), A.free()
 
 
