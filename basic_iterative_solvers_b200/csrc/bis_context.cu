@@ -268,6 +268,8 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_rows") c->opt_spmv_rows = value;
     else if (k == "spmv_stages") c->opt_spmv_stages = value;
     else if (k == "spmv_smem_kb") c->opt_spmv_smem_kb = value;
+    else if (k == "spmv_blocked") c->opt_spmv_blocked = value;
+    else if (k == "spmv_mult") c->opt_spmv_mult = value;
     else {
         bis_set_error("unknown option '%s'", key);
         return 2;

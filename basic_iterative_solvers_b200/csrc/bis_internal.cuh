@@ -115,6 +115,8 @@ struct bis_context {
     int opt_trsv_variant = 0;
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
+    int opt_spmv_mult = 0;      // TMA variant: threads per tile row (1, 2, 4; 0 auto)
+    int opt_spmv_blocked = 0;   // TMA variant: 1 = contiguous tile run per CTA instead of interleaved
     int opt_spmv_smem_kb = 0;   // TMA variant: shared-memory budget per CTA (0 auto)
     int profile = 0;
     ProfTag prof[BIS_PROF_NTAGS];

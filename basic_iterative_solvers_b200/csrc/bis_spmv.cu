@@ -187,16 +187,23 @@ namespace {
 bool tma_plan(const bis_context *c, const bis_matrix *A, tma::Plan *p) {
     if (c->opt_spmv_variant == 1) return false;
     if (A->max_row < 1 || A->max_row > 96) return false;
-    const size_t budget = (size_t)(c->opt_spmv_smem_kb > 0 ? c->opt_spmv_smem_kb : 200) << 10;
-    for (int R : {256, 128, 64}) {
+    // Measured on HPCG-512 (tools/tune_spmv.py, profiles/): small tiles with two stages and
+    // several resident CTAs per SM beat one big CTA -- the tile is consumed in latency-bound
+    // phases, and co-resident CTAs overlap them.  Default: ~20 KB per stage.
+    const size_t budget = (size_t)(c->opt_spmv_smem_kb > 0 ? c->opt_spmv_smem_kb : 44) << 10;
+    const int max_stages = c->opt_spmv_stages > 0 ? c->opt_spmv_stages : 2;
+    for (int R : {256, 128, 64, 32}) {
         if (c->opt_spmv_rows > 0 && R != c->opt_spmv_rows) continue;
         const int cap = (R * A->max_row + 8 + 3) & ~3;
         const size_t stage = (size_t)cap * 12;
         int nstage = (int)((budget - 128) / stage);
-        if (nstage > 4) nstage = 4;
-        if (c->opt_spmv_stages > 0 && nstage > c->opt_spmv_stages) nstage = c->opt_spmv_stages;
+        if (nstage > max_stages) nstage = max_stages;
+        if (nstage > tma::MAX_STAGES) nstage = tma::MAX_STAGES;
         if (nstage < 2) continue;
-        p->threads = R;
+        int mult = c->opt_spmv_mult > 0 ? c->opt_spmv_mult : 2;
+        while (R * mult > 1024) mult >>= 1;
+        p->threads = R * mult;
+        p->rows = R;
         p->cap = cap;
         p->nstage = nstage;
         p->smem_bytes = 128 + stage * nstage;
@@ -216,7 +223,7 @@ int launch_tma(bis_context *c, const tma::Plan &p, SpmvTmaIn in, const Epi &epi,
     int occ = 1;
     BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, p.threads, p.smem_bytes));
     if (occ < 1) occ = 1;
-    const int64_t n_tiles = (in.cnt + p.threads - 1) / p.threads;
+    const int64_t n_tiles = (in.cnt + p.rows - 1) / p.rows;
     int64_t grid = (int64_t)c->sm_count * occ;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
@@ -224,6 +231,8 @@ int launch_tma(bis_context *c, const tma::Plan &p, SpmvTmaIn in, const Epi &epi,
     if (in.tiles_per_cta < 1) in.tiles_per_cta = 1;
     in.cap = p.cap;
     in.nstage = p.nstage;
+    in.interleave = c->opt_spmv_blocked ? 0 : 1;
+    in.rows = p.rows;
     *nb = (int)grid;
     if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + (int)grid;
     kern<<<(unsigned)grid, p.threads, p.smem_bytes, c->stream>>>(in, epi, ra);
@@ -246,7 +255,7 @@ int launch_segment(bis_context *c, const bis_matrix *A, const double *x, const S
         in.rp = A->d_rp; in.col = A->d_col; in.val = A->d_val; in.x = x;
         in.ghost = A->halo.d_ghost; in.n_owned = A->n_cols;
         in.lo = sg.lo; in.cnt = sg.cnt;
-        in.tiles_per_cta = 1; in.cap = 0; in.nstage = 0;
+        in.tiles_per_cta = 1; in.cap = 0; in.nstage = 0; in.interleave = 1; in.rows = 0;
         if (A->rp_bytes == 8)
             return sg.ghost ? launch_tma<int64_t, true, Epi>(c, plan, in, epi, ra, nb)
                             : launch_tma<int64_t, false, Epi>(c, plan, in, epi, ra, nb);
