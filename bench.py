@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric: PCG time/iteration and SpMV HBM GB/s vs roofline on HPCG-512.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 512]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 512]
 
 A "step" is ONE iteration of the solver harness loop (solver_harness.hpp:17-50 of the
 reference: iterate, residual-norm sample read back by the host, pointer exchange) of
@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="HPCG grid edge (BASELINE: 512)")
+    ap.add_argument("--grid", dest="n", type=int, default=512, help="HPCG grid edge (BASELINE: 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="HPCG edge of the CPU sample (0: auto)")
     args = ap.parse_args()

@@ -165,7 +165,21 @@ def test_size_independent_properties_at_scale(ctx):
     assert r.final_true_residual <= 1e-11 * r.history[0]     # true residual of x_star, recomputed
     b = host.solve(ctx, "bi", "j", matrix_name="HPCG-128", want_x=False)
     assert abs(b.history[1] - 2.4190103171406172e+03) <= 1e-10 * b.history[0]
-    assert b.converged and abs(b.iter_count - 189) <= 12
+    assert b.converged and 150 <= b.iter_count <= 230     # reference: 189 at 8 threads; same caveat
     j = host.solve(ctx, "j", "none", matrix_name="HPCG-128", want_x=False)
     assert not j.converged and j.iter_count == 1000
     assert abs(j.history[1000] - 5.8007937268987325e+02) <= 1e-10 * j.history[0]
+
+
+def test_two_gpu_partition_matches_single_gpu():
+    """Needs >= 2 GPUs (skipped on the single-GPU box): tools/dist_check.py under torchrun."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", "tools/dist_check.py", "40"],
+                         cwd=root, capture_output=True, text=True, timeout=600)
+    assert "DIST_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
