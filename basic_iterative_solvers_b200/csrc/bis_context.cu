@@ -270,6 +270,8 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_smem_kb") c->opt_spmv_smem_kb = value;
     else if (k == "spmv_blocked") c->opt_spmv_blocked = value;
     else if (k == "spmv_mult") c->opt_spmv_mult = value;
+    else if (k == "win_rows") c->opt_win_rows = value;
+    else if (k == "spmv_debug") c->opt_spmv_debug = value;
     else {
         bis_set_error("unknown option '%s'", key);
         return 2;
@@ -281,7 +283,8 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
 extern "C" int bis_vector_alloc(bis_context *c, int64_t n, double **v) {
     BIS_REQUIRE(c && v && n >= 0, "bis_vector_alloc: bad argument");
     BIS_CUDA(cudaSetDevice(c->device));
-    size_t bytes = sizeof(double) * (size_t)(n > 0 ? n : 1);
+    // +2: the x windows of SpMV variant 3 are copied in 16-byte units and may overrun an odd length
+    size_t bytes = sizeof(double) * ((size_t)(n > 0 ? n : 1) + 2);
     BIS_CUDA(cudaMalloc(v, bytes));
     BIS_CUDA(cudaMemsetAsync(*v, 0, bytes, c->stream));
     return 0;

@@ -139,7 +139,7 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
     HaloPlan &h = A->halo;
     h.n_ghost = (int64_t)ghost_h.size();
     BIS_CUDA(cudaMalloc(&h.d_ghost_global, sizeof(int) * std::max<size_t>(ghost_h.size(), 1)));
-    BIS_CUDA(cudaMalloc(&h.d_ghost, sizeof(double) * std::max<size_t>(ghost_h.size(), 1)));
+    BIS_CUDA(cudaMalloc(&h.d_ghost, sizeof(double) * (std::max<size_t>(ghost_h.size(), 1) + 2)));
     if (!ghost_h.empty())
         BIS_CUDA(cudaMemcpyAsync(h.d_ghost_global, ghost_h.data(), sizeof(int) * ghost_h.size(), cudaMemcpyHostToDevice, st));
 

@@ -115,6 +115,8 @@ struct bis_context {
     int opt_trsv_variant = 0;
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
+    int opt_spmv_debug = 0;     // perf experiments (results invalid when non-zero)
+    int opt_win_rows = 0;       // variant 3: rows per tile (0 auto; fixed once a matrix's format is built)
     int opt_spmv_mult = 0;      // TMA variant: threads per tile row (1, 2, 4; 0 auto)
     int opt_spmv_blocked = 0;   // TMA variant: 1 = contiguous tile run per CTA instead of interleaved
     int opt_spmv_smem_kb = 0;   // TMA variant: shared-memory budget per CTA (0 auto)
@@ -149,6 +151,20 @@ struct HaloPlan {
     int64_t interior_begin = 0, interior_end = 0;   // rows without ghosts
 };
 
+// Acceleration structure of SpMV variant 3 (bis_spmv_win.cuh), derived lazily from the CRS arrays.
+struct WinFormat {
+    int state = 0;                 // 0 not built, 1 usable, -1 not representable (fall back)
+    int R = 0;                     // rows per tile
+    int cap = 0;                   // nonzeros per stage
+    int xcap = 0;                  // x-window doubles per stage
+    int64_t n_tiles = 0;
+    int *d_seg_start = nullptr;
+    unsigned short *d_seg_len = nullptr;
+    unsigned short *d_seg_off = nullptr;
+    int *d_nseg = nullptr;
+    unsigned short *d_lidx = nullptr;
+};
+
 struct bis_matrix {
     int64_t n_rows = 0;        // local rows
     int64_t n_cols = 0;        // local owned columns (== n_rows when square)
@@ -165,6 +181,7 @@ struct bis_matrix {
     int max_row = 0;
     LevelSets lv;
     HaloPlan halo;
+    mutable WinFormat win;
     bool distributed = false;
 };
 

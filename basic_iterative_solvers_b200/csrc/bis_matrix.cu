@@ -37,6 +37,11 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->halo.d_sendbuf);
     cudaFree(A->halo.d_send_idx);
     cudaFree(A->halo.d_ghost_global);
+    cudaFree(A->win.d_seg_start);
+    cudaFree(A->win.d_seg_len);
+    cudaFree(A->win.d_seg_off);
+    cudaFree(A->win.d_nseg);
+    cudaFree(A->win.d_lidx);
 }
 
 template <typename RP>
@@ -68,8 +73,8 @@ int upload_common(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz, c
     A->max_row = max_row;
     A->mean_row = n_rows ? (double)nnz / (double)n_rows : 0.0;
     RP *d_rp = nullptr;
-    if (dev_alloc(&d_rp, (size_t)n_rows + 1) || dev_alloc(&A->d_col, (size_t)nnz + 4) ||
-        dev_alloc(&A->d_val, (size_t)nnz + 4)) {
+    if (dev_alloc(&d_rp, (size_t)n_rows + 1 + 8) || dev_alloc(&A->d_col, (size_t)nnz + 8) ||
+        dev_alloc(&A->d_val, (size_t)nnz + 8)) {
         A->d_rp = d_rp;
         free_matrix_storage(A);
         delete A;
@@ -410,10 +415,10 @@ extern "C" int bis_matrix_generate_hpcg(bis_context *c, int nx, int ny, int nz, 
     const bool wide = nnz_local >= (int64_t)INT32_MAX;
     A->rp_bytes = wide ? 8 : 4;
     int rc = 0;
-    if (wide) rc |= dev_alloc(reinterpret_cast<int64_t **>(&A->d_rp), (size_t)n_local + 1);
-    else rc |= dev_alloc(reinterpret_cast<int32_t **>(&A->d_rp), (size_t)n_local + 1);
-    rc |= dev_alloc(&A->d_col, (size_t)nnz_local + 4);
-    rc |= dev_alloc(&A->d_val, (size_t)nnz_local + 4);
+    if (wide) rc |= dev_alloc(reinterpret_cast<int64_t **>(&A->d_rp), (size_t)n_local + 1 + 8);
+    else rc |= dev_alloc(reinterpret_cast<int32_t **>(&A->d_rp), (size_t)n_local + 1 + 8);
+    rc |= dev_alloc(&A->d_col, (size_t)nnz_local + 8);
+    rc |= dev_alloc(&A->d_val, (size_t)nnz_local + 8);
     if (rc) {
         free_matrix_storage(A);
         delete A;
@@ -442,7 +447,7 @@ extern "C" int bis_matrix_generate_anderson(bis_context *c, int lx, int ly, int 
     const int64_t n_local = re - rb;
     AndersonP p{lx, ly, lz, ranpot, t, seed, periodic};
     int64_t *d_rp64 = nullptr;
-    BIS_CHECK(dev_alloc(&d_rp64, (size_t)n_local + 1));
+    BIS_CHECK(dev_alloc(&d_rp64, (size_t)n_local + 1 + 8));
     const int blocks = c->sm_count * 8;
     anderson_count_kernel<<<blocks, 256, 0, c->stream>>>(p, rb, n_local, d_rp64);
     BIS_LAUNCH_CHECK(c);
@@ -462,7 +467,7 @@ extern "C" int bis_matrix_generate_anderson(bis_context *c, int lx, int ly, int 
     A->mean_row = n_local ? (double)nnz_local / (double)n_local : 0.0;
     A->rp_bytes = 8;
     A->d_rp = d_rp64;
-    if (dev_alloc(&A->d_col, (size_t)nnz_local + 4) || dev_alloc(&A->d_val, (size_t)nnz_local + 4)) {
+    if (dev_alloc(&A->d_col, (size_t)nnz_local + 8) || dev_alloc(&A->d_val, (size_t)nnz_local + 8)) {
         free_matrix_storage(A);
         delete A;
         return 1;

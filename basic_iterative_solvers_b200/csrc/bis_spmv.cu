@@ -21,6 +21,7 @@
 // Variant 2 (TMA-staged, thread-per-row) lives in bis_spmv_tma.cu.
 #include "bis_device.cuh"
 #include "bis_spmv_tma.cuh"
+#include "bis_spmv_win.cuh"
 
 namespace {
 
@@ -271,6 +272,130 @@ int launch_segment(bis_context *c, const bis_matrix *A, const double *x, const S
 
 } // namespace
 
+// ---- variant 3 (windowed x, everything by TMA): lazy format build, plan, launch ----------------
+namespace {
+
+int win_free(bis_matrix *A) {
+    WinFormat &w = A->win;
+    cudaFree(w.d_seg_start); cudaFree(w.d_seg_len); cudaFree(w.d_seg_off); cudaFree(w.d_nseg); cudaFree(w.d_lidx);
+    w.d_seg_start = nullptr; w.d_seg_len = nullptr; w.d_seg_off = nullptr; w.d_nseg = nullptr; w.d_lidx = nullptr;
+    return 0;
+}
+
+// Builds A->win on first use.  Returns 0 and sets win.state = 1 (usable) or -1 (some tile needs more
+// than WIN_MAXSEG windows: unstructured matrix, variant 2 is used instead).
+int win_build(bis_context *c, const bis_matrix *A) {
+    WinFormat &w = A->win;
+    if (w.state != 0) return 0;
+    w.state = -1;
+    if (A->n_rows == 0 || A->nnz == 0 || A->max_row < 1) return 0;
+    int R = c->opt_win_rows;
+    if (R != 32 && R != 64 && R != 128 && R != 256) {
+        R = 256;
+        while (R > 32 && (size_t)R * A->max_row * 10 > (size_t)40 << 10) R >>= 1;   // ~<= 40 KB of val+lidx per stage
+    }
+    if ((size_t)R * A->max_row * 10 > (size_t)96 << 10) return 0;                     // rows too long for a tile
+    int sort_cap = 1;
+    while (sort_cap < R * A->max_row) sort_cap <<= 1;
+    const int64_t n_tiles = (A->n_rows + R - 1) / R;
+    int *d_status = nullptr;
+    BIS_CUDA(cudaMalloc(&d_status, 2 * sizeof(int)));
+    BIS_CUDA(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), c->stream));
+    BIS_CUDA(cudaMalloc(&w.d_seg_start, sizeof(int) * (size_t)n_tiles * WIN_MAXSEG));
+    BIS_CUDA(cudaMalloc(&w.d_seg_len, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
+    BIS_CUDA(cudaMalloc(&w.d_seg_off, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
+    BIS_CUDA(cudaMalloc(&w.d_nseg, sizeof(int) * (size_t)n_tiles));
+    BIS_CUDA(cudaMalloc(&w.d_lidx, sizeof(unsigned short) * ((size_t)A->nnz + 8)));
+    WinBuildArgs a;
+    a.rp = A->d_rp; a.col = A->d_col; a.n_rows = A->n_rows; a.n_owned = A->n_cols; a.R = R; a.sort_cap = sort_cap;
+    a.seg_start = w.d_seg_start; a.seg_len = w.d_seg_len; a.seg_off = w.d_seg_off; a.nseg = w.d_nseg;
+    a.lidx = w.d_lidx; a.status = d_status;
+    const size_t smem = sizeof(int) * (size_t)sort_cap;
+    if (A->rp_bytes == 8) {
+        BIS_CUDA(cudaFuncSetAttribute(win_build_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        win_build_kernel<int64_t><<<(unsigned)n_tiles, WIN_BUILD_THREADS, smem, c->stream>>>(a);
+    } else {
+        BIS_CUDA(cudaFuncSetAttribute(win_build_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        win_build_kernel<int32_t><<<(unsigned)n_tiles, WIN_BUILD_THREADS, smem, c->stream>>>(a);
+    }
+    BIS_LAUNCH_CHECK(c);
+    int status[2] = {0, 0};
+    BIS_CUDA(cudaMemcpyAsync(status, d_status, sizeof status, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_status);
+    if (status[1] != 0) {
+        win_free(const_cast<bis_matrix *>(A));
+        return 0;
+    }
+    w.R = R;
+    w.cap = (R * A->max_row + 16 + 7) & ~7;
+    w.xcap = (status[0] + 1) & ~1;
+    if (w.xcap < 2) w.xcap = 2;
+    w.n_tiles = n_tiles;
+    w.state = 1;
+    return 0;
+}
+
+struct WinPlan {
+    int nstage;
+    int stage_bytes;
+    size_t smem_bytes;
+};
+
+bool win_plan(const bis_context *c, const bis_matrix *A, WinPlan *p) {
+    const WinFormat &w = A->win;
+    size_t stage = (size_t)w.cap * 8 + (size_t)w.xcap * 8 + (size_t)(w.R + 4) * 8 + (size_t)w.cap * 2;
+    stage = (stage + 127) & ~(size_t)127;
+    const size_t budget = (size_t)(c->opt_spmv_smem_kb > 0 ? c->opt_spmv_smem_kb : 110) << 10;
+    int nstage = (int)((budget - 128) / stage);
+    const int max_stages = c->opt_spmv_stages > 0 ? c->opt_spmv_stages : 4;
+    if (nstage > max_stages) nstage = max_stages;
+    if (nstage > tma::MAX_STAGES) nstage = tma::MAX_STAGES;
+    if (nstage < 2) {
+        if (128 + 2 * stage > ((size_t)220 << 10)) return false;
+        nstage = 2;
+    }
+    while (nstage > 2 && w.R * nstage + 32 > 544) --nstage;      // kernel's launch bound
+    if (w.R * nstage + 32 > 544) return false;
+    p->nstage = nstage;
+    p->stage_bytes = (int)stage;
+    p->smem_bytes = 128 + stage * nstage;
+    return true;
+}
+
+template <typename RP, class Epi>
+int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const double *x, int64_t tile_lo,
+               int64_t tile_cnt, const Epi &epi, RedArgs &ra, int *nb) {
+    auto kern = spmv_win_kernel<RP, Epi>;
+    static size_t configured = 0;
+    if (configured < p.smem_bytes) {
+        BIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        configured = p.smem_bytes;
+    }
+    const WinFormat &w = A->win;
+    const int threads = w.R * p.nstage + 32;          // one consumer group per stage + the producer warp
+    int occ = 1;
+    BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, p.smem_bytes));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)c->sm_count * occ;
+    if (grid > tile_cnt) grid = tile_cnt;
+    if (grid < 1) grid = 1;
+    SpmvWinIn in;
+    in.rp = A->d_rp; in.val = A->d_val; in.lidx = w.d_lidx;
+    in.seg_start = w.d_seg_start; in.seg_len = w.d_seg_len; in.seg_off = w.d_seg_off; in.nseg = w.d_nseg;
+    in.x = x; in.ghost = A->halo.d_ghost; in.n_rows = A->n_rows;
+    in.tile_lo = tile_lo; in.tile_cnt = tile_cnt;
+    in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.stage_bytes = p.stage_bytes;
+    in.debug = c->opt_spmv_debug;
+    *nb = (int)grid;
+    if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + (int)grid;
+    kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra);
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}
+
+} // namespace
+
 // Shared driver: halo exchange (distributed) overlapped with the interior rows.
 template <class Epi>
 static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, const Epi &epi,
@@ -278,30 +403,50 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     BIS_REQUIRE(c && A && x, "spmv: null argument");
     BIS_CUDA(cudaSetDevice(c->device));
     RedArgs ra = bis_red_args(c, slot_a, slot_b);
+    // variant: 3 (windowed x) when the matrix is representable and x is 16-byte aligned (the reference
+    // offsets x, gmres.hpp:168: &V[k*N] with odd N is not), else 2 (TMA tiles + gathers), else 1
+    bool use_win = false;
+    WinPlan wplan;
+    if ((c->opt_spmv_variant == 0 || c->opt_spmv_variant == 3) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        BIS_CHECK(win_build(c, A));
+        use_win = A->win.state == 1 && win_plan(c, A, &wplan);
+    }
+    BIS_REQUIRE(use_win || c->opt_spmv_variant != 3,
+                "spmv_variant=3 forced, but the matrix has no window representation or x is not 16-byte aligned");
     BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPMV));
+    // work list: row ranges (variants 1, 2) or tile ranges (variant 3); `ghost` = needs the halo
     Segment seg[3];
     int nseg = 0;
-    bool halo = A->distributed && A->halo.n_ghost > 0;
+    const bool halo = A->distributed && A->halo.n_ghost > 0;
+    const int64_t unit = use_win ? A->win.R : 1;
+    const int64_t n_units = use_win ? A->win.n_tiles : A->n_rows;
     if (!halo) {
-        seg[nseg++] = {0, A->n_rows, false};
+        seg[nseg++] = {0, n_units, false};
     } else {
-        // rows [interior_begin, interior_end) touch no ghost column: they run
-        // while the halo is in flight, then the two boundary strips.
+        // rows [interior_begin, interior_end) touch no ghost column: they run while the halo is
+        // in flight, then the boundary strips (variant 3: whole tiles inside the interior).
         BIS_CHECK(bis_halo_exchange_begin(c, A, x));
-        const int64_t ib = A->halo.interior_begin, ie = A->halo.interior_end;
+        const int64_t ib = (A->halo.interior_begin + unit - 1) / unit, ie = A->halo.interior_end / unit;
         if (ie > ib) {
             seg[nseg++] = {ib, ie - ib, false};
             if (ib > 0) seg[nseg++] = {0, ib, true};
-            if (A->n_rows > ie) seg[nseg++] = {ie, A->n_rows - ie, true};
+            if (n_units > ie) seg[nseg++] = {ie, n_units - ie, true};
         } else {
-            seg[nseg++] = {0, A->n_rows, true};
+            seg[nseg++] = {0, n_units, true};
         }
     }
     for (int i = 0; i < nseg; ++i) {
         if (halo && seg[i].ghost && (i == 0 || !seg[i - 1].ghost)) BIS_CHECK(bis_halo_exchange_end(c, A));
         int nb = 0;
         ra.finalize = (i == nseg - 1) ? 1 : 0;
-        BIS_CHECK(launch_segment(c, A, x, seg[i], epi, ra, &nb));
+        if (use_win) {
+            if (A->rp_bytes == 8)
+                BIS_CHECK((launch_win<int64_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, epi, ra, &nb)));
+            else
+                BIS_CHECK((launch_win<int32_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, epi, ra, &nb)));
+        } else {
+            BIS_CHECK(launch_segment(c, A, x, seg[i], epi, ra, &nb));
+        }
         ra.block_offset += nb;
     }
     BIS_CHECK(bis_prof_end(c, BIS_PROF_SPMV));

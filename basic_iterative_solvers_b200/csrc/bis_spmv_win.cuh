@@ -1,0 +1,321 @@
+// bis_spmv_win.cuh -- SpMV variant 3: everything a tile needs arrives by TMA,
+// x included ("windowed x").
+//
+// Variant 2 (bis_spmv_tma.cuh) still gathers x[col] from global memory; its ncu
+// profile shows the SM waiting on exactly those gathers (long_scoreboard on the
+// consuming DMUL) and the L1 data pipe ~80 % busy.  Here the x values a tile of R
+// rows touches are described ONCE per matrix as a short list of contiguous column
+// windows (a 27-point stencil tile needs 9 windows of R+2 values), and every
+// nonzero gets a 16-bit index into the tile's concatenated windows.  A producer
+// warp then fetches, per tile, val[], lidx[], the row_ptr slice and the x windows
+// with bulk copies (cp.async.bulk -> mbarrier complete_tx); consumer warps wait on
+// the "full" barrier, walk one row per thread entirely out of shared memory --
+// in-order unfused multiply/add, the reference's summation order, bit-identical to
+// native_spmv (kernels.hpp:22-42) -- and release the stage through an "empty"
+// barrier.  No thread ever waits on a global load inside the tile loop.
+//
+// HBM bytes per nonzero drop from 12 (val + col) to 10 (val + lidx); the windows
+// are re-read from L2.  The tile format is an acceleration structure derived from
+// the CRS arrays, which stay resident and authoritative; matrices whose tiles need
+// more than WIN_MAXSEG windows (unstructured sparsity) keep using variant 2.
+#pragma once
+
+#include "bis_device.cuh"
+#include "bis_spmv_tma.cuh"
+
+constexpr int WIN_MAXSEG = 28;       // x windows per tile (one producer lane each)
+constexpr int WIN_GAP = 8;           // columns closer than this share a window
+constexpr int WIN_BUILD_THREADS = 256;
+
+// ---- build: one CTA per tile ---------------------------------------------------------------
+struct WinBuildArgs {
+    const void *rp;
+    const int *col;
+    int64_t n_rows;
+    int64_t n_owned;      // columns >= n_owned are ghosts (separate base pointer)
+    int R;
+    int sort_cap;         // power of two >= max nonzeros per tile
+    int *seg_start;       // [n_tiles * WIN_MAXSEG]  >= 0: owned column ; < 0: ~ghost index
+    unsigned short *seg_len;   // [n_tiles * WIN_MAXSEG] doubles (even)
+    unsigned short *seg_off;   // [n_tiles * WIN_MAXSEG] offset into the tile's window buffer
+    int *nseg;            // [n_tiles]
+    unsigned short *lidx; // [nnz]
+    int *status;          // [0] = max window length over tiles, [1] = 1 if some tile is not representable
+};
+
+template <typename RP>
+__global__ void __launch_bounds__(WIN_BUILD_THREADS) win_build_kernel(WinBuildArgs a) {
+    extern __shared__ int s_keys[];                 // [sort_cap]
+    __shared__ int s_start[WIN_MAXSEG + 1];         // aligned first column (global numbering) of each window
+    __shared__ int s_end[WIN_MAXSEG + 1];           // aligned one-past-last
+    __shared__ int s_off[WIN_MAXSEG + 1];
+    __shared__ int s_n;
+    const RP *__restrict__ rp = static_cast<const RP *>(a.rp);
+    const int64_t tile = blockIdx.x;
+    const int64_t r0 = tile * a.R;
+    int64_t r1 = r0 + a.R;
+    if (r1 > a.n_rows) r1 = a.n_rows;
+    const int64_t s = (int64_t)rp[r0], e = (int64_t)rp[r1];
+    const int m = (int)(e - s);
+    for (int i = threadIdx.x; i < a.sort_cap; i += blockDim.x) s_keys[i] = i < m ? a.col[s + i] : 0x7fffffff;
+    __syncthreads();
+    // bitonic sort, ascending
+    for (int k = 2; k <= a.sort_cap; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < a.sort_cap; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int x = s_keys[i], y = s_keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        s_keys[i] = y;
+                        s_keys[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // windows: maximal runs of sorted columns with gaps <= WIN_GAP, never across the owned/ghost border;
+    // each window is widened to even bounds relative to its base pointer (16-byte bulk copies)
+    if (threadIdx.x == 0) {
+        int n = 0, off = 0;
+        bool bad = false;
+        const int no = (int)a.n_owned;
+        int i = 0;
+        while (i < m) {
+            const int first = s_keys[i];
+            int last = first;
+            int j = i + 1;
+            while (j < m) {
+                const int c = s_keys[j];
+                if (c - last > WIN_GAP) break;
+                if (last < no && c >= no) break;
+                last = c;
+                ++j;
+            }
+            const int base = first >= no ? no : 0;
+            const int lo = base + ((first - base) & ~1);
+            const int hi = base + ((last - base + 2) & ~1);      // one past, even
+            if (n >= WIN_MAXSEG) {
+                bad = true;
+                break;
+            }
+            s_start[n] = lo;
+            s_end[n] = hi;
+            s_off[n] = off;
+            off += hi - lo;
+            ++n;
+            i = j;
+        }
+        if (off > 65534) bad = true;
+        s_n = bad ? -1 : n;
+        if (bad) atomicExch(a.status + 1, 1);
+        else atomicMax(a.status, off);
+        a.nseg[tile] = bad ? 0 : n;
+        for (int q = 0; q < WIN_MAXSEG; ++q) {
+            const bool live = !bad && q < n;
+            const int lo = live ? s_start[q] : 0;
+            a.seg_start[tile * WIN_MAXSEG + q] = !live ? 0 : (lo >= no ? ~(lo - no) : lo);
+            a.seg_len[tile * WIN_MAXSEG + q] = (unsigned short)(live ? s_end[q] - lo : 0);
+            a.seg_off[tile * WIN_MAXSEG + q] = (unsigned short)(live ? s_off[q] : 0);
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n < 0) return;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int c = a.col[s + i];
+        int lo = 0, hi = n - 1;            // last window whose start <= c
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_start[mid] <= c) lo = mid;
+            else hi = mid - 1;
+        }
+        a.lidx[s + i] = (unsigned short)(s_off[lo] + (c - s_start[lo]));
+    }
+}
+
+// ---- SpMV ----------------------------------------------------------------------------------------
+struct SpmvWinIn {
+    const void *rp;
+    const double *val;
+    const unsigned short *lidx;
+    const int *seg_start;
+    const unsigned short *seg_len;
+    const unsigned short *seg_off;
+    const int *nseg;
+    const double *x;
+    const double *ghost;
+    int64_t n_rows;
+    int64_t tile_lo, tile_cnt;    // tiles handled by this launch
+    int R;                        // rows per tile == consumer threads
+    int cap;                      // nonzeros per stage (multiple of 8)
+    int xcap;                     // window doubles per stage (even)
+    int nstage;
+    int stage_bytes;
+    int debug;                    // perf experiments only (results invalid): 1 = consumers skip the row walk, 2 = no x-window copies
+};
+
+// stage layout: [val cap*8][xwin xcap*8][rp (R+4)*8][lidx cap*2], every part 16-byte aligned
+template <typename RP, class Epi>
+__global__ void __launch_bounds__(544) spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);            // [MAX_STAGES]
+    uint64_t *empty = full + tma::MAX_STAGES;                           // [MAX_STAGES]
+    unsigned char *stages = smem_raw + 128;
+    const int R = in.R;
+    // one consumer GROUP (R threads) per stage: group g computes the tiles that land in stage g, so
+    // while one group walks its rows the next tile's group is already waiting on its own barrier and
+    // starts the moment its copies land -- nstage tiles can be in the compute phase at once
+    const int n_cons_warps = R >> 5;                  // per group
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool producer = warp == n_cons_warps * in.nstage;       // the last warp
+    const int group = warp / n_cons_warps;
+    const int tid_g = (int)threadIdx.x - group * R;   // thread index inside its group
+    // static tile -> CTA map: CTA b takes tiles b, b + grid, ... (all CTAs sweep the matrix together,
+    // so the x windows they fetch are shared in L2)
+    const int64_t my_tiles = in.tile_cnt > blockIdx.x ? (in.tile_cnt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    double acc[Epi::NRED > 0 ? Epi::NRED : 1];
+#pragma unroll
+    for (int q = 0; q < (Epi::NRED > 0 ? Epi::NRED : 1); ++q) acc[q] = 0.0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < in.nstage; ++s) {
+            tma::mbar_init(&full[s], 1);
+            tma::mbar_init(&empty[s], n_cons_warps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (producer) {
+        const RP *__restrict__ rp = static_cast<const RP *>(in.rp);
+        const uint64_t pol_stream = tma::policy_evict_first();
+        uint64_t pol_keep;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        // What this lane copies for one tile: lane 0 val, lane 1 lidx, lane 2 the row_ptr slice,
+        // lanes 3.. one x window each.  The descriptors come from global memory (row_ptr and the
+        // window table), so they are requested PDEPTH tiles ahead: the producer never sits on a
+        // global-load latency between two tiles.
+        // Raw descriptor words are only LOADED ahead of time; nothing is computed from them until
+        // the tile is issued (a dependent instruction right after the load would stall the warp for
+        // a full memory latency per tile and serialise the whole pipeline).
+        struct Desc {
+            int64_t a, b;      // lanes 0,1: rp[r0], rp[r1] ; lane 2: r0, r1 ; lanes 3..: window start, len | off << 16
+        };
+        const uint32_t off_xw = (uint32_t)in.cap * 8u;
+        const uint32_t off_rp = off_xw + (uint32_t)in.xcap * 8u;
+        const uint32_t off_li = off_rp + (uint32_t)(R + 4) * 8u;
+        auto load_desc = [&](int64_t j, Desc &d) {
+            d.a = 0;
+            d.b = 0;
+            if (j >= my_tiles) return;
+            const int64_t tile = in.tile_lo + blockIdx.x + j * gridDim.x;
+            const int64_t r0 = tile * R;
+            int64_t r1 = r0 + R;
+            if (r1 > in.n_rows) r1 = in.n_rows;
+            if (lane < 2) {
+                d.a = (int64_t)rp[r0];
+                d.b = (int64_t)rp[r1];
+            } else if (lane == 2) {
+                d.a = r0;
+                d.b = r1;
+            } else if (lane - 3 < WIN_MAXSEG) {
+                const int64_t q = tile * WIN_MAXSEG + (lane - 3);
+                d.a = in.seg_start[q];
+                d.b = (int64_t)in.seg_len[q] | ((int64_t)in.seg_off[q] << 16);
+            }
+        };
+        auto issue = [&](int64_t j, const Desc &d) {
+            const int st = (int)(j % in.nstage);
+            const void *src = nullptr;
+            uint32_t bytes = 0, dst = 0;
+            if (lane < 2) {
+                const int64_t s_al = d.a & ~(int64_t)7;
+                const uint32_t n_el = (uint32_t)(((d.b + 7) & ~(int64_t)7) - s_al);
+                if (lane == 0) {
+                    src = in.val + s_al;
+                    bytes = n_el * 8u;
+                } else {
+                    src = in.lidx + s_al;
+                    bytes = n_el * 2u;
+                    dst = off_li;
+                }
+            } else if (lane == 2) {
+                src = rp + d.a;
+                bytes = (uint32_t)(((d.b - d.a + 1) + 3) & ~(int64_t)3) * (uint32_t)sizeof(RP);
+                dst = off_rp;
+            } else {
+                const uint32_t len = (uint32_t)(d.b & 0xffff);
+                if (len && !(in.debug & 2)) {
+                    const int start = (int)d.a;
+                    src = start >= 0 ? in.x + start : in.ghost + (~start);
+                    bytes = len * 8u;
+                    dst = off_xw + (uint32_t)((d.b >> 16) & 0xffff) * 8u;
+                }
+            }
+            uint32_t total = bytes;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            // the stage must have been released by every consumer warp
+            if (j >= in.nstage) tma::mbar_wait(&empty[st], (uint32_t)(((j / in.nstage) - 1) & 1));
+            unsigned char *sb = stages + (size_t)st * in.stage_bytes;
+            if (lane == 0) tma::mbar_expect_tx(&full[st], total);
+            __syncwarp();
+            if (bytes) tma::bulk_g2s(sb + dst, src, bytes, &full[st], lane < 3 ? pol_stream : pol_keep);
+        };
+        constexpr int PDEPTH = 4;
+        Desc d0, d1, d2, d3;
+        load_desc(0, d0);
+        load_desc(1, d1);
+        load_desc(2, d2);
+        load_desc(3, d3);
+        for (int64_t j = 0; j < my_tiles; j += PDEPTH) {
+            issue(j, d0);
+            load_desc(j + PDEPTH, d0);
+            if (j + 1 < my_tiles) issue(j + 1, d1);
+            load_desc(j + PDEPTH + 1, d1);
+            if (j + 2 < my_tiles) issue(j + 2, d2);
+            load_desc(j + PDEPTH + 2, d2);
+            if (j + 3 < my_tiles) issue(j + 3, d3);
+            load_desc(j + PDEPTH + 3, d3);
+        }
+    } else {
+        for (int64_t j = group; j < my_tiles; j += in.nstage) {
+            const int st = group;
+            const int64_t tile = in.tile_lo + blockIdx.x + j * gridDim.x;
+            const int64_t row = tile * R + tid_g;
+            const unsigned char *sb = stages + (size_t)st * in.stage_bytes;
+            const double *__restrict__ sval = reinterpret_cast<const double *>(sb);
+            const double *__restrict__ sxw = sval + in.cap;
+            const RP *__restrict__ srp = reinterpret_cast<const RP *>(sxw + in.xcap);
+            const unsigned short *__restrict__ sli =
+                reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(srp) + (size_t)(R + 4) * 8);
+            tma::mbar_wait(&full[st], (uint32_t)((j / in.nstage) & 1));
+            if (row < in.n_rows && !(in.debug & 1)) {
+                const int64_t base = (int64_t)srp[0] & ~(int64_t)7;
+                const int ks = (int)((int64_t)srp[tid_g] - base);
+                const int ke = (int)((int64_t)srp[tid_g + 1] - base);
+                double sum = 0.0;
+                int k = ks;
+                for (; k + 9 <= ke; k += 9) {
+                    double a[9], xv[9];
+#pragma unroll
+                    for (int u = 0; u < 9; ++u) {
+                        a[u] = sval[k + u];
+                        xv[u] = sxw[sli[k + u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 9; ++u) sum = add_rn(sum, mul_rn(a[u], xv[u]));
+                }
+                for (; k < ke; ++k) sum = add_rn(sum, mul_rn(sval[k], sxw[sli[k]]));
+                epi(row, sum, acc);
+            }
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty[st]);
+        }
+    }
+    if constexpr (Epi::NRED > 0) block_reduce_finish<Epi::NRED>(acc, ra);
+}

@@ -35,11 +35,12 @@ def f64(*a):
     return np.array(a, np.float64)
 
 
-def run_spmv(ctx, rp, col, val, x, lanes=0, **opts):
-    """lanes = 0: default variant (TMA-staged, thread per row, in-order sums: bit-exact);
-    lanes > 0: the vector-CRS variant with that many lanes per row (tolerance only)."""
+def run_spmv(ctx, rp, col, val, x, lanes=0, variant=None, **opts):
+    """variant 0 (default): auto = 3 (windowed x, all operands by TMA) when the matrix is representable,
+    else 2 (TMA-staged CRS tiles + x gathers); both add the products in storage order: bit-exact.
+    lanes > 0: variant 1, vector CRS with that many lanes per row (tolerance only)."""
     A = ctx.upload_crs(rp, col, val)
-    ctx.set_option("spmv_variant", 1 if lanes else 0)
+    ctx.set_option("spmv_variant", (1 if lanes else 0) if variant is None else variant)
     for k, v in opts.items():
         ctx.set_option(k, v)
     ctx.set_option("spmv_lanes", lanes)
@@ -129,8 +130,42 @@ def test_spmv_tma_tile_shapes_bit_exact(ctx, rows, stages, smem_kb):
         col = rng.integers(0, n, rp[-1]).astype(np.int32)
         val = rng.uniform(-1, 1, rp[-1])
         x = rng.uniform(-1, 1, n)
-        got = run_spmv(ctx, rp, col, val, x, 0, spmv_rows=rows, spmv_stages=stages, spmv_smem_kb=smem_kb)
+        got = run_spmv(ctx, rp, col, val, x, 0, variant=2, spmv_rows=rows, spmv_stages=stages, spmv_smem_kb=smem_kb)
         assert np.array_equal(got, port.spmv(rp.astype(np.int32), col, val, x))
+
+
+@pytest.mark.parametrize("rows,stages,smem_kb", [(0, 0, 0), (32, 2, 0), (64, 3, 0), (128, 2, 0), (256, 2, 200), (128, 4, 200)])
+@pytest.mark.parametrize("dims", [(24, 20, 17), (7, 5, 3), (130, 3, 2)])
+def test_spmv_windowed_bit_exact(ctx, rows, stages, smem_kb, dims):
+    """Variant 3 (x windows + 16-bit local column ids, producer warp + mbarrier full/empty pipeline) on
+    stencil matrices, forced (spmv_variant=3 fails loudly if the matrix is not representable): every tile
+    shape and pipeline depth gives the reference's bits, 32- and 64-bit row_ptr, odd sizes."""
+    rp, col, val = matgen.hpcg(*dims)
+    x = np.random.default_rng(3).uniform(-1, 1, len(rp) - 1)
+    want = port.spmv(rp, col, val, x)
+    for r in (rp, rp.astype(np.int64)):
+        got = run_spmv(ctx, r, col, val, x, 0, variant=3, win_rows=rows, spmv_stages=stages, spmv_smem_kb=smem_kb)
+        assert np.array_equal(got, want)
+
+
+def test_spmv_windowed_anderson_periodic_and_fallback(ctx):
+    """Periodic Anderson rows wrap around (far-away columns: more windows per tile); unstructured
+    matrices are not representable: auto falls back to variant 2, forcing variant 3 is an error."""
+    rp, col, val = matgen.anderson(12, 10, 9, 5.0, 1.0, 7, True)
+    x = np.random.default_rng(5).uniform(-1, 1, len(rp) - 1)
+    assert np.array_equal(run_spmv(ctx, rp, col, val, x, 0, variant=3), port.spmv(rp, col, val, x))
+    rng = np.random.default_rng(6)
+    n = 4000
+    lens = rng.integers(1, 20, n)
+    rp = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=rp[1:])
+    col = rng.integers(0, n, rp[-1]).astype(np.int32)
+    val = rng.uniform(-1, 1, rp[-1])
+    x = rng.uniform(-1, 1, n)
+    assert np.array_equal(run_spmv(ctx, rp, col, val, x, 0), port.spmv(rp, col, val, x))
+    with pytest.raises(capi.BisError):
+        run_spmv(ctx, rp, col, val, x, 0, variant=3)
+    ctx.set_option("spmv_variant", 0)
 
 
 def test_spmv_ragged_empty_rows_and_64bit_rowptr(ctx):

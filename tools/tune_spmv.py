@@ -31,11 +31,9 @@ with capi.Context(0) as ctx:
         for k in opts:
             ctx.set_option(k, 0)
 
-    for lanes in (4, 8, 16):
-        run(f"vector lanes={lanes}", spmv_variant=1, spmv_lanes=lanes)
-    for blocked in (0, 1):
-        for rows, stages, kb, mult in ((256, 2, 0, 1), (256, 2, 0, 2), (256, 2, 0, 4), (128, 2, 100, 2), (128, 2, 100, 4),
-                                       (128, 2, 100, 8), (64, 2, 50, 2), (64, 2, 50, 4), (128, 4, 0, 4), (128, 4, 0, 8),
-                                       (64, 2, 70, 4), (64, 3, 70, 4)):
-            run(f"tma rows={rows} stages<={stages} smem_kb={kb or 200} mult={mult} blocked={blocked}", spmv_rows=rows,
-                spmv_stages=stages, spmv_smem_kb=kb, spmv_blocked=blocked, spmv_mult=mult)
+    run("default (auto)")
+    for stages, kb in ((2, 0), (3, 0), (2, 75), (3, 150), (4, 200)):
+        run(f"win (variant 3) stages<={stages} smem_kb={kb or 110}", spmv_variant=3, spmv_stages=stages, spmv_smem_kb=kb)
+    run("win, debug=1 no compute (supply ceiling; result invalid)", spmv_variant=3, spmv_debug=1)
+    run("win, debug=2 no x copies (result invalid)", spmv_variant=3, spmv_debug=2)
+    run("tma (variant 2) default", spmv_variant=2)
