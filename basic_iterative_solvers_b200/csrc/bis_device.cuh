@@ -15,6 +15,11 @@ __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
+// per-row operands an SpMV epilogue fetches ahead of time (bis_spmv.cu: Epi*::load)
+struct EpiPre {
+    double a, b, c;
+};
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)

@@ -38,18 +38,22 @@ struct SpmvIn {
     int64_t lo1, cnt1, lo2, cnt2;
 };
 
+// Epilogues.  load(r) fetches the per-row operands (issued BEFORE the row's sum is available so
+// that their latency overlaps the tile wait / row walk); operator() consumes them.
 struct EpiStore {
     static constexpr int NRED = 0;
     double *y;
-    __device__ __forceinline__ void operator()(int64_t r, double s, double *) const { y[r] = s; }
+    __device__ __forceinline__ EpiPre load(int64_t) const { return EpiPre{0.0, 0.0, 0.0}; }
+    __device__ __forceinline__ void operator()(int64_t r, double s, const EpiPre &, double *) const { y[r] = s; }
 };
 struct EpiDot {
     static constexpr int NRED = 2;
     double *y;
     const double *w;
-    __device__ __forceinline__ void operator()(int64_t r, double s, double *acc) const {
+    __device__ __forceinline__ EpiPre load(int64_t r) const { return EpiPre{w[r], 0.0, 0.0}; }
+    __device__ __forceinline__ void operator()(int64_t r, double s, const EpiPre &p, double *acc) const {
         y[r] = s;
-        acc[0] = fma(s, w[r], acc[0]);
+        acc[0] = fma(s, p.a, acc[0]);
         acc[1] = fma(s, s, acc[1]);
     }
 };
@@ -58,9 +62,10 @@ struct EpiResid {
     const double *b;
     double *res;
     double *tmp;
-    __device__ __forceinline__ void operator()(int64_t r, double s, double *acc) const {
+    __device__ __forceinline__ EpiPre load(int64_t r) const { return EpiPre{b[r], 0.0, 0.0}; }
+    __device__ __forceinline__ void operator()(int64_t r, double s, const EpiPre &p, double *acc) const {
         if (tmp) tmp[r] = s;
-        double v = sub_rn(b[r], s);   // subtract_vectors with scale 1.0
+        double v = sub_rn(p.a, s);   // subtract_vectors with scale 1.0
         res[r] = v;
         acc[0] = fma(v, v, acc[0]);
     }
@@ -69,19 +74,20 @@ struct EpiJacobi {
     static constexpr int NRED = 0;
     const double *D, *b, *x_old;
     double *x_new;
-    __device__ __forceinline__ void operator()(int64_t r, double s, double *) const {
-        double d = D[r];
-        double scaled = mul_rn(d, x_old[r]);
+    __device__ __forceinline__ EpiPre load(int64_t r) const { return EpiPre{D[r], x_old[r], b[r]}; }
+    __device__ __forceinline__ void operator()(int64_t r, double s, const EpiPre &p, double *) const {
+        double scaled = mul_rn(p.a, p.b);
         double adj = sub_rn(s, scaled);
-        x_new[r] = div_rn(sub_rn(b[r], adj), d);
+        x_new[r] = div_rn(sub_rn(p.c, adj), p.a);
     }
 };
 struct EpiSub {
     static constexpr int NRED = 0;
     const double *b;
     double *out;
-    __device__ __forceinline__ void operator()(int64_t r, double s, double *) const {
-        out[r] = sub_rn(b[r], s);
+    __device__ __forceinline__ EpiPre load(int64_t r) const { return EpiPre{b[r], 0.0, 0.0}; }
+    __device__ __forceinline__ void operator()(int64_t r, double s, const EpiPre &p, double *) const {
+        out[r] = sub_rn(p.a, s);
     }
 };
 
@@ -123,7 +129,7 @@ spmv_vec_kernel(SpmvIn in, Epi epi, RedArgs ra) {
         }
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, LPR);
-        if (live && sub == 0) epi(r, sum, acc);
+        if (live && sub == 0) epi(r, sum, epi.load(r), acc);
     }
     if constexpr (Epi::NRED > 0) block_reduce_finish<Epi::NRED>(acc, ra);
 }
@@ -290,8 +296,8 @@ int win_build(bis_context *c, const bis_matrix *A) {
     w.state = -1;
     if (A->n_rows == 0 || A->nnz == 0 || A->max_row < 1) return 0;
     int R = c->opt_win_rows;
-    if (R != 32 && R != 64 && R != 128 && R != 256) {
-        R = 256;
+    if (R != 32 && R != 64 && R != 128) {
+        R = 128;
         while (R > 32 && (size_t)R * A->max_row * 10 > (size_t)40 << 10) R >>= 1;   // ~<= 40 KB of val+lidx per stage
     }
     if ((size_t)R * A->max_row * 10 > (size_t)96 << 10) return 0;                     // rows too long for a tile
@@ -355,8 +361,8 @@ bool win_plan(const bis_context *c, const bis_matrix *A, WinPlan *p) {
         if (128 + 2 * stage > ((size_t)220 << 10)) return false;
         nstage = 2;
     }
-    while (nstage > 2 && w.R * nstage + 32 > 544) --nstage;      // kernel's launch bound
-    if (w.R * nstage + 32 > 544) return false;
+    while (nstage > 2 && w.R * nstage + 32 > WIN_MAX_THREADS) --nstage;      // kernel's launch bound
+    if (w.R * nstage + 32 > WIN_MAX_THREADS) return false;
     p->nstage = nstage;
     p->stage_bytes = (int)stage;
     p->smem_bytes = 128 + stage * nstage;

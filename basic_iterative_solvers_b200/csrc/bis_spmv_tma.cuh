@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(1024) spmv_tma_kernel(SpmvTmaIn in, Epi epi, R
         tile_range(j + 1, nts, nte);
         row_bounds(j + 1, nks, nke, nrow);
         if (threadIdx.x == 0) tile_range(j + in.nstage, is, ie);
+        EpiPre pre{0.0, 0.0, 0.0};
+        if (row >= 0) pre = epi.load(row);   // in flight during the wait and both phases
         tma::mbar_wait(&bars[st], parity);
 
         const int64_t base = ts & ~(int64_t)3;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(1024) spmv_tma_kernel(SpmvTmaIn in, Epi epi, R
                 for (int u = 0; u < 9; ++u) sum = add_rn(sum, p[u]);
             }
             for (; k < b; ++k) sum = add_rn(sum, sv[k]);
-            epi(row, sum, acc);
+            epi(row, sum, pre, acc);
         }
         __syncthreads();   // every thread is done with stage `st`
         if (threadIdx.x == 0 && j + in.nstage < my_tiles) {

@@ -158,8 +158,10 @@ struct SpmvWinIn {
 };
 
 // stage layout: [val cap*8][xwin xcap*8][rp (R+4)*8][lidx cap*2], every part 16-byte aligned
+constexpr int WIN_MAX_THREADS = 320;   // consumer groups (R x nstage) + the producer warp
+
 template <typename RP, class Epi>
-__global__ void __launch_bounds__(544) spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra) {
+__global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);            // [MAX_STAGES]
     uint64_t *empty = full + tma::MAX_STAGES;                           // [MAX_STAGES]
@@ -203,38 +205,48 @@ __global__ void __launch_bounds__(544) spmv_win_kernel(SpmvWinIn in, Epi epi, Re
         // the tile is issued (a dependent instruction right after the load would stall the warp for
         // a full memory latency per tile and serialise the whole pipeline).
         struct Desc {
-            int64_t a, b;      // lanes 0,1: rp[r0], rp[r1] ; lane 2: r0, r1 ; lanes 3..: window start, len | off << 16
+            RP a, b;                 // rp[r0], rp[r1]            (lanes 0, 1)
+            int start;               // window start              (lanes 3..)
+            unsigned short len, off; // window length / offset    (lanes 3..)
         };
         const uint32_t off_xw = (uint32_t)in.cap * 8u;
         const uint32_t off_rp = off_xw + (uint32_t)in.xcap * 8u;
         const uint32_t off_li = off_rp + (uint32_t)(R + 4) * 8u;
+        auto tile_rows = [&](int64_t j, int64_t &tile, int64_t &r0, int64_t &r1) {
+            tile = in.tile_lo + blockIdx.x + j * gridDim.x;
+            r0 = tile * R;
+            r1 = r0 + R;
+            if (r1 > in.n_rows) r1 = in.n_rows;
+        };
+        // loads only -- no conversion, no arithmetic on the loaded words (see above)
         auto load_desc = [&](int64_t j, Desc &d) {
             d.a = 0;
             d.b = 0;
+            d.start = 0;
+            d.len = 0;
+            d.off = 0;
             if (j >= my_tiles) return;
-            const int64_t tile = in.tile_lo + blockIdx.x + j * gridDim.x;
-            const int64_t r0 = tile * R;
-            int64_t r1 = r0 + R;
-            if (r1 > in.n_rows) r1 = in.n_rows;
+            int64_t tile, r0, r1;
+            tile_rows(j, tile, r0, r1);
             if (lane < 2) {
-                d.a = (int64_t)rp[r0];
-                d.b = (int64_t)rp[r1];
-            } else if (lane == 2) {
-                d.a = r0;
-                d.b = r1;
-            } else if (lane - 3 < WIN_MAXSEG) {
+                d.a = rp[r0];
+                d.b = rp[r1];
+            } else if (lane >= 3 && lane - 3 < WIN_MAXSEG) {
                 const int64_t q = tile * WIN_MAXSEG + (lane - 3);
-                d.a = in.seg_start[q];
-                d.b = (int64_t)in.seg_len[q] | ((int64_t)in.seg_off[q] << 16);
+                d.start = in.seg_start[q];
+                d.len = in.seg_len[q];
+                d.off = in.seg_off[q];
             }
         };
         auto issue = [&](int64_t j, const Desc &d) {
             const int st = (int)(j % in.nstage);
+            int64_t tile, r0, r1;
+            tile_rows(j, tile, r0, r1);
             const void *src = nullptr;
             uint32_t bytes = 0, dst = 0;
             if (lane < 2) {
-                const int64_t s_al = d.a & ~(int64_t)7;
-                const uint32_t n_el = (uint32_t)(((d.b + 7) & ~(int64_t)7) - s_al);
+                const int64_t s_al = (int64_t)d.a & ~(int64_t)7;
+                const uint32_t n_el = (uint32_t)((((int64_t)d.b + 7) & ~(int64_t)7) - s_al);
                 if (lane == 0) {
                     src = in.val + s_al;
                     bytes = n_el * 8u;
@@ -244,17 +256,13 @@ __global__ void __launch_bounds__(544) spmv_win_kernel(SpmvWinIn in, Epi epi, Re
                     dst = off_li;
                 }
             } else if (lane == 2) {
-                src = rp + d.a;
-                bytes = (uint32_t)(((d.b - d.a + 1) + 3) & ~(int64_t)3) * (uint32_t)sizeof(RP);
+                src = rp + r0;
+                bytes = (uint32_t)(((r1 - r0 + 1) + 3) & ~(int64_t)3) * (uint32_t)sizeof(RP);
                 dst = off_rp;
-            } else {
-                const uint32_t len = (uint32_t)(d.b & 0xffff);
-                if (len && !(in.debug & 2)) {
-                    const int start = (int)d.a;
-                    src = start >= 0 ? in.x + start : in.ghost + (~start);
-                    bytes = len * 8u;
-                    dst = off_xw + (uint32_t)((d.b >> 16) & 0xffff) * 8u;
-                }
+            } else if (d.len && !(in.debug & 2)) {
+                src = d.start >= 0 ? in.x + d.start : in.ghost + (~d.start);
+                bytes = (uint32_t)d.len * 8u;
+                dst = off_xw + (uint32_t)d.off * 8u;
             }
             uint32_t total = bytes;
 #pragma unroll
@@ -293,6 +301,8 @@ __global__ void __launch_bounds__(544) spmv_win_kernel(SpmvWinIn in, Epi epi, Re
             const RP *__restrict__ srp = reinterpret_cast<const RP *>(sxw + in.xcap);
             const unsigned short *__restrict__ sli =
                 reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(srp) + (size_t)(R + 4) * 8);
+            EpiPre pre{0.0, 0.0, 0.0};
+            if (row < in.n_rows) pre = epi.load(row);   // in flight during the wait and the row walk
             tma::mbar_wait(&full[st], (uint32_t)((j / in.nstage) & 1));
             if (row < in.n_rows && !(in.debug & 1)) {
                 const int64_t base = (int64_t)srp[0] & ~(int64_t)7;
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(544) spmv_win_kernel(SpmvWinIn in, Epi epi, Re
                     for (int u = 0; u < 9; ++u) sum = add_rn(sum, mul_rn(a[u], xv[u]));
                 }
                 for (; k < ke; ++k) sum = add_rn(sum, mul_rn(sval[k], sxw[sli[k]]));
-                epi(row, sum, acc);
+                epi(row, sum, pre, acc);
             }
             __syncwarp();
             if (lane == 0) tma::mbar_arrive(&empty[st]);

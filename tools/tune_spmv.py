@@ -17,23 +17,38 @@ with capi.Context(0) as ctx:
     nbytes = A.spmv_bytes()
     print(f"HPCG-{n}: rows {inf['n_rows']} nnz {inf['nnz']} rp_bytes {inf['rp_bytes']} bytes/spmv {nbytes/1e9:.3f} GB")
 
+    w = ctx.alloc(inf["n_rows"])
+    ctx.call("bis_init_vector", w, 0.5, inf["n_rows"])
+    kind = {"v": "spmv"}
+
+    def launch():
+        if kind["v"] == "spmv":
+            ctx.call("bis_spmv", A.h, x, y)
+        elif kind["v"] == "dot_self":      # CG: w is x itself
+            ctx.call("bis_spmv_dot", A.h, x, y, x, 40, -1)
+        elif kind["v"] == "dot":
+            ctx.call("bis_spmv_dot", A.h, x, y, w, 40, 41)
+        elif kind["v"] == "resid":
+            ctx.call("bis_spmv_residual", A.h, x, w, y, None, 40)
+        elif kind["v"] == "jacobi":
+            ctx.call("bis_spmv_jacobi", A.h, w, w, x, y)
+        elif kind["v"] == "sub":
+            ctx.call("bis_spmv_sub", A.h, x, w, y)
+
     def run(label, **opts):
         for k, v in opts.items():
             ctx.set_option(k, v)
         for _ in range(2):
-            ctx.call("bis_spmv", A.h, x, y)
+            launch()
         ctx.sync()
         ctx.timer_start()
         for _ in range(reps):
-            ctx.call("bis_spmv", A.h, x, y)
+            launch()
         ms = ctx.timer_stop() / reps
         print(f"{label:55s} {ms:8.3f} ms  {nbytes/ms/1e6:8.1f} GB/s", flush=True)
         for k in opts:
             ctx.set_option(k, 0)
 
-    run("default (auto)")
-    for stages, kb in ((2, 0), (3, 0), (2, 75), (3, 150), (4, 200)):
-        run(f"win (variant 3) stages<={stages} smem_kb={kb or 110}", spmv_variant=3, spmv_stages=stages, spmv_smem_kb=kb)
-    run("win, debug=1 no compute (supply ceiling; result invalid)", spmv_variant=3, spmv_debug=1)
-    run("win, debug=2 no x copies (result invalid)", spmv_variant=3, spmv_debug=2)
-    run("tma (variant 2) default", spmv_variant=2)
+    for k in ("spmv", "sub", "jacobi", "resid", "dot", "dot_self"):
+        kind["v"] = k
+        run(f"{k}: default (auto)")
