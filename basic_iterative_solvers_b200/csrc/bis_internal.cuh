@@ -194,6 +194,8 @@ int bis_matrix_finalize_distributed(bis_context *ctx, bis_matrix *A,
                                     int *d_col_global_in_place);
 int bis_build_levels_device(bis_context *ctx, bis_matrix *T);
 int bis_matrix_stats(bis_context *ctx, bis_matrix *A);
+// builds the SpMV acceleration structure of a general matrix (bis_spmv.cu); lazy on first SpMV otherwise
+int bis_spmv_prepare(bis_context *ctx, const bis_matrix *A);
 int bis_prof_begin(bis_context *ctx, int tag);
 int bis_prof_end(bis_context *ctx, int tag);
 

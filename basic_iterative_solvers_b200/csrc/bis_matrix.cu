@@ -98,7 +98,8 @@ extern "C" int bis_matrix_upload_crs(bis_context *c, int64_t n_rows, int64_t n_c
                                      bis_matrix **A) {
     BIS_REQUIRE(!c || c->nranks == 1,
                 "bis_matrix_upload_crs: distributed context; use bis_matrix_upload_crs_distributed");
-    return upload_common<int32_t>(c, n_rows, n_cols, nnz, rp, col, val, A);
+    BIS_CHECK(upload_common<int32_t>(c, n_rows, n_cols, nnz, rp, col, val, A));
+    return bis_spmv_prepare(c, *A);
 }
 
 extern "C" int bis_matrix_upload_crs64(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz,
@@ -106,7 +107,8 @@ extern "C" int bis_matrix_upload_crs64(bis_context *c, int64_t n_rows, int64_t n
                                        bis_matrix **A) {
     BIS_REQUIRE(!c || c->nranks == 1,
                 "bis_matrix_upload_crs64: distributed context; use bis_matrix_upload_crs_distributed");
-    return upload_common<int64_t>(c, n_rows, n_cols, nnz, rp, col, val, A);
+    BIS_CHECK(upload_common<int64_t>(c, n_rows, n_cols, nnz, rp, col, val, A));
+    return bis_spmv_prepare(c, *A);
 }
 
 extern "C" int bis_matrix_upload_crs_distributed(bis_context *c, int64_t row_begin,
@@ -125,7 +127,7 @@ extern "C" int bis_matrix_upload_crs_distributed(bis_context *c, int64_t row_beg
         return 1;
     }
     *out = A;
-    return 0;
+    return bis_spmv_prepare(c, A);
 }
 
 // ---- level sets ---------------------------------------------------------------
@@ -389,7 +391,7 @@ int finish_generated(bis_context *c, bis_matrix *A, bis_matrix **out) {
     }
     BIS_CUDA(cudaStreamSynchronize(c->stream));
     *out = A;
-    return 0;
+    return bis_spmv_prepare(c, A);
 }
 
 } // namespace

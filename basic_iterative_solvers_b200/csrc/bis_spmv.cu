@@ -402,6 +402,11 @@ int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const doub
 
 } // namespace
 
+int bis_spmv_prepare(bis_context *c, const bis_matrix *A) {
+    if (c->opt_spmv_variant != 0 && c->opt_spmv_variant != 3) return 0;
+    return win_build(c, A);
+}
+
 // Shared driver: halo exchange (distributed) overlapped with the interior rows.
 template <class Epi>
 static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, const Epi &epi,

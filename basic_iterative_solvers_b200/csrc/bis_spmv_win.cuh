@@ -76,50 +76,80 @@ __global__ void __launch_bounds__(WIN_BUILD_THREADS) win_build_kernel(WinBuildAr
             __syncthreads();
         }
     }
-    // windows: maximal runs of sorted columns with gaps <= WIN_GAP, never across the owned/ghost border;
+    // windows: maximal runs of sorted columns with gaps <= WIN_GAP, never across the owned/ghost border.
+    // Parallel: every thread flags the run starts in its slice of the sorted keys, a block scan numbers
+    // the runs, the first / last key of each run is written by the thread that sees it.
+    __shared__ int s_warp[WIN_BUILD_THREADS / 32];
+    __shared__ int s_total;
+    const int no = (int)a.n_owned;
+    const int per = (a.sort_cap + WIN_BUILD_THREADS - 1) / WIN_BUILD_THREADS;
+    const int i0 = threadIdx.x * per, i1 = min(i0 + per, m);
+    auto is_start = [&](int i) {
+        if (i == 0) return true;
+        const int p = s_keys[i - 1], c = s_keys[i];
+        return (c - p > WIN_GAP) || (p < no && c >= no);
+    };
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += is_start(i) ? 1 : 0;
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)(threadIdx.x & 31) >= o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < WIN_BUILD_THREADS / 32; ++w) {
+            const int v = s_warp[w];
+            s_warp[w] = run;
+            run += v;
+        }
+        s_total = run;
+    }
+    __syncthreads();
+    const int n_runs = s_total;
+    const bool too_many = n_runs > WIN_MAXSEG;
+    if (!too_many) {
+        int idx = s_warp[threadIdx.x >> 5] + incl - cnt - 1;   // index of the run open at the slice start
+        for (int i = i0; i < i1; ++i) {
+            if (is_start(i)) {
+                ++idx;
+                s_start[idx] = s_keys[i];                       // first key of the run (aligned below)
+            }
+            if (i == m - 1 || is_start(i + 1)) s_end[idx] = s_keys[i];   // last key of the run
+        }
+    }
+    __syncthreads();
     // each window is widened to even bounds relative to its base pointer (16-byte bulk copies)
     if (threadIdx.x == 0) {
-        int n = 0, off = 0;
-        bool bad = false;
-        const int no = (int)a.n_owned;
-        int i = 0;
-        while (i < m) {
-            const int first = s_keys[i];
-            int last = first;
-            int j = i + 1;
-            while (j < m) {
-                const int c = s_keys[j];
-                if (c - last > WIN_GAP) break;
-                if (last < no && c >= no) break;
-                last = c;
-                ++j;
-            }
+        int off = 0;
+        bool bad = too_many;
+        const int n = bad ? 0 : n_runs;
+        for (int q = 0; q < n; ++q) {
+            const int first = s_start[q], last = s_end[q];
             const int base = first >= no ? no : 0;
             const int lo = base + ((first - base) & ~1);
             const int hi = base + ((last - base + 2) & ~1);      // one past, even
-            if (n >= WIN_MAXSEG) {
-                bad = true;
-                break;
-            }
-            s_start[n] = lo;
-            s_end[n] = hi;
-            s_off[n] = off;
+            s_start[q] = lo;
+            s_end[q] = hi;
+            s_off[q] = off;
             off += hi - lo;
-            ++n;
-            i = j;
         }
         if (off > 65534) bad = true;
         s_n = bad ? -1 : n;
         if (bad) atomicExch(a.status + 1, 1);
         else atomicMax(a.status, off);
         a.nseg[tile] = bad ? 0 : n;
-        for (int q = 0; q < WIN_MAXSEG; ++q) {
-            const bool live = !bad && q < n;
-            const int lo = live ? s_start[q] : 0;
-            a.seg_start[tile * WIN_MAXSEG + q] = !live ? 0 : (lo >= no ? ~(lo - no) : lo);
-            a.seg_len[tile * WIN_MAXSEG + q] = (unsigned short)(live ? s_end[q] - lo : 0);
-            a.seg_off[tile * WIN_MAXSEG + q] = (unsigned short)(live ? s_off[q] : 0);
-        }
+    }
+    __syncthreads();
+    if (threadIdx.x < WIN_MAXSEG) {
+        const int q = threadIdx.x;
+        const bool live = s_n >= 0 && q < s_n;
+        const int lo = live ? s_start[q] : 0;
+        a.seg_start[tile * WIN_MAXSEG + q] = !live ? 0 : (lo >= no ? ~(lo - no) : lo);
+        a.seg_len[tile * WIN_MAXSEG + q] = (unsigned short)(live ? s_end[q] - lo : 0);
+        a.seg_off[tile * WIN_MAXSEG + q] = (unsigned short)(live ? s_off[q] : 0);
     }
     __syncthreads();
     const int n = s_n;

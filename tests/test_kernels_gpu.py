@@ -39,11 +39,11 @@ def run_spmv(ctx, rp, col, val, x, lanes=0, variant=None, **opts):
     """variant 0 (default): auto = 3 (windowed x, all operands by TMA) when the matrix is representable,
     else 2 (TMA-staged CRS tiles + x gathers); both add the products in storage order: bit-exact.
     lanes > 0: variant 1, vector CRS with that many lanes per row (tolerance only)."""
-    A = ctx.upload_crs(rp, col, val)
     ctx.set_option("spmv_variant", (1 if lanes else 0) if variant is None else variant)
     for k, v in opts.items():
         ctx.set_option(k, v)
     ctx.set_option("spmv_lanes", lanes)
+    A = ctx.upload_crs(rp, col, val)      # the tile format (variant 3) is built at upload with these options
     dx, dy = ctx.upload(x), ctx.alloc(len(rp) - 1)
     ctx.call("bis_spmv", A.h, dx, dy)
     y = ctx.download(dy, len(rp) - 1)
