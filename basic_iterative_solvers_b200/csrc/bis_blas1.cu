@@ -12,31 +12,49 @@ namespace {
 
 constexpr int EW_THREADS = 256;
 constexpr int EW_UNROLL = 4;
+constexpr int EW_MAXIN = 6;
 
-// Generic streaming kernel: P() once per thread (loads the device scalars and
-// forms alpha/beta/omega), then F(i, acc, scalars) per element; NRED fused
-// reductions.
-template <int NRED, class P, class F>
-__global__ void __launch_bounds__(EW_THREADS) ew_kernel(int64_t n, P prep, F f, RedArgs ra) {
+// Input vectors of a streaming kernel.  The kernel reads ALL inputs of EW_UNROLL elements before it
+// runs the per-element body (which stores): outputs may alias inputs element-wise
+// (gauss_seidel.hpp:34, gmres.hpp:25, kernels.hpp:369), so the compiler cannot hoist a later element's
+// loads above an earlier element's stores by itself, and a thread would have one element's loads in
+// flight at a time.  Loading first gives NIN x EW_UNROLL independent loads per thread.
+template <int NIN> struct EwIn {
+    const double *p[NIN > 0 ? NIN : 1];
+};
+
+// Generic streaming kernel: prep() once per thread (loads the device scalars and forms
+// alpha/beta/omega), then f(i, v, acc, scalars) per element with v[k] = in.p[k][i]; NRED fused reductions.
+template <int NRED, int NIN, class P, class F>
+__global__ void __launch_bounds__(EW_THREADS) ew_kernel(int64_t n, P prep, EwIn<NIN> in, F f, RedArgs ra) {
     const auto sc = prep();
     double acc[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int q = 0; q < (NRED > 0 ? NRED : 1); ++q) acc[q] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * EW_THREADS;
     int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x;
-    // main body: EW_UNROLL independent elements per thread per trip
     for (; i + (EW_UNROLL - 1) * stride < n; i += EW_UNROLL * stride) {
+        double v[EW_UNROLL][NIN > 0 ? NIN : 1];
 #pragma unroll
-        for (int u = 0; u < EW_UNROLL; ++u) f(i + u * stride, acc, sc);
+        for (int u = 0; u < EW_UNROLL; ++u)
+#pragma unroll
+            for (int k = 0; k < NIN; ++k) v[u][k] = in.p[k][i + u * stride];
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) f(i + u * stride, v[u], acc, sc);
     }
-    for (; i < n; i += stride) f(i, acc, sc);
+    for (; i < n; i += stride) {
+        double v[NIN > 0 ? NIN : 1];
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) v[k] = in.p[k][i];
+        f(i, v, acc, sc);
+    }
     if constexpr (NRED > 0) block_reduce_finish<NRED>(acc, ra);
 }
 
 struct Sc3 { double a, b, c; };
 
-template <int NRED, class P, class F>
-int launch_ew2(bis_context *c, int64_t n, P prep, F f, int slot_a = -1, int slot_b = -1) {
+template <int NRED, int NIN, class P, class F>
+int launch_ew2(bis_context *c, int64_t n, P prep, const EwIn<NIN> &in, F f, int slot_a = -1, int slot_b = -1) {
     // fixed launch shape for a given n => bit-reproducible reductions
     int cap = c->sm_count * 8;
     if (cap > BIS_MAX_RED_BLOCKS) cap = BIS_MAX_RED_BLOCKS;
@@ -44,17 +62,18 @@ int launch_ew2(bis_context *c, int64_t n, P prep, F f, int slot_a = -1, int slot
     RedArgs ra = bis_red_args(c, slot_a, slot_b);
     ra.total_blocks = blocks;
     BIS_CHECK(bis_prof_begin(c, BIS_PROF_VECTOR));
-    ew_kernel<NRED, P, F><<<blocks, EW_THREADS, 0, c->stream>>>(n, prep, f, ra);
+    ew_kernel<NRED, NIN, P, F><<<blocks, EW_THREADS, 0, c->stream>>>(n, prep, in, f, ra);
     BIS_LAUNCH_CHECK(c);
     BIS_CHECK(bis_prof_end(c, BIS_PROF_VECTOR));
     if (NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));
     return 0;
 }
 
-template <int NRED, class F>
-int launch_ew(bis_context *c, int64_t n, F f, int slot_a = -1, int slot_b = -1) {
-    return launch_ew2<NRED>(c, n, [] __device__() { return 0; },
-                            [=] __device__(int64_t i, double *acc, int) { f(i, acc); }, slot_a, slot_b);
+template <int NRED, int NIN, class F>
+int launch_ew(bis_context *c, int64_t n, const EwIn<NIN> &in, F f, int slot_a = -1, int slot_b = -1) {
+    return launch_ew2<NRED, NIN>(c, n, [] __device__() { return 0; }, in,
+                                 [=] __device__(int64_t i, const double *v, double *acc, int) { f(i, v, acc); },
+                                 slot_a, slot_b);
 }
 
 inline bool slot_ok(int s) { return s >= 0 && s < BIS_NUM_SCALARS; }
@@ -68,36 +87,40 @@ inline bool slot_ok(int s) { return s >= 0 && s < BIS_NUM_SCALARS; }
 extern "C" int bis_subtract_vectors(bis_context *c, double *out, const double *a, const double *b,
                                     int64_t n, double scale) {
     REQ_CTX(c);
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) { out[i] = fma(-scale, b[i], a[i]); });
+    return launch_ew<0, 2>(c, n, EwIn<2>{{a, b}},
+                           [=] __device__(int64_t i, const double *v, double *) { out[i] = fma(-scale, v[1], v[0]); });
 }
 extern "C" int bis_sum_vectors(bis_context *c, double *out, const double *a, const double *b,
                                int64_t n, double scale) {
     REQ_CTX(c);
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) { out[i] = fma(scale, b[i], a[i]); });
+    return launch_ew<0, 2>(c, n, EwIn<2>{{a, b}},
+                           [=] __device__(int64_t i, const double *v, double *) { out[i] = fma(scale, v[1], v[0]); });
 }
 extern "C" int bis_elemwise_mult_vectors(bis_context *c, double *out, const double *a,
                                          const double *b, int64_t n, double scale) {
     REQ_CTX(c);
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) {
-        out[i] = mul_rn(mul_rn(a[i], scale), b[i]);
+    return launch_ew<0, 2>(c, n, EwIn<2>{{a, b}}, [=] __device__(int64_t i, const double *v, double *) {
+        out[i] = mul_rn(mul_rn(v[0], scale), v[1]);
     });
 }
 extern "C" int bis_elemwise_div_vectors(bis_context *c, double *out, const double *a,
                                         const double *b, int64_t n, double scale) {
     REQ_CTX(c);
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) {
-        out[i] = div_rn(a[i], mul_rn(scale, b[i]));
+    return launch_ew<0, 2>(c, n, EwIn<2>{{a, b}}, [=] __device__(int64_t i, const double *v, double *) {
+        out[i] = div_rn(v[0], mul_rn(scale, v[1]));
     });
 }
 // kernels.hpp:214-220
-extern "C" int bis_scale(bis_context *c, double *out, const double *v, double scalar, int64_t n) {
+extern "C" int bis_scale(bis_context *c, double *out, const double *v_in, double scalar, int64_t n) {
     REQ_CTX(c);
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) { out[i] = mul_rn(v[i], scalar); });
+    return launch_ew<0, 1>(c, n, EwIn<1>{{v_in}},
+                           [=] __device__(int64_t i, const double *v, double *) { out[i] = mul_rn(v[0], scalar); });
 }
 // kernels.hpp:236-241
-extern "C" int bis_init_vector(bis_context *c, double *v, double value, int64_t n) {
+extern "C" int bis_init_vector(bis_context *c, double *v_out, double value, int64_t n) {
     REQ_CTX(c);
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) { v[i] = value; });
+    return launch_ew<0, 0>(c, n, EwIn<0>{{nullptr}},
+                           [=] __device__(int64_t i, const double *, double *) { v_out[i] = value; });
 }
 // kernels.hpp:252-257
 extern "C" int bis_copy_vector(bis_context *c, double *out, const double *in, int64_t n) {
@@ -110,11 +133,10 @@ extern "C" int bis_copy_vector(bis_context *c, double *out, const double *in, in
 extern "C" int bis_normalize_x(bis_context *c, double *x_new, const double *x_old, const double *D,
                                const double *b, int64_t n) {
     REQ_CTX(c);
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) {
-        double d = D[i];
-        double scaled = mul_rn(d, x_old[i]);
-        double adj = sub_rn(x_new[i], scaled);
-        x_new[i] = div_rn(sub_rn(b[i], adj), d);
+    return launch_ew<0, 4>(c, n, EwIn<4>{{x_new, x_old, D, b}}, [=] __device__(int64_t i, const double *v, double *) {
+        double scaled = mul_rn(v[2], v[1]);
+        double adj = sub_rn(v[0], scaled);
+        x_new[i] = div_rn(sub_rn(v[3], adj), v[2]);
     });
 }
 
@@ -122,16 +144,16 @@ extern "C" int bis_normalize_x(bis_context *c, double *x_new, const double *x_ol
 extern "C" int bis_dot_to_slot(bis_context *c, const double *a, const double *b, int64_t n, int slot) {
     REQ_CTX(c);
     REQ_SLOT(slot);
-    return launch_ew<1>(c, n, [=] __device__(int64_t i, double *acc) { acc[0] = fma(a[i], b[i], acc[0]); },
-                        slot);
+    return launch_ew<1, 2>(c, n, EwIn<2>{{a, b}},
+                           [=] __device__(int64_t, const double *v, double *acc) { acc[0] = fma(v[0], v[1], acc[0]); },
+                           slot);
 }
-extern "C" int bis_sumsq_to_slot(bis_context *c, const double *v, int64_t n, int slot) {
+extern "C" int bis_sumsq_to_slot(bis_context *c, const double *v_in, int64_t n, int slot) {
     REQ_CTX(c);
     REQ_SLOT(slot);
-    return launch_ew<1>(c, n, [=] __device__(int64_t i, double *acc) {
-        double t = v[i];
-        acc[0] = fma(t, t, acc[0]);
-    }, slot);
+    return launch_ew<1, 1>(c, n, EwIn<1>{{v_in}},
+                           [=] __device__(int64_t, const double *v, double *acc) { acc[0] = fma(v[0], v[0], acc[0]); },
+                           slot);
 }
 extern "C" int bis_dot(bis_context *c, const double *a, const double *b, int64_t n, double *result) {
     REQ_CTX(c);
@@ -159,12 +181,13 @@ extern "C" int bis_cg_update(bis_context *c, int precond, int64_t n, double *x_n
     const double *S = c->d_scalars;
     // alpha <- (r_old, z_old) / (Ap_old, p_old), cg.hpp:19-23
     auto prep = [=] __device__() { return div_rn(S[slot_rz], S[slot_pAp]); };
+    const EwIn<4> in{{x_old, p_old, r_old, Ap}};
     if (precond == BIS_PRECOND_NONE) {
         REQ_SLOT(slot_rz_new);
         // z_new = r_new (copy_vector, kernels.hpp:396-399); (r,z) == (r,r)
-        BIS_CHECK((launch_ew2<1>(c, n, prep, [=] __device__(int64_t i, double *acc, double alpha) {
-            x_new[i] = fma(alpha, p_old[i], x_old[i]);
-            double r = fma(-alpha, Ap[i], r_old[i]);
+        BIS_CHECK((launch_ew2<1, 4>(c, n, prep, in, [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+            x_new[i] = fma(alpha, v[1], v[0]);
+            double r = fma(-alpha, v[3], v[2]);
             r_new[i] = r;
             z_new[i] = r;
             acc[0] = fma(r, r, acc[0]);
@@ -173,19 +196,20 @@ extern "C" int bis_cg_update(bis_context *c, int precond, int64_t n, double *x_n
     }
     if (precond == BIS_PRECOND_JACOBI) {
         REQ_SLOT(slot_rz_new);
-        return launch_ew2<2>(c, n, prep, [=] __device__(int64_t i, double *acc, double alpha) {
-            x_new[i] = fma(alpha, p_old[i], x_old[i]);
-            double r = fma(-alpha, Ap[i], r_old[i]);
+        return launch_ew2<2, 5>(c, n, prep, EwIn<5>{{x_old, p_old, r_old, Ap, A_D}},
+                                [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+            x_new[i] = fma(alpha, v[1], v[0]);
+            double r = fma(-alpha, v[3], v[2]);
             r_new[i] = r;
-            double z = div_rn(r, A_D[i]);   // elemwise_div_vectors with scale = 1.0 (1.0*d == d)
+            double z = div_rn(r, v[4]);   // elemwise_div_vectors with scale = 1.0 (1.0*d == d)
             z_new[i] = z;
             acc[0] = fma(r, r, acc[0]);
             acc[1] = fma(r, z, acc[1]);
         }, slot_rr, slot_rz_new);
     }
-    return launch_ew2<1>(c, n, prep, [=] __device__(int64_t i, double *acc, double alpha) {
-        x_new[i] = fma(alpha, p_old[i], x_old[i]);
-        double r = fma(-alpha, Ap[i], r_old[i]);
+    return launch_ew2<1, 4>(c, n, prep, in, [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+        x_new[i] = fma(alpha, v[1], v[0]);
+        double r = fma(-alpha, v[3], v[2]);
         r_new[i] = r;
         acc[0] = fma(r, r, acc[0]);
     }, slot_rr);
@@ -196,10 +220,11 @@ extern "C" int bis_cg_direction(bis_context *c, int64_t n, double *p_new, const 
     REQ_CTX(c);
     REQ_SLOT(slot_rz_new); REQ_SLOT(slot_rz);
     const double *S = c->d_scalars;
-    return launch_ew2<0>(c, n, [=] __device__() { return div_rn(S[slot_rz_new], S[slot_rz]); },
-                         [=] __device__(int64_t i, double *, double beta) {
-                             p_new[i] = fma(beta, p_old[i], z_new[i]);
-                         });
+    return launch_ew2<0, 2>(c, n, [=] __device__() { return div_rn(S[slot_rz_new], S[slot_rz]); },
+                            EwIn<2>{{z_new, p_old}},
+                            [=] __device__(int64_t i, const double *v, double *, double beta) {
+                                p_new[i] = fma(beta, v[1], v[0]);
+                            });
 }
 
 // ---- BiCGSTAB: methods/bicgstab.hpp:8-83 ----------------------------------------
@@ -210,13 +235,14 @@ extern "C" int bis_bicgstab_s(bis_context *c, int precond, int64_t n, double *s,
     REQ_SLOT(slot_rho_old); REQ_SLOT(slot_r0v);
     const double *S = c->d_scalars;
     const int mode = (precond == BIS_PRECOND_NONE) ? 0 : (precond == BIS_PRECOND_JACOBI ? 1 : 2);
-    return launch_ew2<0>(c, n, [=] __device__() { return div_rn(S[slot_rho_old], S[slot_r0v]); },
-                         [=] __device__(int64_t i, double *, double alpha) {
-                             double sv = fma(-alpha, v[i], r_old[i]);
-                             s[i] = sv;
-                             if (mode == 0) s_tmp[i] = sv;
-                             else if (mode == 1) s_tmp[i] = div_rn(sv, A_D[i]);
-                         });
+    return launch_ew2<0, 3>(c, n, [=] __device__() { return div_rn(S[slot_rho_old], S[slot_r0v]); },
+                            EwIn<3>{{r_old, v, mode == 1 ? A_D : r_old}},
+                            [=] __device__(int64_t i, const double *w, double *, double alpha) {
+                                double sv = fma(-alpha, w[1], w[0]);
+                                s[i] = sv;
+                                if (mode == 0) s_tmp[i] = sv;
+                                else if (mode == 1) s_tmp[i] = div_rn(sv, w[2]);
+                            });
 }
 
 extern "C" int bis_bicgstab_xr(bis_context *c, int64_t n, double *h, double *x_new,
@@ -228,19 +254,19 @@ extern "C" int bis_bicgstab_xr(bis_context *c, int64_t n, double *h, double *x_n
     REQ_SLOT(slot_rho_old); REQ_SLOT(slot_r0v); REQ_SLOT(slot_zs); REQ_SLOT(slot_zz);
     REQ_SLOT(slot_rho_new); REQ_SLOT(slot_rr);
     const double *S = c->d_scalars;
-    return launch_ew2<2>(c, n, [=] __device__() {
+    return launch_ew2<2, 6>(c, n, [=] __device__() {
         Sc3 sc;
         sc.a = div_rn(S[slot_rho_old], S[slot_r0v]);   // alpha, bicgstab.hpp:34
         sc.b = div_rn(S[slot_zs], S[slot_zz]);         // omega, bicgstab.hpp:51
         sc.c = 0.0;
         return sc;
-    }, [=] __device__(int64_t i, double *acc, Sc3 sc) {
-        double hv = fma(sc.a, y[i], x_old[i]);
+    }, EwIn<6>{{x_old, y, s_tmp, s, z, r0}}, [=] __device__(int64_t i, const double *v, double *acc, Sc3 sc) {
+        double hv = fma(sc.a, v[1], v[0]);
         if (h) h[i] = hv;
-        x_new[i] = fma(sc.b, s_tmp[i], hv);
-        double r = fma(-sc.b, z[i], s[i]);
+        x_new[i] = fma(sc.b, v[2], hv);
+        double r = fma(-sc.b, v[4], v[3]);
         r_new[i] = r;
-        acc[0] = fma(r0[i], r, acc[0]);
+        acc[0] = fma(v[5], r, acc[0]);
         acc[1] = fma(r, r, acc[1]);
     }, slot_rho_new, slot_rr);
 }
@@ -254,7 +280,7 @@ extern "C" int bis_bicgstab_p(bis_context *c, int precond, int64_t n, double *tm
     REQ_SLOT(slot_zz);
     const double *S = c->d_scalars;
     const int mode = !y_next ? 2 : ((precond == BIS_PRECOND_NONE) ? 0 : (precond == BIS_PRECOND_JACOBI ? 1 : 2));
-    return launch_ew2<0>(c, n, [=] __device__() {
+    return launch_ew2<0, 4>(c, n, [=] __device__() {
         Sc3 sc;
         double alpha = div_rn(S[slot_rho_old], S[slot_r0v]);
         sc.b = div_rn(S[slot_zs], S[slot_zz]);   // omega
@@ -262,13 +288,13 @@ extern "C" int bis_bicgstab_p(bis_context *c, int precond, int64_t n, double *tm
         sc.a = mul_rn(div_rn(S[slot_rho_new], S[slot_rho_old]), div_rn(alpha, sc.b));
         sc.c = 0.0;
         return sc;
-    }, [=] __device__(int64_t i, double *, Sc3 sc) {
-        double t = fma(-sc.b, v[i], p_old[i]);
+    }, EwIn<4>{{p_old, v, r_new, mode == 1 ? A_D : r_new}}, [=] __device__(int64_t i, const double *w, double *, Sc3 sc) {
+        double t = fma(-sc.b, w[1], w[0]);
         if (tmp) tmp[i] = t;
-        double p = fma(sc.a, t, r_new[i]);
+        double p = fma(sc.a, t, w[2]);
         p_new[i] = p;
         if (mode == 0) y_next[i] = p;
-        else if (mode == 1) y_next[i] = div_rn(p, A_D[i]);
+        else if (mode == 1) y_next[i] = div_rn(p, w[3]);
     });
 }
 
@@ -280,13 +306,15 @@ extern "C" int bis_mgs_step(bis_context *c, int64_t n, double *w, const double *
     const double *S = c->d_scalars;
     auto prep = [=] __device__() { return S[slot_h_j]; };
     if (v_next)
-        return launch_ew2<1>(c, n, prep, [=] __device__(int64_t i, double *acc, double h) {
-            double t = fma(-h, v_j[i], w[i]);
+        return launch_ew2<1, 3>(c, n, prep, EwIn<3>{{w, v_j, v_next}},
+                                [=] __device__(int64_t i, const double *v, double *acc, double h) {
+            double t = fma(-h, v[1], v[0]);
             w[i] = t;
-            acc[0] = fma(t, v_next[i], acc[0]);
+            acc[0] = fma(t, v[2], acc[0]);
         }, slot_out);
-    return launch_ew2<1>(c, n, prep, [=] __device__(int64_t i, double *acc, double h) {
-        double t = fma(-h, v_j[i], w[i]);
+    return launch_ew2<1, 2>(c, n, prep, EwIn<2>{{w, v_j}},
+                            [=] __device__(int64_t i, const double *v, double *acc, double h) {
+        double t = fma(-h, v[1], v[0]);
         w[i] = t;
         acc[0] = fma(t, t, acc[0]);
     }, slot_out);
@@ -297,8 +325,8 @@ extern "C" int bis_scale_inv_norm(bis_context *c, int64_t n, double *out, const 
     REQ_CTX(c);
     REQ_SLOT(slot_sumsq);
     const double *S = c->d_scalars;
-    return launch_ew2<0>(c, n, [=] __device__() { return div_rn(1.0, sqrt(S[slot_sumsq])); },
-                         [=] __device__(int64_t i, double *, double inv) { out[i] = mul_rn(w[i], inv); });
+    return launch_ew2<0, 1>(c, n, [=] __device__() { return div_rn(1.0, sqrt(S[slot_sumsq])); }, EwIn<1>{{w}},
+                            [=] __device__(int64_t i, const double *v, double *, double inv) { out[i] = mul_rn(v[0], inv); });
 }
 
 namespace {
@@ -312,11 +340,11 @@ extern "C" int bis_gmres_update_x(bis_context *c, int64_t n, int k, const double
     BIS_REQUIRE(k == 0 || y, "bis_gmres_update_x: null y");
     YCoef yc;
     for (int j = 0; j < 64; ++j) yc.y[j] = (j < k) ? y[j] : 0.0;
-    return launch_ew<0>(c, n, [=] __device__(int64_t i, double *) {
+    return launch_ew<0, 1>(c, n, EwIn<1>{{x_old}}, [=] __device__(int64_t i, const double *v, double *) {
         // dgemm_transpose1 (kernels.hpp:259-271): left-to-right, unfused
         double t = 0.0;
         for (int j = 0; j < k; ++j) t = add_rn(t, mul_rn(V[(int64_t)j * n + i], yc.y[j]));
         if (Vy) Vy[i] = t;
-        x[i] = add_rn(x_old[i], t);
+        x[i] = add_rn(v[0], t);
     });
 }

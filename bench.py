@@ -297,7 +297,7 @@ def main():
                 "x_star_check": e2e_check},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "spmv_tma_kernel<EpiDot> (y = A p fused with (y,p); TMA-staged CRS tiles)",
+        "roofline": {"bound": "hbm", "kernel": "spmv_win_kernel<long, EpiDot> (y = A p fused with (y,p); val, 16-bit local column ids, row_ptr slice and x windows by TMA)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
