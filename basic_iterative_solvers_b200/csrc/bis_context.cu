@@ -265,6 +265,9 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     if (k == "spmv_variant") c->opt_spmv_variant = value;
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
     else if (k == "trsv_variant") c->opt_trsv_variant = value;
+    else if (k == "trsv_debug") c->opt_trsv_debug = value;
+    else if (k == "trsv_poll_ns") c->opt_trsv_poll_ns = value;
+    else if (k == "trsv_warp_flag") c->opt_trsv_warp_flag = value;
     else if (k == "spmv_rows") c->opt_spmv_rows = value;
     else if (k == "spmv_stages") c->opt_spmv_stages = value;
     else if (k == "spmv_smem_kb") c->opt_spmv_smem_kb = value;

@@ -113,6 +113,9 @@ struct bis_context {
     int opt_spmv_variant = 0;
     int opt_spmv_lanes = 0;
     int opt_trsv_variant = 0;
+    int opt_trsv_poll_ns = 0;   // sleep between polls in the triangular solve (0: default)
+    int opt_trsv_warp_flag = 0; // triangular solve: one poller per warp on the producing warp's flag (experiment)
+    int opt_trsv_debug = 0;     // dump per-row timestamps of each solve to $BIS_TRSV_DEBUG_FILE
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
     int opt_spmv_debug = 0;     // perf experiments (results invalid when non-zero)
@@ -129,10 +132,14 @@ struct LevelSets {
     int64_t n_slots = 0;              // == n_rows: position in the level-ordered row list
     int *d_slot_row = nullptr;        // [n_slots] original row
     int *d_slot_level = nullptr;      // [n_slots] level of that row (non-decreasing)
+    int *d_slot_crit = nullptr;       // [n_slots] column of the dependency that completes last (-1: none)
+    int *d_warp_crit = nullptr;       // [n_slots/32] the other warp (of 32 slots) this warp needs that comes last
+    unsigned int *d_warp_flag = nullptr;   // [n_slots/32] set when all rows of that warp are published
     int *d_level_size = nullptr;      // [n_levels] rows per level
     std::vector<int64_t> level_start; // [n_levels+1] host copy (per-level launch variant)
     unsigned int *d_level_done = nullptr;   // [n_levels] completion counters
     unsigned int *d_ticket = nullptr; // chunk ticket
+    double *d_w = nullptr;            // [n_slots] scratch of the solve: sentinel until the row's value is final
     // level-ordered copy of the strict factor (rows stored in slot order)
     int64_t *d_rp = nullptr;          // [n_slots+1]
     int *d_col = nullptr;
@@ -179,7 +186,7 @@ struct bis_matrix {
     int triangular = 0;        // 0 general, 1 strictly lower, 2 strictly upper
     double mean_row = 0.0;
     int max_row = 0;
-    LevelSets lv;
+    mutable LevelSets lv;
     HaloPlan halo;
     mutable WinFormat win;
     bool distributed = false;

@@ -27,9 +27,13 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->d_val);
     cudaFree(A->lv.d_slot_row);
     cudaFree(A->lv.d_slot_level);
+    cudaFree(A->lv.d_slot_crit);
+    cudaFree(A->lv.d_warp_crit);
+    cudaFree(A->lv.d_warp_flag);
     cudaFree(A->lv.d_level_size);
     cudaFree(A->lv.d_level_done);
     cudaFree(A->lv.d_ticket);
+    cudaFree(A->lv.d_w);
     cudaFree(A->lv.d_rp);
     cudaFree(A->lv.d_col);
     cudaFree(A->lv.d_val);
@@ -189,6 +193,38 @@ extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t n
             slot_level[s] = level[r];
         }
     }
+    // per row: the dependency that becomes final LAST (largest level, then largest slot) -- the solve
+    // polls this one value while it waits and looks at the others only once it is there
+    std::vector<int> slot_crit((size_t)n, -1);
+    {
+        std::vector<int64_t> slot_of((size_t)n);
+        for (int64_t sl = 0; sl < n; ++sl) slot_of[slot_row[sl]] = sl;
+        for (int64_t sl = 0; sl < n; ++sl) {
+            const int r = slot_row[sl];
+            int64_t best = -1;
+            for (int32_t k = rp[r]; k < rp[r + 1]; ++k)
+                if (slot_of[col[k]] > best) {
+                    best = slot_of[col[k]];
+                    slot_crit[sl] = col[k];
+                }
+        }
+    }
+    // per warp of 32 consecutive slots: the (other) warp whose rows it needs that comes last in slot order;
+    // the solve watches that warp's completion flag with ONE poller per warp instead of 32 scattered ones
+    const int64_t n_warps = (n + 31) / 32;
+    std::vector<int> warp_crit((size_t)std::max<int64_t>(n_warps, 1), -1);
+    {
+        std::vector<int64_t> slot_of((size_t)n);
+        for (int64_t sl = 0; sl < n; ++sl) slot_of[slot_row[sl]] = sl;
+        for (int64_t sl = 0; sl < n; ++sl) {
+            const int r = slot_row[sl];
+            const int64_t me = sl / 32;
+            for (int32_t k = rp[r]; k < rp[r + 1]; ++k) {
+                const int64_t w = slot_of[col[k]] / 32;
+                if (w != me && w > warp_crit[me]) warp_crit[me] = (int)w;
+            }
+        }
+    }
     std::vector<int64_t> rp2((size_t)n + 1, 0);
     std::vector<int32_t> col2((size_t)nnz);
     std::vector<double> val2((size_t)nnz);
@@ -208,9 +244,13 @@ extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t n
     int rc = 0;
     rc |= dev_alloc(&lv.d_slot_row, (size_t)n);
     rc |= dev_alloc(&lv.d_slot_level, (size_t)n);
+    rc |= dev_alloc(&lv.d_slot_crit, (size_t)n);
+    rc |= dev_alloc(&lv.d_warp_crit, (size_t)n_warps);
+    rc |= dev_alloc(&lv.d_warp_flag, (size_t)n_warps);
     rc |= dev_alloc(&lv.d_level_size, (size_t)n_levels);
     rc |= dev_alloc(&lv.d_level_done, (size_t)n_levels);
     rc |= dev_alloc(&lv.d_ticket, 1);
+    rc |= dev_alloc(&lv.d_w, (size_t)n);
     rc |= dev_alloc(&lv.d_rp, (size_t)n + 1);
     rc |= dev_alloc(&lv.d_col, (size_t)nnz);
     rc |= dev_alloc(&lv.d_val, (size_t)nnz);
@@ -224,6 +264,8 @@ extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t n
     };
     BIS_CUDA(h2d(lv.d_slot_row, slot_row.data(), sizeof(int) * (size_t)n));
     BIS_CUDA(h2d(lv.d_slot_level, slot_level.data(), sizeof(int) * (size_t)n));
+    BIS_CUDA(h2d(lv.d_slot_crit, slot_crit.data(), sizeof(int) * (size_t)n));
+    BIS_CUDA(h2d(lv.d_warp_crit, warp_crit.data(), sizeof(int) * (size_t)n_warps));
     BIS_CUDA(h2d(lv.d_level_size, level_size.data(), sizeof(int) * (size_t)n_levels));
     BIS_CUDA(h2d(lv.d_rp, rp2.data(), sizeof(int64_t) * ((size_t)n + 1)));
     BIS_CUDA(h2d(lv.d_col, col2.data(), sizeof(int32_t) * (size_t)nnz));

@@ -22,6 +22,8 @@
 // (HPCG-n has 7n-6 levels).
 #include "bis_device.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int TRSV_THREADS = 256;
@@ -31,6 +33,12 @@ struct TrsvArgs {
     int64_t n_slots;
     const int *slot_row;
     const int *slot_level;
+    const int *slot_crit;
+    unsigned long long *dbg;   // debug timestamps (3 per row) or nullptr
+    unsigned int poll_ns;      // sleep between two polls of the missing operands
+    const int *warp_crit;
+    unsigned int *warp_flag;
+    int use_warp_flag;
     const int64_t *rp;      // level-ordered
     const int *col;
     const double *val;
@@ -117,6 +125,159 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) 
     }
 }
 
+// ---- default: the value is its own ready flag ("sync-free" in level order) -----------------------
+// The level counters above make every row of level l wait for ALL rows of level l-1 and funnel
+// thousands of pollers and the completing atomics through one L2 address per level (measured: ~5 us
+// per level).  Here a row waits only for the rows it actually reads, and what it polls is the value
+// itself: results go to a scratch vector w that is pre-filled with a sentinel (a NaN payload the
+// arithmetic can never produce), a consumer re-reads w[dep] (8-byte loads are single-copy atomic) until
+// it is not the sentinel -- the load that observes readiness also delivers the operand, so one hop of
+// the dependency chain costs one store-to-L2 plus one load-from-L2, with no fence and no second round
+// trip.  All dependencies of a row are polled together (independent loads).  Rows are still handed out
+// in level order through the ticket counter, so every dependency belongs to an earlier slot, i.e. to a
+// block that is already running (or to an earlier level handled by this very warp): no deadlock, no
+// co-residency assumption.  x may alias b (each thread reads its b[row] before any x is written and
+// nobody else touches that element).  Summation order per row is unchanged: bit-identical results.
+constexpr unsigned long long TRSV_SENTINEL = 0xFFF87E5E7E5E7E5EULL;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) trsv_fill_sentinel_kernel(int64_t n, double *w, unsigned int *warp_flag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        reinterpret_cast<unsigned long long *>(w)[i] = TRSV_SENTINEL;
+        if ((i & 31) == 0) warp_flag[i >> 5] = 0u;
+    }
+}
+
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(TRSV_THREADS) sptrsv_flag_kernel(TrsvArgs a, double *w) {
+    __shared__ unsigned int s_chunk;
+    if (threadIdx.x == 0) s_chunk = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int64_t slot = (int64_t)s_chunk * TRSV_THREADS + threadIdx.x;
+    const bool live = slot < a.n_slots;
+
+    int row = 0, lvl = 0x7fffffff, crit = -1;
+    int64_t s = 0, e = 0;
+    double bb = 0.0, dd = 1.0;
+    if (live) {
+        row = a.slot_row[slot];
+        lvl = a.slot_level[slot];
+        crit = a.slot_crit[slot];
+        s = a.rp[slot];
+        e = a.rp[slot + 1];
+        bb = a.b[row];
+        dd = a.D[row];
+    }
+    // the head of the row is in registers before anything is waited for
+    double av[TRSV_PF];
+    int cv[TRSV_PF];
+#pragma unroll
+    for (int j = 0; j < TRSV_PF; ++j) {
+        const bool ok = s + j < e;
+        av[j] = ok ? __ldcs(a.val + s + j) : 0.0;
+        cv[j] = ok ? __ldcs(a.col + s + j) : -1;
+    }
+    // rows of one warp are consecutive slots, i.e. at most a few consecutive levels; rows of the same
+    // level never read one another, so the warp handles its levels one after the other in lockstep
+    int lv_lo = lvl, lv_hi = live ? lvl : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lv_lo = min(lv_lo, __shfl_xor_sync(0xffffffffu, lv_lo, o));
+        lv_hi = max(lv_hi, __shfl_xor_sync(0xffffffffu, lv_hi, o));
+    }
+    // operands: everything already published is taken now; only the missing ones are polled, and the
+    // load that finds a value is the load that delivers it (no second round trip)
+    unsigned long long xv[TRSV_PF];
+    bool missing = false;
+#pragma unroll
+    for (int j = 0; j < TRSV_PF; ++j) {
+        xv[j] = cv[j] >= 0 ? ld_relaxed_u64(w + cv[j]) : 0ull;
+        missing |= (xv[j] == TRSV_SENTINEL);
+    }
+    // While values are missing, ONE lane per warp watches the completion flag of the warp that produces
+    // the last of them (32 lanes polling 32 scattered sectors several times each cost ~0.7 us per poll
+    // in the SM's load pipeline alone).  The flag is only a hint: every value is still checked below.
+    const int64_t warp_id = slot >> 5;
+    if (a.use_warp_flag && __any_sync(0xffffffffu, missing)) {
+        const int wc = a.warp_crit[warp_id < (a.n_slots + 31) / 32 ? warp_id : 0];
+        if ((threadIdx.x & 31) == 0 && wc >= 0) {
+            unsigned int spins = 0;
+            while (ld_relaxed_u32(a.warp_flag + wc) == 0u) {
+                __nanosleep(a.poll_ns);
+                if ((++spins & 0xffffu) == 0 && *reinterpret_cast<volatile int *>(a.errflag)) break;
+            }
+        }
+        __syncwarp();
+    }
+    for (int lv = lv_lo; lv <= lv_hi; ++lv) {
+        if (live && lvl == lv) {
+            long long t0 = 0;
+            unsigned int spins = 0;
+            bool ok = true;
+            unsigned long long ts0 = 0, ts1 = 0, ts2 = 0;
+            if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0));
+            for (;;) {
+                bool ready = true;
+#pragma unroll
+                for (int j = 0; j < TRSV_PF; ++j)
+                    if (xv[j] == TRSV_SENTINEL) {
+                        xv[j] = ld_relaxed_u64(w + cv[j]);
+                        ready &= (xv[j] != TRSV_SENTINEL);
+                    }
+                if (ready) break;
+                __nanosleep(a.poll_ns);
+                if ((++spins & 4095u) == 0) {
+                    if (t0 == 0) t0 = clock64();
+                    if (*reinterpret_cast<volatile int *>(a.errflag) || clock64() - t0 > 6000000000LL) {
+                        atomicExch(a.errflag, 1);
+                        ok = false;
+                        break;
+                    }
+                }
+            }
+            if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1));
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < TRSV_PF; ++j)
+                if (cv[j] >= 0) sum = add_rn(sum, mul_rn(av[j], __longlong_as_double((long long)xv[j])));
+            for (int64_t k = s + TRSV_PF; ok && k < e; ++k) {   // rows longer than the register window
+                unsigned long long t;
+                unsigned int sp2 = 0;
+                while ((t = ld_relaxed_u64(w + a.col[k])) == TRSV_SENTINEL) {
+                    if ((++sp2 & 0xfffffu) == 0 && *reinterpret_cast<volatile int *>(a.errflag)) break;
+                }
+                sum = add_rn(sum, mul_rn(a.val[k], __longlong_as_double((long long)t)));
+            }
+            const double r = div_rn(sub_rn(bb, sum), dd);
+            // publish: the value doubles as the flag.  A result that IS the sentinel pattern cannot occur
+            // (hardware NaNs are canonical), so readers can never mistake a result for "not ready".
+            __stcg(w + row, r);
+            a.x[row] = r;
+            if (a.dbg) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2));
+                a.dbg[3 * (int64_t)row] = ts0;       // critical dependency observed
+                a.dbg[3 * (int64_t)row + 1] = ts1;   // all operands in registers
+                a.dbg[3 * (int64_t)row + 2] = ts2;   // result published
+            }
+        }
+        __syncwarp();
+    }
+    // all rows of this warp are published (hint for the warps that wait on it)
+    if ((threadIdx.x & 31) == 0 && warp_id < (a.n_slots + 31) / 32) {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.warp_flag + warp_id), "r"(1u) : "memory");
+    }
+}
+
 // Safety-net variant: one launch per level (opt "trsv_variant" = 1).
 __global__ void __launch_bounds__(TRSV_THREADS)
 sptrsv_one_level_kernel(TrsvArgs a, int64_t slot_begin, int64_t slot_end) {
@@ -139,12 +300,16 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
                 want_kind == 1 ? "lower" : "upper");
     BIS_REQUIRE(!T->distributed, "sptrsv: triangular sweeps do not shard (single-GPU only)");
     BIS_CUDA(cudaSetDevice(c->device));
-    const LevelSets &lv = T->lv;
+    LevelSets &lv = T->lv;
     if (T->n_rows == 0) return 0;
     TrsvArgs a;
     a.n_slots = lv.n_slots;
     a.slot_row = lv.d_slot_row;
     a.slot_level = lv.d_slot_level;
+    a.slot_crit = lv.d_slot_crit;
+    a.warp_crit = lv.d_warp_crit;
+    a.warp_flag = lv.d_warp_flag;
+    a.use_warp_flag = c->opt_trsv_warp_flag;
     a.rp = lv.d_rp;
     a.col = lv.d_col;
     a.val = lv.d_val;
@@ -152,6 +317,10 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.level_done = lv.d_level_done;
     a.ticket = lv.d_ticket;
     a.errflag = c->d_errflag;
+    a.dbg = nullptr;
+    a.poll_ns = c->opt_trsv_poll_ns > 0 ? (unsigned int)c->opt_trsv_poll_ns : 20u;
+    const char *dbg_file = c->opt_trsv_debug ? getenv("BIS_TRSV_DEBUG_FILE") : nullptr;
+    if (dbg_file) BIS_CUDA(cudaMalloc(&a.dbg, sizeof(unsigned long long) * 3 * (size_t)lv.n_slots));
     a.x = x;
     a.D = D;
     a.b = b;
@@ -166,9 +335,27 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
         }
         return bis_prof_end(c, BIS_PROF_SPTRSV);
     }
-    BIS_CUDA(cudaMemsetAsync(lv.d_level_done, 0, sizeof(unsigned int) * (size_t)lv.n_levels, c->stream));
-    BIS_CUDA(cudaMemsetAsync(lv.d_ticket, 0, sizeof(unsigned int), c->stream));
     const int64_t blocks = (lv.n_slots + TRSV_THREADS - 1) / TRSV_THREADS;
+    BIS_CUDA(cudaMemsetAsync(lv.d_ticket, 0, sizeof(unsigned int), c->stream));
+    if (c->opt_trsv_variant != 2) {
+        trsv_fill_sentinel_kernel<<<bis_blocks_for(lv.n_slots, 1024, c->sm_count * 8), 256, 0, c->stream>>>(lv.n_slots, lv.d_w, lv.d_warp_flag);
+        BIS_LAUNCH_CHECK(c);
+        sptrsv_flag_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a, lv.d_w);
+        BIS_LAUNCH_CHECK(c);
+        if (a.dbg) {   // debug aid (tools/trsv_trace.py): per-row timestamps of the last solve
+            std::vector<unsigned long long> h(3 * (size_t)lv.n_slots);
+            BIS_CUDA(cudaMemcpyAsync(h.data(), a.dbg, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+            BIS_CUDA(cudaStreamSynchronize(c->stream));
+            if (FILE *f = fopen(dbg_file, "wb")) {
+                fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+                fclose(f);
+            }
+            cudaFree(a.dbg);
+        }
+        return bis_prof_end(c, BIS_PROF_SPTRSV);
+    }
+    // variant 2: per-level completion counters (kept for comparison)
+    BIS_CUDA(cudaMemsetAsync(lv.d_level_done, 0, sizeof(unsigned int) * (size_t)lv.n_levels, c->stream));
     sptrsv_level_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a);
     BIS_LAUNCH_CHECK(c);
     return bis_prof_end(c, BIS_PROF_SPTRSV);

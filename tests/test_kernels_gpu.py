@@ -230,7 +230,7 @@ def test_spmv_and_fused_forms_vs_reference_fixture(ctx, name):
 
 
 # ---- triangular solves and preconditioners: bit-exact ------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("name", ["fdm2d16", "band_klein", "hpcg16"])
 def test_triangular_solves_bit_exact(ctx, name, variant):
     g = golden(name)
