@@ -110,6 +110,12 @@ extern "C" int bis_context_create_distributed(int device, int rank, int nranks,
             delete c;
             return 1;
         }
+        if (bis_peer_link_setup(c) != 0) {
+            ncclCommDestroy(c->comm_halo);
+            ncclCommDestroy(c->comm);
+            delete c;
+            return 1;
+        }
     }
     *ctx = c;
     return 0;
@@ -119,6 +125,7 @@ extern "C" int bis_context_destroy(bis_context *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    bis_peer_link_teardown(c);
     if (c->comm_halo) ncclCommDestroy(c->comm_halo);
     if (c->comm) ncclCommDestroy(c->comm);
     cudaFree(c->d_scalars);
@@ -146,8 +153,9 @@ extern "C" int bis_context_synchronize(bis_context *c) {
     BIS_CUDA(cudaMemcpy(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) {
         cudaMemset(c->d_errflag, 0, sizeof(int));
-        bis_set_error("device watchdog fired (code %d): a level-scheduled triangular solve did "
-                      "not make progress", flag);
+        bis_set_error("device watchdog fired (code %d): %s", flag,
+                      flag >= 20 ? "a peer rank did not deliver its part of a reduction or halo exchange"
+                                 : "a level-scheduled triangular solve did not make progress");
         return 3;
     }
     return 0;
@@ -171,6 +179,7 @@ extern "C" int bis_context_info(bis_context *c, int64_t info[8]) {
     info[2] = (int64_t)tot;
     info[3] = c->launches;
     info[4] = (int64_t)c->l2_bytes;
+    info[5] = (c->peer_on && c->opt_dist_p2p) ? 1 : 0;   // 1: collectives run over peer memory, 0: NCCL
     return 0;
 }
 
@@ -263,6 +272,11 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     BIS_REQUIRE(c && key, "null argument");
     std::string k(key);
     if (k == "spmv_variant") c->opt_spmv_variant = value;
+    else if (k == "dist_p2p") {
+        // the transport must change on all ranks at the same point of the stream
+        BIS_CUDA(cudaStreamSynchronize(c->stream));
+        c->opt_dist_p2p = value;
+    }
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
     else if (k == "trsv_variant") c->opt_trsv_variant = value;
     else if (k == "trsv_debug") c->opt_trsv_debug = value;
@@ -351,6 +365,7 @@ extern "C" int bis_scalar_copy(bis_context *c, int dst_slot, int src_slot) {
 // Called after a reduction kernel wrote its slot(s): sum over ranks.
 int bis_reduce_finish(bis_context *c, int slot_a, int slot_b) {
     if (c->nranks <= 1) return 0;
+    if (c->peer_on && c->opt_dist_p2p) return 0;   // the reducing kernel's last block already summed over ranks
     if (slot_a >= 0 && slot_b == slot_a + 1) {
         BIS_NCCL(ncclAllReduce(c->d_scalars + slot_a, c->d_scalars + slot_a, 2, ncclDouble, ncclSum,
                                c->comm, c->stream));
@@ -375,5 +390,14 @@ RedArgs bis_red_args(bis_context *c, int slot_a, int slot_b) {
     ra.block_offset = 0;
     ra.total_blocks = 0;
     ra.finalize = 1;
+    ra.peer_n = 0;
+    ra.peer_rank = c->rank;
+    ra.peer_epoch = 0;
+    for (int p = 0; p < BIS_MAX_PEERS; ++p) ra.peer_bank[p] = c->peer_bank[p];
+    ra.errflag = c->d_errflag;
+    if (c->nranks > 1 && c->peer_on && c->opt_dist_p2p && (slot_a >= 0 || slot_b >= 0)) {
+        ra.peer_n = c->nranks;
+        ra.peer_epoch = ++c->red_epoch;
+    }
     return ra;
 }

@@ -21,6 +21,8 @@
 #include <thrust/unique.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -72,6 +74,83 @@ __global__ void pack_kernel(int64_t n_send, const int *idx, const double *x, dou
         buf[i] = x[idx[i]];
 }
 
+// Peer-memory halo exchange ------------------------------------------------------------------
+// The pack kernel of rank r stores x[send_idx[i]] straight into the ghost buffer of the rank
+// that needs it (NVLink stores through the CUDA-IPC mapping), then publishes the exchange's
+// epoch in that rank's bank; the receiver's boundary rows start behind halo_wait_kernel.
+// Ghost buffers exist twice (epoch parity).  Before overwriting the copy last read by exchange
+// e-2 the sender checks the receiver's ack: a rank acks epoch e (to every rank) at the start
+// of its own pack e, which stream order places after all of its SpMVs before e.
+struct HaloPeerArgs {
+    int n_dst, n_ranks, me;
+    int dst_rank[BIS_MAX_PEERS];
+    int64_t seg_off[BIS_MAX_PEERS + 1];            // segments of the send list, one per destination
+    double *dst[BIS_MAX_PEERS];                    // where that segment lands (destination's ghost copy of this parity)
+    unsigned long long *dst_flag[BIS_MAX_PEERS];   // destination's bank: HALO_FLAG + me
+    unsigned long long *ack_out[BIS_MAX_PEERS];    // rank p's bank: HALO_ACK + me
+    const unsigned long long *ack_in;              // my bank: HALO_ACK
+    unsigned long long epoch;
+    unsigned int *ticket;
+    int *errflag;
+};
+
+__global__ void __launch_bounds__(256) pack_peer_kernel(HaloPeerArgs a, const int *idx, const double *x) {
+    __shared__ bool s_last;
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0 && t < a.n_ranks && t != a.me)
+        *reinterpret_cast<volatile unsigned long long *>(a.ack_out[t]) = a.epoch;
+    if (t < a.n_dst && a.epoch >= 2) {
+        const volatile unsigned long long *ack = a.ack_in + a.dst_rank[t];
+        const unsigned long long t0 = bis_globaltimer();
+        while (*ack + 1 < a.epoch) {
+            if (bis_globaltimer() - t0 > BIS_PEER_TIMEOUT_NS) {
+                atomicExch(a.errflag, 30 + a.dst_rank[t]);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t n_send = a.seg_off[a.n_dst];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < n_send; i += (int64_t)gridDim.x * blockDim.x) {
+        int d = 0;
+        while (i >= a.seg_off[d + 1]) ++d;
+        a.dst[d][i - a.seg_off[d]] = x[idx[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    if (t < a.n_dst) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(a.dst_flag[t]) = a.epoch;
+    }
+    if (t == 0) *a.ticket = 0u;
+}
+
+struct HaloWaitArgs {
+    int n_src;
+    int src_rank[BIS_MAX_PEERS];
+    const unsigned long long *flag;   // my bank: HALO_FLAG
+    unsigned long long epoch;
+    int *errflag;
+};
+
+__global__ void halo_wait_kernel(HaloWaitArgs a) {
+    const int t = threadIdx.x;
+    if (t < a.n_src) {
+        const volatile unsigned long long *f = a.flag + a.src_rank[t];
+        const unsigned long long t0 = bis_globaltimer();
+        while (*f < a.epoch) {
+            if (bis_globaltimer() - t0 > BIS_PEER_TIMEOUT_NS) {
+                atomicExch(a.errflag, 40 + a.src_rank[t]);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+
 __global__ void sub_offset_kernel(int64_t n, int *v, int off) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
@@ -79,6 +158,93 @@ __global__ void sub_offset_kernel(int64_t n, int *v, int off) {
 }
 
 } // namespace
+
+// ---- peer-memory link ------------------------------------------------------------------------
+// Collective.  Returns 0 with *ok = 1 when every rank mapped every other rank's buffer,
+// 0 with *ok = 0 when some rank could not (the callers then keep NCCL), non-zero on a hard error.
+static int peer_map_try(bis_context *c, void *mine, void **out, int *ok) {
+    const int P = c->nranks, me = c->rank;
+    cudaStream_t st = c->stream;
+    *ok = 0;
+    cudaIpcMemHandle_t hmine;
+    int good = cudaIpcGetMemHandle(&hmine, mine) == cudaSuccess ? 1 : 0;
+    if (!good) { cudaGetLastError(); memset(&hmine, 0, sizeof hmine); }
+    unsigned char *d_h = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    BIS_CUDA(cudaMalloc(&d_h, hb * (size_t)(P + 1)));
+    BIS_CUDA(cudaMemcpyAsync(d_h + hb * P, &hmine, hb, cudaMemcpyHostToDevice, st));
+    BIS_NCCL(ncclAllGather(d_h + hb * P, d_h, hb, ncclUint8, c->comm, st));
+    std::vector<cudaIpcMemHandle_t> all(P);
+    BIS_CUDA(cudaMemcpyAsync(all.data(), d_h, hb * P, cudaMemcpyDeviceToHost, st));
+    BIS_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_h);
+    std::vector<void *> opened;
+    for (int p = 0; p < P; ++p) {
+        out[p] = nullptr;
+        if (p == me) { out[p] = mine; continue; }
+        if (!good) continue;
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            good = 0;
+            continue;
+        }
+        out[p] = q;
+        opened.push_back(q);
+    }
+    // agree: the link is used only if it is up everywhere
+    int *d_ok = nullptr;
+    BIS_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+    BIS_CUDA(cudaMemcpyAsync(d_ok, &good, sizeof(int), cudaMemcpyHostToDevice, st));
+    BIS_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, st));
+    int all_good = 0;
+    BIS_CUDA(cudaMemcpyAsync(&all_good, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BIS_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_ok);
+    if (!all_good) {
+        for (void *q : opened) cudaIpcCloseMemHandle(q);
+        for (int p = 0; p < P; ++p) out[p] = (p == me) ? mine : nullptr;
+        return 0;
+    }
+    for (void *q : opened) c->ipc_opened.push_back(q);
+    *ok = 1;
+    return 0;
+}
+
+int bis_peer_map(bis_context *c, void *mine, void **out) {
+    int ok = 0;
+    BIS_CHECK(peer_map_try(c, mine, out, &ok));
+    return ok ? 0 : -1;
+}
+
+int bis_peer_link_setup(bis_context *c) {
+    c->peer_on = 0;
+    if (c->nranks <= 1 || c->nranks > BIS_MAX_PEERS) return 0;
+    const char *env = getenv("BIS_P2P");
+    if (env && env[0] == '0') return 0;   // must be set on every rank alike
+    BIS_CUDA(cudaMalloc(&c->d_bank, BIS_BANK_BYTES));
+    BIS_CUDA(cudaMemset(c->d_bank, 0, BIS_BANK_BYTES));
+    BIS_CUDA(cudaMalloc(&c->d_pack_ticket, sizeof(unsigned int)));
+    BIS_CUDA(cudaMemset(c->d_pack_ticket, 0, sizeof(unsigned int)));
+    BIS_CUDA(cudaDeviceSynchronize());   // banks are zero before the allgather below lets anyone write
+    void *banks[BIS_MAX_PEERS] = {};
+    int ok = 0;
+    BIS_CHECK(peer_map_try(c, c->d_bank, banks, &ok));
+    if (!ok) return 0;
+    for (int p = 0; p < c->nranks; ++p) c->peer_bank[p] = static_cast<double *>(banks[p]);
+    c->peer_on = 1;
+    return 0;
+}
+
+void bis_peer_link_teardown(bis_context *c) {
+    for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+    c->ipc_opened.clear();
+    cudaFree(c->d_bank);
+    cudaFree(c->d_pack_ticket);
+    c->d_bank = nullptr;
+    c->d_pack_ticket = nullptr;
+    c->peer_on = 0;
+}
 
 // A->d_col holds GLOBAL ids on entry (d_col_global == A->d_col) and local ids
 // (ghosts >= n_cols) on return.
@@ -139,7 +305,14 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
     HaloPlan &h = A->halo;
     h.n_ghost = (int64_t)ghost_h.size();
     BIS_CUDA(cudaMalloc(&h.d_ghost_global, sizeof(int) * std::max<size_t>(ghost_h.size(), 1)));
-    BIS_CUDA(cudaMalloc(&h.d_ghost, sizeof(double) * (std::max<size_t>(ghost_h.size(), 1) + 2)));
+    h.ghost_stride = (int64_t)((ghost_h.size() + 2 + 15) & ~(size_t)15);
+    {
+        size_t bytes = sizeof(double) * 2 * (size_t)h.ghost_stride;
+        bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        BIS_CUDA(cudaMalloc(&h.d_ghost, bytes));
+        BIS_CUDA(cudaMemsetAsync(h.d_ghost, 0, bytes, st));
+    }
+    h.cur_ghost = h.d_ghost;
     if (!ghost_h.empty())
         BIS_CUDA(cudaMemcpyAsync(h.d_ghost_global, ghost_h.data(), sizeof(int) * ghost_h.size(), cudaMemcpyHostToDevice, st));
 
@@ -207,13 +380,79 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
     h.interior_begin = (int64_t)range[0];
     h.interior_end = (int64_t)range[1];
     if (h.interior_end < h.interior_begin) h.interior_end = h.interior_begin;   // no interior
+
+    // (h) peer-memory transport: map every rank's ghost buffer, learn where my values land in it
+    h.peer_ready = false;
+    if (c->peer_on) {
+        BIS_CUDA(cudaStreamSynchronize(st));
+        void *pg[BIS_MAX_PEERS] = {};
+        int ok = 0;
+        BIS_CHECK(peer_map_try(c, h.d_ghost, pg, &ok));
+        int64_t *d_ro = nullptr;
+        BIS_CUDA(cudaMalloc(&d_ro, sizeof(int64_t) * (size_t)(P + 1) * (P + 2)));
+        std::vector<int64_t> mine_ro(P + 2);
+        for (int p = 0; p <= P; ++p) mine_ro[p] = h.recv_off[p];
+        mine_ro[P + 1] = ok ? h.ghost_stride : -1;
+        BIS_CUDA(cudaMemcpyAsync(d_ro + (size_t)P * (P + 2), mine_ro.data(), sizeof(int64_t) * (P + 2), cudaMemcpyHostToDevice, st));
+        BIS_NCCL(ncclAllGather(d_ro + (size_t)P * (P + 2), d_ro, P + 2, ncclInt64, c->comm, st));
+        std::vector<int64_t> all_ro((size_t)P * (P + 2));
+        BIS_CUDA(cudaMemcpyAsync(all_ro.data(), d_ro, sizeof(int64_t) * all_ro.size(), cudaMemcpyDeviceToHost, st));
+        BIS_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_ro);
+        if (ok) {
+            h.peer_recv_off.assign(P, 0);
+            h.peer_stride.assign(P, 0);
+            for (int p = 0; p < P; ++p) {
+                h.peer_ghost[p] = static_cast<double *>(pg[p]);
+                h.peer_recv_off[p] = all_ro[(size_t)p * (P + 2) + me];
+                h.peer_stride[p] = all_ro[(size_t)p * (P + 2) + P + 1];
+            }
+            h.peer_ready = true;
+        }
+    }
     return 0;
 }
 
-// Start the halo exchange of x on the comm stream (after everything already
-// queued on the main stream, which produced x and consumed the old ghosts).
+// Start the halo exchange of x.  Peer-memory transport: one pack kernel on the main stream that
+// stores into the neighbours' ghost buffers.  NCCL transport: pack + grouped send/recv on the
+// comm stream (after everything already queued on the main stream, which produced x and
+// consumed the old ghosts).
 int bis_halo_exchange_begin(bis_context *c, const bis_matrix *A, const double *x) {
     const HaloPlan &h = A->halo;
+    if (c->peer_on && c->opt_dist_p2p && h.peer_ready) {
+        const unsigned long long e = ++c->halo_epoch;
+        const int par = (int)(e & 1ull);
+        h.cur_ghost = h.d_ghost + (size_t)par * h.ghost_stride;
+        HaloPeerArgs a;
+        a.n_dst = 0; a.n_ranks = c->nranks; a.me = c->rank;
+        a.seg_off[0] = 0;
+        unsigned long long *mybank = reinterpret_cast<unsigned long long *>(c->d_bank);
+        for (int p = 0; p < c->nranks; ++p) {
+            unsigned long long *pb = reinterpret_cast<unsigned long long *>(c->peer_bank[p]);
+            a.ack_out[p] = pb + BIS_BANK_HALO_ACK + c->rank;
+            const int64_t ns = h.send_off[p + 1] - h.send_off[p];
+            if (p == c->rank || ns == 0) continue;
+            const int d = a.n_dst++;
+            a.dst_rank[d] = p;
+            a.seg_off[d] = h.send_off[p];      // the send list is ordered by destination rank
+            a.seg_off[d + 1] = h.send_off[p + 1];
+            a.dst[d] = h.peer_ghost[p] + (size_t)par * h.peer_stride[p] + h.peer_recv_off[p];
+            a.dst_flag[d] = pb + BIS_BANK_HALO_FLAG + c->rank;
+        }
+        for (int d = a.n_dst; d < BIS_MAX_PEERS; ++d) {
+            a.dst_rank[d] = 0; a.dst[d] = nullptr; a.dst_flag[d] = nullptr;
+            a.seg_off[d + 1] = a.seg_off[a.n_dst];
+        }
+        for (int p = c->nranks; p < BIS_MAX_PEERS; ++p) a.ack_out[p] = nullptr;
+        a.ack_in = mybank + BIS_BANK_HALO_ACK;
+        a.epoch = e;
+        a.ticket = c->d_pack_ticket;
+        a.errflag = c->d_errflag;
+        pack_peer_kernel<<<bis_blocks_for(h.n_send, 256 * 4, c->sm_count * 2), 256, 0, c->stream>>>(a, h.d_send_idx, x);
+        BIS_LAUNCH_CHECK(c);
+        return 0;
+    }
+    h.cur_ghost = h.d_ghost;
     BIS_CUDA(cudaEventRecord(c->ev_main, c->stream));
     BIS_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
     if (h.n_send) {
@@ -234,8 +473,23 @@ int bis_halo_exchange_begin(bis_context *c, const bis_matrix *A, const double *x
     return 0;
 }
 
+// Everything queued on the main stream after this sees the ghosts of the current exchange.
 int bis_halo_exchange_end(bis_context *c, const bis_matrix *A) {
-    (void)A;
+    const HaloPlan &h = A->halo;
+    if (c->peer_on && c->opt_dist_p2p && h.peer_ready) {
+        HaloWaitArgs w;
+        w.n_src = 0;
+        for (int p = 0; p < c->nranks; ++p)
+            if (p != c->rank && h.recv_off[p + 1] > h.recv_off[p]) w.src_rank[w.n_src++] = p;
+        for (int d = w.n_src; d < BIS_MAX_PEERS; ++d) w.src_rank[d] = 0;
+        if (w.n_src == 0) return 0;
+        w.flag = reinterpret_cast<const unsigned long long *>(c->d_bank) + BIS_BANK_HALO_FLAG;
+        w.epoch = c->halo_epoch;
+        w.errflag = c->d_errflag;
+        halo_wait_kernel<<<1, 32, 0, c->stream>>>(w);
+        BIS_LAUNCH_CHECK(c);
+        return 0;
+    }
     BIS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
     return 0;
 }

@@ -68,6 +68,19 @@ void bis_set_error(const char *fmt, ...);
 // partials in a fixed order and writes the device scalar slot(s).
 constexpr int BIS_MAX_RED_BLOCKS = 8192;   // partials per quantity
 constexpr int BIS_MAX_RED = 2;             // quantities per kernel
+constexpr int BIS_MAX_PEERS = 8;           // ranks a peer-memory link can span (one NVSwitch box)
+
+// Peer-memory link (bis_dist.cu): every rank owns a small "bank" that all other ranks of the
+// box map through CUDA IPC.  Dot products are summed over ranks by the last block of the
+// reducing kernel itself (it stores its partial into every peer's bank over NVLink and adds
+// the ranks' partials in rank order), and halo values are stored straight into the
+// neighbour's ghost buffer by the pack kernel: no NCCL call on the iteration path.
+// Bank layout, in doubles: [0, 2*P*4) reduction records {v0, v1, epoch, -} indexed by
+// (epoch parity, source rank); BIS_BANK_HALO_FLAG + s: newest halo epoch whose values from
+// source s have landed; BIS_BANK_HALO_ACK + q: rank q has finished every SpMV before that epoch.
+constexpr int BIS_BANK_HALO_FLAG = 256;
+constexpr int BIS_BANK_HALO_ACK = 320;
+constexpr size_t BIS_BANK_BYTES = (size_t)2 << 20;
 
 struct RedArgs {
     double *partials;        // [BIS_MAX_RED][BIS_MAX_RED_BLOCKS]
@@ -77,6 +90,12 @@ struct RedArgs {
     int block_offset;        // first partial index written by this launch
     int total_blocks;        // partials to add when finalising
     int finalize;            // 0: only write partials (a later launch finalises)
+    // sum over ranks through peer memory (peer_n > 1), done by the finalising block
+    int peer_n;
+    int peer_rank;
+    unsigned long long peer_epoch;
+    double *peer_bank[BIS_MAX_PEERS];
+    int *errflag;
 };
 
 // Optional per-kernel-family device timing (bis_profile_enable): cudaEvent pairs
@@ -108,8 +127,17 @@ struct bis_context {
     size_t flush_bytes = 0;
     ncclComm_t comm = nullptr;           // reductions (main stream)
     ncclComm_t comm_halo = nullptr;      // halo exchange (comm stream)
+    // peer-memory link (nranks <= BIS_MAX_PEERS on one box); NCCL stays as the fallback transport
+    int peer_on = 0;
+    double *d_bank = nullptr;                       // this rank's bank (BIS_BANK_BYTES)
+    double *peer_bank[BIS_MAX_PEERS] = {};          // every rank's bank as mapped here
+    unsigned long long red_epoch = 0;               // finalised reductions so far (same on all ranks)
+    unsigned long long halo_epoch = 0;              // halo exchanges so far (same on all ranks)
+    unsigned int *d_pack_ticket = nullptr;
+    std::vector<void *> ipc_opened;                 // mappings to close
     int64_t launches = 0;
     // options
+    int opt_dist_p2p = 1;       // 0: NCCL transport even when the peer-memory link is up
     int opt_spmv_variant = 0;
     int opt_spmv_lanes = 0;
     int opt_trsv_variant = 0;
@@ -156,6 +184,13 @@ struct HaloPlan {
     std::vector<int64_t> recv_off;       // [nranks+1] segments of d_ghost
     std::vector<int64_t> send_off;       // [nranks+1] segments of d_sendbuf
     int64_t interior_begin = 0, interior_end = 0;   // rows without ghosts
+    // peer-memory transport: d_ghost holds two copies (epoch parity), ghost_stride doubles apart
+    int64_t ghost_stride = 0;
+    mutable const double *cur_ghost = nullptr;      // the copy the current SpMV reads
+    double *peer_ghost[BIS_MAX_PEERS] = {};         // rank p's d_ghost as mapped here
+    std::vector<int64_t> peer_recv_off;             // [nranks] where my values start in rank p's ghost list
+    std::vector<int64_t> peer_stride;               // [nranks] rank p's ghost_stride
+    bool peer_ready = false;
 };
 
 // Acceleration structure of SpMV variant 3 (bis_spmv_win.cuh), derived lazily from the CRS arrays.
@@ -197,6 +232,10 @@ int bis_reduce_finish(bis_context *ctx, int slot_a, int slot_b);
 RedArgs bis_red_args(bis_context *ctx, int slot_a, int slot_b);
 int bis_halo_exchange_begin(bis_context *ctx, const bis_matrix *A, const double *x);
 int bis_halo_exchange_end(bis_context *ctx, const bis_matrix *A);
+int bis_peer_link_setup(bis_context *ctx);
+void bis_peer_link_teardown(bis_context *ctx);
+// maps a cudaMalloc'ed buffer of every rank into this process (collective); out[p] for p == rank is `mine`
+int bis_peer_map(bis_context *ctx, void *mine, void **out);
 int bis_matrix_finalize_distributed(bis_context *ctx, bis_matrix *A,
                                     int *d_col_global_in_place);
 int bis_build_levels_device(bis_context *ctx, bis_matrix *T);

@@ -260,7 +260,7 @@ int launch_segment(bis_context *c, const bis_matrix *A, const double *x, const S
     if (tma_plan(c, A, &plan)) {
         SpmvTmaIn in;
         in.rp = A->d_rp; in.col = A->d_col; in.val = A->d_val; in.x = x;
-        in.ghost = A->halo.d_ghost; in.n_owned = A->n_cols;
+        in.ghost = A->halo.cur_ghost; in.n_owned = A->n_cols;
         in.lo = sg.lo; in.cnt = sg.cnt;
         in.tiles_per_cta = 1; in.cap = 0; in.nstage = 0; in.interleave = 1; in.rows = 0;
         if (A->rp_bytes == 8)
@@ -271,7 +271,7 @@ int launch_segment(bis_context *c, const bis_matrix *A, const double *x, const S
     }
     SpmvIn in;
     in.rp = A->d_rp; in.col = A->d_col; in.val = A->d_val; in.x = x;
-    in.ghost = A->halo.d_ghost; in.n_owned = A->n_cols;
+    in.ghost = A->halo.cur_ghost; in.n_owned = A->n_cols;
     in.lo1 = sg.lo; in.cnt1 = sg.cnt; in.lo2 = 0; in.cnt2 = 0;
     return sg.ghost ? launch_rp<true, Epi>(c, A, in, epi, ra, nb) : launch_rp<false, Epi>(c, A, in, epi, ra, nb);
 }
@@ -389,7 +389,7 @@ int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const doub
     SpmvWinIn in;
     in.rp = A->d_rp; in.val = A->d_val; in.lidx = w.d_lidx;
     in.seg_start = w.d_seg_start; in.seg_len = w.d_seg_len; in.seg_off = w.d_seg_off; in.nseg = w.d_nseg;
-    in.x = x; in.ghost = A->halo.d_ghost; in.n_rows = A->n_rows;
+    in.x = x; in.ghost = A->halo.cur_ghost; in.n_rows = A->n_rows;
     in.tile_lo = tile_lo; in.tile_cnt = tile_cnt;
     in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.stage_bytes = p.stage_bytes;
     in.debug = c->opt_spmv_debug;
@@ -428,7 +428,9 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     // work list: row ranges (variants 1, 2) or tile ranges (variant 3); `ghost` = needs the halo
     Segment seg[3];
     int nseg = 0;
-    const bool halo = A->distributed && A->halo.n_ghost > 0;
+    // every rank of a distributed matrix takes part in the exchange, also one that needs no ghosts
+    const bool halo = A->distributed;
+    const bool has_ghost = A->halo.n_ghost > 0;
     const int64_t unit = use_win ? A->win.R : 1;
     const int64_t n_units = use_win ? A->win.n_tiles : A->n_rows;
     if (!halo) {
@@ -438,7 +440,9 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
         // in flight, then the boundary strips (variant 3: whole tiles inside the interior).
         BIS_CHECK(bis_halo_exchange_begin(c, A, x));
         const int64_t ib = (A->halo.interior_begin + unit - 1) / unit, ie = A->halo.interior_end / unit;
-        if (ie > ib) {
+        if (!has_ghost) {
+            seg[nseg++] = {0, n_units, false};
+        } else if (ie > ib) {
             seg[nseg++] = {ib, ie - ib, false};
             if (ib > 0) seg[nseg++] = {0, ib, true};
             if (n_units > ie) seg[nseg++] = {ie, n_units - ie, true};

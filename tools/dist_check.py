@@ -25,10 +25,27 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 name = f"HPCG-{n}"
 ok = True
 results = {}
+peer = ctx.info()["peer_memory"]
+if rank == 0:
+    print(f"transport: {'peer memory (CUDA IPC + NVLink stores in the kernels)' if peer else 'NCCL'}", flush=True)
 for method, pre in (("cg", "none"), ("cg", "j"), ("bi", "j"), ("j", "none"), ("gm", "j")):
     r = host.solve(ctx, method, pre, matrix_name=name, want_x=False, max_iters=300)
     results[(method, pre)] = r
 dist.barrier()
+if peer:
+    # the same solves over NCCL: only the order in which the ranks' partial sums are added differs
+    ctx.set_option("dist_p2p", 0)
+    dist.barrier()
+    for (method, pre), r in list(results.items()):
+        q = host.solve(ctx, method, pre, matrix_name=name, want_x=False, max_iters=300)
+        k = min(q.history.size, r.history.size)
+        err = float(np.max(np.abs(q.history[:k] - r.history[:k])) / r.history[0])
+        if rank == 0:
+            print(f"{name} -{method} -p {pre}: peer-memory vs NCCL transport: its {r.iter_count} vs {q.iter_count}, "
+                  f"max |dr|/r0 = {err:.2e}", flush=True)
+        ok &= err <= 1e-10
+    ctx.set_option("dist_p2p", 1)
+    dist.barrier()
 if rank == 0:
     with capi.Context(local) as solo:
         for (method, pre), r in results.items():
