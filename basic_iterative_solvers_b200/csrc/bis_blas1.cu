@@ -12,7 +12,6 @@ namespace {
 
 constexpr int EW_THREADS = 256;
 constexpr int EW_UNROLL = 4;
-constexpr int EW_MAXIN = 6;
 
 // Input vectors of a streaming kernel.  The kernel reads ALL inputs of EW_UNROLL elements before it
 // runs the per-element body (which stores): outputs may alias inputs element-wise

@@ -280,8 +280,12 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
     else if (k == "trsv_variant") c->opt_trsv_variant = value;
     else if (k == "trsv_debug") c->opt_trsv_debug = value;
+    else if (k == "trsv_gates") c->opt_trsv_gates = value;
+    else if (k == "trsv_sleep1") c->opt_trsv_sleep[0] = value;
+    else if (k == "trsv_sleep2") c->opt_trsv_sleep[1] = value;
+    else if (k == "trsv_sleep3") c->opt_trsv_sleep[2] = value;
+    else if (k == "trsv_sleep4") c->opt_trsv_sleep[3] = value;
     else if (k == "trsv_poll_ns") c->opt_trsv_poll_ns = value;
-    else if (k == "trsv_warp_flag") c->opt_trsv_warp_flag = value;
     else if (k == "spmv_rows") c->opt_spmv_rows = value;
     else if (k == "spmv_stages") c->opt_spmv_stages = value;
     else if (k == "spmv_smem_kb") c->opt_spmv_smem_kb = value;

@@ -142,7 +142,8 @@ struct bis_context {
     int opt_spmv_lanes = 0;
     int opt_trsv_variant = 0;
     int opt_trsv_poll_ns = 0;   // sleep between polls in the triangular solve (0: default)
-    int opt_trsv_warp_flag = 0; // triangular solve: one poller per warp on the producing warp's flag (experiment)
+    int opt_trsv_gates = 1;     // triangular solve: staged waiting on the per-row gates (0: poll all operands)
+    int opt_trsv_sleep[4] = {0, 60, 250, 1000};   // ns between polls of a gate 1, 2, 3, >= 4 levels back (>= 6: twice the last)
     int opt_trsv_debug = 0;     // dump per-row timestamps of each solve to $BIS_TRSV_DEBUG_FILE
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
@@ -160,15 +161,13 @@ struct LevelSets {
     int64_t n_slots = 0;              // == n_rows: position in the level-ordered row list
     int *d_slot_row = nullptr;        // [n_slots] original row
     int *d_slot_level = nullptr;      // [n_slots] level of that row (non-decreasing)
-    int *d_slot_crit = nullptr;       // [n_slots] column of the dependency that completes last (-1: none)
-    int *d_warp_crit = nullptr;       // [n_slots/32] the other warp (of 32 slots) this warp needs that comes last
-    unsigned int *d_warp_flag = nullptr;   // [n_slots/32] set when all rows of that warp are published
+    int *d_slot_gate = nullptr;       // [4*n_slots] three gate columns + their packed level distances (bis_matrix.cu)
     int *d_level_size = nullptr;      // [n_levels] rows per level
     std::vector<int64_t> level_start; // [n_levels+1] host copy (per-level launch variant)
     unsigned int *d_level_done = nullptr;   // [n_levels] completion counters
     unsigned int *d_ticket = nullptr; // chunk ticket
-    double *d_w = nullptr;            // [n_slots] scratch of the solve: sentinel until the row's value is final
-    // level-ordered copy of the strict factor (rows stored in slot order)
+    double *d_w = nullptr;            // [n_slots] working vector of the solve IN SLOT ORDER: sentinel until the slot's value is final
+    // level-ordered copy of the strict factor (rows stored in slot order, operands named by slot)
     int64_t *d_rp = nullptr;          // [n_slots+1]
     int *d_col = nullptr;
     double *d_val = nullptr;

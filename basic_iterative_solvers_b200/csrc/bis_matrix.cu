@@ -27,9 +27,7 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->d_val);
     cudaFree(A->lv.d_slot_row);
     cudaFree(A->lv.d_slot_level);
-    cudaFree(A->lv.d_slot_crit);
-    cudaFree(A->lv.d_warp_crit);
-    cudaFree(A->lv.d_warp_flag);
+    cudaFree(A->lv.d_slot_gate);
     cudaFree(A->lv.d_level_size);
     cudaFree(A->lv.d_level_done);
     cudaFree(A->lv.d_ticket);
@@ -193,48 +191,62 @@ extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t n
             slot_level[s] = level[r];
         }
     }
-    // per row: the dependency that becomes final LAST (largest level, then largest slot) -- the solve
-    // polls this one value while it waits and looks at the others only once it is there
-    std::vector<int> slot_crit((size_t)n, -1);
+    // per row: up to three "gates" -- dependencies whose level lies further and further back
+    // (the oldest one; the newest one at least 3 levels back; the newest one 2 levels back).  A row that
+    // waits looks at ONE gate at a time and sleeps in proportion to the gate's distance, so rows far ahead
+    // of the wavefront cost one load every few microseconds instead of a load per operand per poll
+    // (the SM's load pipe, not the L2 round trip, bounded the level-to-level latency before).
+    // gate[4*sl + i] = SLOT of gate i (-1: none), gate[4*sl + 3] = the three distances, one byte each.
+    std::vector<int> slot_gate((size_t)n * 4, -1);
     {
         std::vector<int64_t> slot_of((size_t)n);
         for (int64_t sl = 0; sl < n; ++sl) slot_of[slot_row[sl]] = sl;
         for (int64_t sl = 0; sl < n; ++sl) {
             const int r = slot_row[sl];
-            int64_t best = -1;
-            for (int32_t k = rp[r]; k < rp[r + 1]; ++k)
-                if (slot_of[col[k]] > best) {
-                    best = slot_of[col[k]];
-                    slot_crit[sl] = col[k];
-                }
-        }
-    }
-    // per warp of 32 consecutive slots: the (other) warp whose rows it needs that comes last in slot order;
-    // the solve watches that warp's completion flag with ONE poller per warp instead of 32 scattered ones
-    const int64_t n_warps = (n + 31) / 32;
-    std::vector<int> warp_crit((size_t)std::max<int64_t>(n_warps, 1), -1);
-    {
-        std::vector<int64_t> slot_of((size_t)n);
-        for (int64_t sl = 0; sl < n; ++sl) slot_of[slot_row[sl]] = sl;
-        for (int64_t sl = 0; sl < n; ++sl) {
-            const int r = slot_row[sl];
-            const int64_t me = sl / 32;
+            const int lvr = level[r];
+            int64_t best[3] = {-1, -1, -1};   // chosen by (level, slot) == slot order
+            int gcol[3] = {-1, -1, -1}, glev[3] = {0, 0, 0};
+            int64_t oldest = INT64_MAX;
             for (int32_t k = rp[r]; k < rp[r + 1]; ++k) {
-                const int64_t w = slot_of[col[k]] / 32;
-                if (w != me && w > warp_crit[me]) warp_crit[me] = (int)w;
+                const int cc = col[k];
+                const int d = lvr - level[cc];
+                const int64_t so = slot_of[cc];
+                // rows of one warp (32 consecutive slots) run their levels in lockstep: a gate inside the
+                // own warp could never open
+                if (so / 32 == sl / 32) continue;
+                if (d >= 4 && so < oldest) { oldest = so; gcol[0] = (int)so; glev[0] = level[cc]; }
+                if (d >= 3 && so > best[1]) { best[1] = so; gcol[1] = (int)so; glev[1] = level[cc]; }
+                if (d == 2 && so > best[2]) { best[2] = so; gcol[2] = (int)so; glev[2] = level[cc]; }
             }
+            if (gcol[0] == gcol[1]) gcol[0] = -1;
+            int packed = 0;
+            for (int i = 0; i < 3; ++i) {
+                slot_gate[4 * (size_t)sl + i] = gcol[i];
+                const int d = gcol[i] >= 0 ? std::min(lvr - glev[i], 15) : 0;
+                packed |= d << (8 * i);
+            }
+            slot_gate[4 * (size_t)sl + 3] = packed;
         }
     }
     std::vector<int64_t> rp2((size_t)n + 1, 0);
     std::vector<int32_t> col2((size_t)nnz);
     std::vector<double> val2((size_t)nnz);
-    for (int64_t s = 0; s < n; ++s) {
-        int r = slot_row[s];
-        int32_t len = rp[r + 1] - rp[r];
-        rp2[s + 1] = rp2[s] + len;
-        if (len) {
-            memcpy(&col2[rp2[s]], &col[rp[r]], sizeof(int32_t) * len);
-            memcpy(&val2[rp2[s]], &val[rp[r]], sizeof(double) * len);
+    // The level-ordered copy names its operands by SLOT, not by row: the solve keeps its working vector
+    // in slot order, so the 32 results of a warp are one contiguous 256-byte store and the operands of
+    // 32 consecutive slots (neighbouring rows of one level) fall into a few sectors of the previous
+    // levels instead of 32 scattered ones (tools/micro/wavefront.cu: the scattered sectors of a poll,
+    // not the L2 round trip, set the cost of a level-to-level hop).  Storage order inside a row is kept.
+    {
+        std::vector<int64_t> slot_of((size_t)n);
+        for (int64_t sl = 0; sl < n; ++sl) slot_of[slot_row[sl]] = sl;
+        for (int64_t s = 0; s < n; ++s) {
+            int r = slot_row[s];
+            int32_t len = rp[r + 1] - rp[r];
+            rp2[s + 1] = rp2[s] + len;
+            for (int32_t k = 0; k < len; ++k) {
+                col2[rp2[s] + k] = (int32_t)slot_of[col[rp[r] + k]];
+                val2[rp2[s] + k] = val[rp[r] + k];
+            }
         }
     }
     LevelSets &lv = T->lv;
@@ -244,9 +256,7 @@ extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t n
     int rc = 0;
     rc |= dev_alloc(&lv.d_slot_row, (size_t)n);
     rc |= dev_alloc(&lv.d_slot_level, (size_t)n);
-    rc |= dev_alloc(&lv.d_slot_crit, (size_t)n);
-    rc |= dev_alloc(&lv.d_warp_crit, (size_t)n_warps);
-    rc |= dev_alloc(&lv.d_warp_flag, (size_t)n_warps);
+    rc |= dev_alloc(&lv.d_slot_gate, (size_t)n * 4 + 4);
     rc |= dev_alloc(&lv.d_level_size, (size_t)n_levels);
     rc |= dev_alloc(&lv.d_level_done, (size_t)n_levels);
     rc |= dev_alloc(&lv.d_ticket, 1);
@@ -264,8 +274,7 @@ extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t n
     };
     BIS_CUDA(h2d(lv.d_slot_row, slot_row.data(), sizeof(int) * (size_t)n));
     BIS_CUDA(h2d(lv.d_slot_level, slot_level.data(), sizeof(int) * (size_t)n));
-    BIS_CUDA(h2d(lv.d_slot_crit, slot_crit.data(), sizeof(int) * (size_t)n));
-    BIS_CUDA(h2d(lv.d_warp_crit, warp_crit.data(), sizeof(int) * (size_t)n_warps));
+    BIS_CUDA(h2d(lv.d_slot_gate, slot_gate.data(), sizeof(int) * (size_t)n * 4));
     BIS_CUDA(h2d(lv.d_level_size, level_size.data(), sizeof(int) * (size_t)n_levels));
     BIS_CUDA(h2d(lv.d_rp, rp2.data(), sizeof(int64_t) * ((size_t)n + 1)));
     BIS_CUDA(h2d(lv.d_col, col2.data(), sizeof(int32_t) * (size_t)nnz));

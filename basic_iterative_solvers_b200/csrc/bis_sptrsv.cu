@@ -33,13 +33,11 @@ struct TrsvArgs {
     int64_t n_slots;
     const int *slot_row;
     const int *slot_level;
-    const int *slot_crit;
-    unsigned long long *dbg;   // debug timestamps (3 per row) or nullptr
-    unsigned int poll_ns;      // sleep between two polls of the missing operands
-    const int *warp_crit;
-    unsigned int *warp_flag;
-    int use_warp_flag;
-    const int64_t *rp;      // level-ordered
+    const int4 *gate;              // per slot: three gate slots + packed distances (nullptr: no staged waiting)
+    unsigned int gate_sleep[16];   // ns between polls, by the gate's level distance
+    unsigned long long *dbg;       // debug timestamps (4 per row) or nullptr
+    unsigned int poll_ns;          // sleep between two polls of the missing operands
+    const int64_t *rp;             // level-ordered copy: rows in slot order, operands named by slot
     const int *col;
     const double *val;
     const int *level_size;
@@ -55,7 +53,8 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
     return *reinterpret_cast<const volatile unsigned int *>(p);
 }
 
-__global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) {
+// Comparison variant (opt "trsv_variant" = 2): per-level completion counters.
+__global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a, double *w) {
     __shared__ unsigned int s_chunk;
     if (threadIdx.x == 0) s_chunk = atomicAdd(a.ticket, 1u);
     __syncthreads();
@@ -74,7 +73,6 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) 
         bb = a.b[row];
         dd = a.D[row];
     }
-    // prefetch the head of the row while earlier levels are still running
     double av[TRSV_PF];
     int cv[TRSV_PF];
 #pragma unroll
@@ -83,7 +81,6 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) 
         av[j] = ok ? __ldcs(a.val + s + j) : 0.0;
         cv[j] = ok ? __ldcs(a.col + s + j) : 0;
     }
-    // levels present in this warp (rows are sorted by level)
     int lv_lo = lvl, lv_hi = live ? lvl : -1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -105,7 +102,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) 
                         }
                     }
                 }
-                __threadfence();   // acquire: order the x loads after the counter read
+                __threadfence();   // acquire: order the operand loads after the counter read
             }
             __syncwarp();
         }
@@ -114,11 +111,13 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) 
             double sum = 0.0;
 #pragma unroll
             for (int j = 0; j < TRSV_PF; ++j)
-                if (s + j < e) sum = add_rn(sum, mul_rn(av[j], __ldcg(a.x + cv[j])));
+                if (s + j < e) sum = add_rn(sum, mul_rn(av[j], __ldcg(w + cv[j])));
             for (int64_t k = s + TRSV_PF; k < e; ++k)
-                sum = add_rn(sum, mul_rn(a.val[k], __ldcg(a.x + a.col[k])));
-            __stcg(a.x + row, div_rn(sub_rn(bb, sum), dd));
-            __threadfence();   // release: x[row] visible before the counter moves
+                sum = add_rn(sum, mul_rn(a.val[k], __ldcg(w + a.col[k])));
+            const double r = div_rn(sub_rn(bb, sum), dd);
+            __stcg(w + slot, r);
+            a.x[row] = r;
+            __threadfence();   // release: the value is visible before the counter moves
         }
         const unsigned int m = __ballot_sync(0xffffffffu, mine);
         if (lane == 0 && m) atomicAdd(a.level_done + lv, (unsigned int)__popc(m));
@@ -126,18 +125,28 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a) 
 }
 
 // ---- default: the value is its own ready flag ("sync-free" in level order) -----------------------
-// The level counters above make every row of level l wait for ALL rows of level l-1 and funnel
-// thousands of pollers and the completing atomics through one L2 address per level (measured: ~5 us
-// per level).  Here a row waits only for the rows it actually reads, and what it polls is the value
-// itself: results go to a scratch vector w that is pre-filled with a sentinel (a NaN payload the
-// arithmetic can never produce), a consumer re-reads w[dep] (8-byte loads are single-copy atomic) until
-// it is not the sentinel -- the load that observes readiness also delivers the operand, so one hop of
-// the dependency chain costs one store-to-L2 plus one load-from-L2, with no fence and no second round
-// trip.  All dependencies of a row are polled together (independent loads).  Rows are still handed out
-// in level order through the ticket counter, so every dependency belongs to an earlier slot, i.e. to a
-// block that is already running (or to an earlier level handled by this very warp): no deadlock, no
-// co-residency assumption.  x may alias b (each thread reads its b[row] before any x is written and
-// nobody else touches that element).  Summation order per row is unchanged: bit-identical results.
+// A row waits only for the rows it actually reads, and what it polls is the value itself: results go
+// to a working vector w (in SLOT order) that is pre-filled with a sentinel (a NaN payload the
+// arithmetic can never produce); a consumer re-reads w[dep] (8-byte loads are single-copy atomic)
+// until it is not the sentinel -- the load that observes readiness also delivers the operand, so one
+// hop of the dependency chain costs one store-to-L2 plus one load-from-L2, with no fence and no second
+// round trip.  Rows are handed out in level order through the ticket counter, so every dependency
+// belongs to an earlier slot, i.e. to a block that is already running (or to an earlier level handled
+// by this very warp): no deadlock, no co-residency assumption.  x may alias b (each thread reads its
+// b[row] before any x is written and nobody else touches that element).  Summation order per row is
+// unchanged: bit-identical results.
+//
+// What the hop costs was measured (tools/micro/latency.cu, wavefront.cu, tools/trsv_trace.py): 0.28 us
+// for a clean L2 store -> poll, but 2.3 us in the first version of this kernel.  Three things made the
+// difference, in this order:
+//  * every poll touched 32 scattered sectors per operand (w indexed by row): w is now in slot order,
+//    the warp's results are one 256-byte store and its operands a few sectors of the previous levels;
+//  * lanes left the wait loop one by one and the warp then time-multiplexed a polling path and a
+//    computing path: the wait loop is warp-uniform (leave when all rows of the level are ready);
+//  * a poll round chained its loads (each predicated on the previous load's result): the loads of a
+//    round are predicated on a bit mask and are all in flight together;
+// and rows far ahead of the wavefront wait on their "gates" (bis_matrix.cu) with long sleeps instead of
+// polling every operand.
 constexpr unsigned long long TRSV_SENTINEL = 0xFFF87E5E7E5E7E5EULL;
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
@@ -146,17 +155,9 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) trsv_fill_sentinel_kernel(int64_t n, double *w, unsigned int *warp_flag) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) trsv_fill_sentinel_kernel(int64_t n, double *w) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         reinterpret_cast<unsigned long long *>(w)[i] = TRSV_SENTINEL;
-        if ((i & 31) == 0) warp_flag[i >> 5] = 0u;
-    }
-}
-
-__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
 }
 
 __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_flag_kernel(TrsvArgs a, double *w) {
@@ -166,13 +167,12 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_flag_kernel(TrsvArgs a, d
     const int64_t slot = (int64_t)s_chunk * TRSV_THREADS + threadIdx.x;
     const bool live = slot < a.n_slots;
 
-    int row = 0, lvl = 0x7fffffff, crit = -1;
+    int row = 0, lvl = 0x7fffffff;
     int64_t s = 0, e = 0;
     double bb = 0.0, dd = 1.0;
     if (live) {
         row = a.slot_row[slot];
         lvl = a.slot_level[slot];
-        crit = a.slot_crit[slot];
         s = a.rp[slot];
         e = a.rp[slot + 1];
         bb = a.b[row];
@@ -195,57 +195,73 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_flag_kernel(TrsvArgs a, d
         lv_lo = min(lv_lo, __shfl_xor_sync(0xffffffffu, lv_lo, o));
         lv_hi = max(lv_hi, __shfl_xor_sync(0xffffffffu, lv_hi, o));
     }
-    // operands: everything already published is taken now; only the missing ones are polled, and the
-    // load that finds a value is the load that delivers it (no second round trip)
-    unsigned long long xv[TRSV_PF];
-    bool missing = false;
+    // staged waiting: one gate at a time, oldest first, sleeping in proportion to its distance
+    if (a.gate && live) {
+        const int4 g = a.gate[slot];
 #pragma unroll
-    for (int j = 0; j < TRSV_PF; ++j) {
-        xv[j] = cv[j] >= 0 ? ld_relaxed_u64(w + cv[j]) : 0ull;
-        missing |= (xv[j] == TRSV_SENTINEL);
-    }
-    // While values are missing, ONE lane per warp watches the completion flag of the warp that produces
-    // the last of them (32 lanes polling 32 scattered sectors several times each cost ~0.7 us per poll
-    // in the SM's load pipeline alone).  The flag is only a hint: every value is still checked below.
-    const int64_t warp_id = slot >> 5;
-    if (a.use_warp_flag && __any_sync(0xffffffffu, missing)) {
-        const int wc = a.warp_crit[warp_id < (a.n_slots + 31) / 32 ? warp_id : 0];
-        if ((threadIdx.x & 31) == 0 && wc >= 0) {
+        for (int i = 0; i < 3; ++i) {
+            const int gc = i == 0 ? g.x : (i == 1 ? g.y : g.z);
+            if (gc < 0) continue;
+            const unsigned int ns = a.gate_sleep[(g.w >> (8 * i)) & 15];
             unsigned int spins = 0;
-            while (ld_relaxed_u32(a.warp_flag + wc) == 0u) {
-                __nanosleep(a.poll_ns);
-                if ((++spins & 0xffffu) == 0 && *reinterpret_cast<volatile int *>(a.errflag)) break;
-            }
-        }
-        __syncwarp();
-    }
-    for (int lv = lv_lo; lv <= lv_hi; ++lv) {
-        if (live && lvl == lv) {
-            long long t0 = 0;
-            unsigned int spins = 0;
-            bool ok = true;
-            unsigned long long ts0 = 0, ts1 = 0, ts2 = 0;
-            if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0));
-            for (;;) {
-                bool ready = true;
-#pragma unroll
-                for (int j = 0; j < TRSV_PF; ++j)
-                    if (xv[j] == TRSV_SENTINEL) {
-                        xv[j] = ld_relaxed_u64(w + cv[j]);
-                        ready &= (xv[j] != TRSV_SENTINEL);
-                    }
-                if (ready) break;
-                __nanosleep(a.poll_ns);
-                if ((++spins & 4095u) == 0) {
-                    if (t0 == 0) t0 = clock64();
-                    if (*reinterpret_cast<volatile int *>(a.errflag) || clock64() - t0 > 6000000000LL) {
-                        atomicExch(a.errflag, 1);
-                        ok = false;
+            unsigned long long t_gate = 0;
+            while (ld_relaxed_u64(w + gc) == TRSV_SENTINEL) {
+                if (ns) __nanosleep(ns);
+                if ((++spins & 1023u) == 0) {
+                    if (t_gate == 0) t_gate = bis_globaltimer();
+                    if (*reinterpret_cast<volatile int *>(a.errflag)) break;
+                    if (bis_globaltimer() - t_gate > 3000000000ull) {
+                        atomicExch(a.errflag, 2);
                         break;
                     }
                 }
             }
-            if (a.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1));
+        }
+    }
+    __syncwarp();
+    // operands: everything already published is taken now; only the missing ones are polled, and the
+    // load that finds a value is the load that delivers it (no second round trip)
+    unsigned long long xv[TRSV_PF];
+#pragma unroll
+    for (int j = 0; j < TRSV_PF; ++j) xv[j] = cv[j] >= 0 ? ld_relaxed_u64(w + cv[j]) : 0ull;
+    // bit j: operand j has not been seen yet.  The mask, not the loaded values, decides which loads a
+    // poll round issues, so that all of them are in flight together.
+    unsigned int miss = 0u;
+#pragma unroll
+    for (int j = 0; j < TRSV_PF; ++j) miss |= (xv[j] == TRSV_SENTINEL ? 1u : 0u) << j;
+
+    for (int lv = lv_lo; lv <= lv_hi; ++lv) {
+        const bool mine = live && lvl == lv;
+        unsigned long long ts0 = 0, ts1 = 0, ts2 = 0, ts_first = 0, t_wd = 0;
+        unsigned int spins = 0;
+        bool ok = true;
+        if (a.dbg) ts0 = bis_globaltimer();
+        // warp-uniform wait: the warp moves on when every row of this level has its operands
+        for (;;) {
+            if (mine && miss) {
+#pragma unroll
+                for (int j = 0; j < TRSV_PF; ++j)
+                    if (miss & (1u << j)) xv[j] = ld_relaxed_u64(w + cv[j]);
+#pragma unroll
+                for (int j = 0; j < TRSV_PF; ++j)
+                    if (xv[j] != TRSV_SENTINEL) miss &= ~(1u << j);
+            }
+            if (__all_sync(0xffffffffu, !mine || miss == 0u)) break;
+            if (a.dbg && spins == 0) ts_first = bis_globaltimer();
+            if (a.poll_ns) __nanosleep(a.poll_ns);
+            bool give_up = false;
+            if ((++spins & 4095u) == 0) {
+                if (t_wd == 0) t_wd = bis_globaltimer();
+                give_up = *reinterpret_cast<volatile int *>(a.errflag) != 0 || bis_globaltimer() - t_wd > 3000000000ull;
+            }
+            if (__any_sync(0xffffffffu, give_up)) {
+                atomicExch(a.errflag, 1);
+                ok = false;
+                break;
+            }
+        }
+        if (mine) {
+            if (a.dbg) ts1 = bis_globaltimer();
             double sum = 0.0;
 #pragma unroll
             for (int j = 0; j < TRSV_PF; ++j)
@@ -261,33 +277,33 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_flag_kernel(TrsvArgs a, d
             const double r = div_rn(sub_rn(bb, sum), dd);
             // publish: the value doubles as the flag.  A result that IS the sentinel pattern cannot occur
             // (hardware NaNs are canonical), so readers can never mistake a result for "not ready".
-            __stcg(w + row, r);
+            __stcg(w + slot, r);
             a.x[row] = r;
             if (a.dbg) {
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2));
-                a.dbg[3 * (int64_t)row] = ts0;       // critical dependency observed
-                a.dbg[3 * (int64_t)row + 1] = ts1;   // all operands in registers
-                a.dbg[3 * (int64_t)row + 2] = ts2;   // result published
+                ts2 = bis_globaltimer();
+                a.dbg[4 * (int64_t)row] = ts0;       // the row's level came up in its warp
+                a.dbg[4 * (int64_t)row + 1] = ts1;   // all operands in registers
+                a.dbg[4 * (int64_t)row + 2] = ts2;   // result published
+                // poll rounds that found something missing, and how long the first one took
+                a.dbg[4 * (int64_t)row + 3] = (unsigned long long)spins | ((ts_first ? ts_first - ts0 : 0ull) << 32);
             }
         }
         __syncwarp();
-    }
-    // all rows of this warp are published (hint for the warps that wait on it)
-    if ((threadIdx.x & 31) == 0 && warp_id < (a.n_slots + 31) / 32) {
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.warp_flag + warp_id), "r"(1u) : "memory");
     }
 }
 
 // Safety-net variant: one launch per level (opt "trsv_variant" = 1).
 __global__ void __launch_bounds__(TRSV_THREADS)
-sptrsv_one_level_kernel(TrsvArgs a, int64_t slot_begin, int64_t slot_end) {
+sptrsv_one_level_kernel(TrsvArgs a, double *w, int64_t slot_begin, int64_t slot_end) {
     const int64_t slot = slot_begin + (int64_t)blockIdx.x * TRSV_THREADS + threadIdx.x;
     if (slot >= slot_end) return;
     const int row = a.slot_row[slot];
     const int64_t s = a.rp[slot], e = a.rp[slot + 1];
     double sum = 0.0;
-    for (int64_t k = s; k < e; ++k) sum = add_rn(sum, mul_rn(a.val[k], __ldcg(a.x + a.col[k])));
-    a.x[row] = div_rn(sub_rn(a.b[row], sum), a.D[row]);
+    for (int64_t k = s; k < e; ++k) sum = add_rn(sum, mul_rn(a.val[k], __ldcg(w + a.col[k])));
+    const double r = div_rn(sub_rn(a.b[row], sum), a.D[row]);
+    w[slot] = r;
+    a.x[row] = r;
 }
 
 } // namespace
@@ -306,10 +322,11 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.n_slots = lv.n_slots;
     a.slot_row = lv.d_slot_row;
     a.slot_level = lv.d_slot_level;
-    a.slot_crit = lv.d_slot_crit;
-    a.warp_crit = lv.d_warp_crit;
-    a.warp_flag = lv.d_warp_flag;
-    a.use_warp_flag = c->opt_trsv_warp_flag;
+    a.gate = c->opt_trsv_gates ? reinterpret_cast<const int4 *>(lv.d_slot_gate) : nullptr;
+    for (int d = 0; d < 16; ++d) {
+        const int *sl = c->opt_trsv_sleep;
+        a.gate_sleep[d] = (unsigned int)(d <= 1 ? sl[0] : d == 2 ? sl[1] : d == 3 ? sl[2] : d < 6 ? sl[3] : 2 * sl[3]);
+    }
     a.rp = lv.d_rp;
     a.col = lv.d_col;
     a.val = lv.d_val;
@@ -318,9 +335,9 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.ticket = lv.d_ticket;
     a.errflag = c->d_errflag;
     a.dbg = nullptr;
-    a.poll_ns = c->opt_trsv_poll_ns > 0 ? (unsigned int)c->opt_trsv_poll_ns : 20u;
+    a.poll_ns = c->opt_trsv_poll_ns > 0 ? (unsigned int)c->opt_trsv_poll_ns : (c->opt_trsv_poll_ns < 0 ? 0u : 20u);   // < 0: spin without sleeping
     const char *dbg_file = c->opt_trsv_debug ? getenv("BIS_TRSV_DEBUG_FILE") : nullptr;
-    if (dbg_file) BIS_CUDA(cudaMalloc(&a.dbg, sizeof(unsigned long long) * 3 * (size_t)lv.n_slots));
+    if (dbg_file) BIS_CUDA(cudaMalloc(&a.dbg, sizeof(unsigned long long) * 4 * (size_t)lv.n_slots));
     a.x = x;
     a.D = D;
     a.b = b;
@@ -330,7 +347,7 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
         for (int l = 0; l < lv.n_levels; ++l) {
             int64_t cnt = ls[l + 1] - ls[l];
             int blocks = (int)((cnt + TRSV_THREADS - 1) / TRSV_THREADS);
-            sptrsv_one_level_kernel<<<blocks, TRSV_THREADS, 0, c->stream>>>(a, ls[l], ls[l + 1]);
+            sptrsv_one_level_kernel<<<blocks, TRSV_THREADS, 0, c->stream>>>(a, lv.d_w, ls[l], ls[l + 1]);
             BIS_LAUNCH_CHECK(c);
         }
         return bis_prof_end(c, BIS_PROF_SPTRSV);
@@ -338,12 +355,12 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     const int64_t blocks = (lv.n_slots + TRSV_THREADS - 1) / TRSV_THREADS;
     BIS_CUDA(cudaMemsetAsync(lv.d_ticket, 0, sizeof(unsigned int), c->stream));
     if (c->opt_trsv_variant != 2) {
-        trsv_fill_sentinel_kernel<<<bis_blocks_for(lv.n_slots, 1024, c->sm_count * 8), 256, 0, c->stream>>>(lv.n_slots, lv.d_w, lv.d_warp_flag);
+        trsv_fill_sentinel_kernel<<<bis_blocks_for(lv.n_slots, 1024, c->sm_count * 8), 256, 0, c->stream>>>(lv.n_slots, lv.d_w);
         BIS_LAUNCH_CHECK(c);
         sptrsv_flag_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a, lv.d_w);
         BIS_LAUNCH_CHECK(c);
         if (a.dbg) {   // debug aid (tools/trsv_trace.py): per-row timestamps of the last solve
-            std::vector<unsigned long long> h(3 * (size_t)lv.n_slots);
+            std::vector<unsigned long long> h(4 * (size_t)lv.n_slots);
             BIS_CUDA(cudaMemcpyAsync(h.data(), a.dbg, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
             BIS_CUDA(cudaStreamSynchronize(c->stream));
             if (FILE *f = fopen(dbg_file, "wb")) {
@@ -356,7 +373,7 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     }
     // variant 2: per-level completion counters (kept for comparison)
     BIS_CUDA(cudaMemsetAsync(lv.d_level_done, 0, sizeof(unsigned int) * (size_t)lv.n_levels, c->stream));
-    sptrsv_level_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a);
+    sptrsv_level_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a, lv.d_w);
     BIS_LAUNCH_CHECK(c);
     return bis_prof_end(c, BIS_PROF_SPTRSV);
 }

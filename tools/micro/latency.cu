@@ -65,6 +65,31 @@ __global__ void ring(unsigned long long *w, int laps, long long *cycles) {
     if (me == 0) cycles[0] = t1 - t0;
 }
 
+// how long does __nanosleep(t) really take?
+__global__ void sleep_cost(unsigned int ns, int n, long long *cycles) {
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) __nanosleep(ns);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+// ping-pong with a sleep between two polls (the shape of the triangular solve's wait loop)
+__global__ void pingpong_sleep(unsigned long long *w, int n, unsigned int ns, long long *cycles) {
+    if (threadIdx.x != 0) return;
+    const int me = blockIdx.x;
+    long long t0 = clock64();
+    for (int i = 1; i <= n; ++i) {
+        if (me == 0) {
+            __stcg(&w[0], (unsigned long long)i);
+            while (ld_relaxed(&w[16]) != (unsigned long long)i) __nanosleep(ns);
+        } else {
+            while (ld_relaxed(&w[0]) != (unsigned long long)i) __nanosleep(ns);
+            __stcg(&w[16], (unsigned long long)i);
+        }
+    }
+    long long t1 = clock64();
+    if (me == 0) cycles[0] = t1 - t0;
+}
+
 int main() {
     double *d;
     long long *c, h;
@@ -90,6 +115,17 @@ int main() {
         pingpong<<<2, 32>>>(w, 2000, c);
         cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
         if (rep) printf("2-SM ping-pong : %.0f cycles per one-way hop (%.2f us at %d MHz)\n", (double)h / 4000, (double)h / 4000 / (clk / 1e3), clk / 1000);
+        for (unsigned int ns : {0u, 1u, 20u, 100u, 400u, 1000u, 4000u}) {
+            sleep_cost<<<1, 32>>>(ns, 1000, c);
+            cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
+            if (rep) printf("__nanosleep(%4u): %.0f cycles (%.0f ns) per call\n", ns, (double)h / 1000, (double)h / 1000 / (clk / 1e6));
+        }
+        for (unsigned int ns : {1u, 20u, 100u, 400u}) {
+            cudaMemset(w, 0, 148 * 16 * 8);
+            pingpong_sleep<<<2, 32>>>(w, 2000, ns, c);
+            cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
+            if (rep) printf("ping-pong, __nanosleep(%u) between polls: %.0f cycles per one-way hop\n", ns, (double)h / 4000);
+        }
         for (int nb : {8, 64, 148}) {
             cudaMemset(w, 0, 148 * 16 * 8);
             ring<<<nb, 32>>>(w, 50, c);

@@ -18,13 +18,24 @@ with capi.Context(0) as ctx:
     D, b, x = ctx.upload(f.A_D), ctx.upload(np.ones(N)), ctx.alloc(N)
     ctx.call("bis_sptrsv", L.h, x, D, b)
     ctx.sync()
+    for kv in sys.argv[2:]:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     ctx.set_option("trsv_debug", 1)
     ctx.call("bis_sptrsv", L.h, x, D, b)
     ctx.sync()
-ts = np.fromfile(path, dtype=np.uint64).reshape(N, 3).astype(np.int64)
+raw = np.fromfile(path, dtype=np.uint64).reshape(N, 4)
+ts = raw[:, :3].astype(np.int64)
+spins = (raw[:, 3] & np.uint64(0xffffffff)).astype(np.int64)
+first_round = (raw[:, 3] >> np.uint64(32)).astype(np.int64)
 t0 = ts[:, 2].min()
 ts -= t0
-np.save(path + ".npy", ts[:, 2].astype(np.int32))      # publication time per row (ns), for offline DAG analysis
+np.save(path + ".npy", ts[:, 2].astype(np.int32))
+np.save(path + ".all.npy", np.concatenate([ts, spins[:, None], first_round[:, None]], axis=1).astype(np.int32))
+print("poll rounds that found an operand missing: median %d mean %.1f p90 %d ; first round took (ns) median %d p90 %d" %
+      (np.median(spins), spins.mean(), np.percentile(spins, 90), np.median(first_round[spins > 0]), np.percentile(first_round[spins > 0], 90)))
+w = ts[:, 1] - ts[:, 0]
+print("time in the final wait loop (ns): median %d ; per round: median %.0f" % (np.median(w), np.median(w[spins > 0] / (spins[spins > 0] + 1))))
 os.remove(path)
 idx = np.arange(N)
 lvl = idx % n + 2 * ((idx // n) % n) + 4 * (idx // (n * n))      # level(x,y,z) = x + 2y + 4z
