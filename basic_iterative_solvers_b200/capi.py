@@ -61,6 +61,7 @@ _SIGS = {
     "bis_matrix_download_crs": ([c_ctx, c_mat, C.c_void_p, C.c_void_p, C.c_void_p], cint),
     "bis_matrix_extract_diagonal": ([c_ctx, c_mat, c_dev, c_dev], cint),
     "bis_matrix_split_triangular": ([c_ctx, c_mat, C.POINTER(c_mat), C.POINTER(c_mat)], cint),
+    "bis_matrix_ilu0": ([c_ctx, c_mat, C.c_double, C.c_double, C.POINTER(c_mat), C.POINTER(c_mat), c_dev, c_dev], cint),
     "bis_spmv": ([c_ctx, c_mat, c_dev, c_dev], cint),
     "bis_sptrsv": ([c_ctx, c_mat, c_dev, c_dev, c_dev], cint),
     "bis_bsptrsv": ([c_ctx, c_mat, c_dev, c_dev, c_dev], cint),
@@ -299,6 +300,13 @@ class Context:
         return Matrix(self, l), Matrix(self, u)
 
     # scalars -----------------------------------------------------------------
+    def ilu0(self, A: Matrix, n: int, pivot_tolerance: float = 1e-8, pivot_replacement: float = 1e-4):
+        """Device ILU(0): returns (L_strict, U_strict, L_D, U_D) with L_D/U_D device vectors."""
+        l, u = c_mat(), c_mat()
+        ld, ud = self.alloc(n), self.alloc(n)
+        self.call("bis_matrix_ilu0", A.h, pivot_tolerance, pivot_replacement, C.byref(l), C.byref(u), ld, ud)
+        return Matrix(self, l), Matrix(self, u), ld, ud
+
     def scalars(self, first: int, count: int = 1) -> np.ndarray:
         arr = (dbl * count)()
         self.call("bis_scalar_get", first, count, arr)

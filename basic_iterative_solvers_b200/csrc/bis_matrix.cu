@@ -141,145 +141,12 @@ extern "C" int bis_matrix_upload_triangular(bis_context *c, int64_t n, int64_t n
     bis_matrix *T = nullptr;
     BIS_CHECK(upload_common<int32_t>(c, n, n, nnz, rp, col, val, &T));
     T->triangular = upper ? 2 : 1;
-    // level(r) = 1 + max level over the rows it reads (host, one pass in
-    // dependency order; the device-side analysis is SURVEY.md 8(f) "next")
-    std::vector<int> level((size_t)n, 0);
-    int n_levels = n > 0 ? 1 : 0;
-    auto fail = [&](const char *msg, int64_t r) {
-        bis_set_error("bis_matrix_upload_triangular: %s at row %lld", msg, (long long)r);
+    // validation (strictly triangular), level analysis, level-ordered copy and gates: all on the device
+    if (bis_build_levels_device(c, T) != 0) {
         free_matrix_storage(T);
         delete T;
         return 2;
-    };
-    if (!upper) {
-        for (int64_t r = 0; r < n; ++r) {
-            int lv = 0;
-            for (int32_t k = rp[r]; k < rp[r + 1]; ++k) {
-                int32_t cc = col[k];
-                if (cc < 0 || cc >= r) return fail("entry not strictly below the diagonal", r);
-                lv = std::max(lv, level[cc] + 1);
-            }
-            level[r] = lv;
-            n_levels = std::max(n_levels, lv + 1);
-        }
-    } else {
-        for (int64_t r = n - 1; r >= 0; --r) {
-            int lv = 0;
-            for (int32_t k = rp[r]; k < rp[r + 1]; ++k) {
-                int32_t cc = col[k];
-                if (cc <= r || cc >= n) return fail("entry not strictly above the diagonal", r);
-                lv = std::max(lv, level[cc] + 1);
-            }
-            level[r] = lv;
-            n_levels = std::max(n_levels, lv + 1);
-        }
     }
-    // counting sort by level, ascending row inside a level
-    std::vector<int64_t> start((size_t)n_levels + 1, 0);
-    for (int64_t r = 0; r < n; ++r) start[level[r] + 1]++;
-    std::vector<int> level_size((size_t)std::max(n_levels, 1), 0);
-    for (int l = 0; l < n_levels; ++l) {
-        level_size[l] = (int)start[l + 1];
-        start[l + 1] += start[l];
-    }
-    std::vector<int> slot_row((size_t)n), slot_level((size_t)n);
-    {
-        std::vector<int64_t> cur(start.begin(), start.end() - 1);
-        for (int64_t r = 0; r < n; ++r) {
-            int64_t s = cur[level[r]]++;
-            slot_row[s] = (int)r;
-            slot_level[s] = level[r];
-        }
-    }
-    // per row: up to three "gates" -- dependencies whose level lies further and further back
-    // (the oldest one; the newest one at least 3 levels back; the newest one 2 levels back).  A row that
-    // waits looks at ONE gate at a time and sleeps in proportion to the gate's distance, so rows far ahead
-    // of the wavefront cost one load every few microseconds instead of a load per operand per poll
-    // (the SM's load pipe, not the L2 round trip, bounded the level-to-level latency before).
-    // gate[4*sl + i] = SLOT of gate i (-1: none), gate[4*sl + 3] = the three distances, one byte each.
-    std::vector<int> slot_gate((size_t)n * 4, -1);
-    {
-        std::vector<int64_t> slot_of((size_t)n);
-        for (int64_t sl = 0; sl < n; ++sl) slot_of[slot_row[sl]] = sl;
-        for (int64_t sl = 0; sl < n; ++sl) {
-            const int r = slot_row[sl];
-            const int lvr = level[r];
-            int64_t best[3] = {-1, -1, -1};   // chosen by (level, slot) == slot order
-            int gcol[3] = {-1, -1, -1}, glev[3] = {0, 0, 0};
-            int64_t oldest = INT64_MAX;
-            for (int32_t k = rp[r]; k < rp[r + 1]; ++k) {
-                const int cc = col[k];
-                const int d = lvr - level[cc];
-                const int64_t so = slot_of[cc];
-                // rows of one warp (32 consecutive slots) run their levels in lockstep: a gate inside the
-                // own warp could never open
-                if (so / 32 == sl / 32) continue;
-                if (d >= 4 && so < oldest) { oldest = so; gcol[0] = (int)so; glev[0] = level[cc]; }
-                if (d >= 3 && so > best[1]) { best[1] = so; gcol[1] = (int)so; glev[1] = level[cc]; }
-                if (d == 2 && so > best[2]) { best[2] = so; gcol[2] = (int)so; glev[2] = level[cc]; }
-            }
-            if (gcol[0] == gcol[1]) gcol[0] = -1;
-            int packed = 0;
-            for (int i = 0; i < 3; ++i) {
-                slot_gate[4 * (size_t)sl + i] = gcol[i];
-                const int d = gcol[i] >= 0 ? std::min(lvr - glev[i], 15) : 0;
-                packed |= d << (8 * i);
-            }
-            slot_gate[4 * (size_t)sl + 3] = packed;
-        }
-    }
-    std::vector<int64_t> rp2((size_t)n + 1, 0);
-    std::vector<int32_t> col2((size_t)nnz);
-    std::vector<double> val2((size_t)nnz);
-    // The level-ordered copy names its operands by SLOT, not by row: the solve keeps its working vector
-    // in slot order, so the 32 results of a warp are one contiguous 256-byte store and the operands of
-    // 32 consecutive slots (neighbouring rows of one level) fall into a few sectors of the previous
-    // levels instead of 32 scattered ones (tools/micro/wavefront.cu: the scattered sectors of a poll,
-    // not the L2 round trip, set the cost of a level-to-level hop).  Storage order inside a row is kept.
-    {
-        std::vector<int64_t> slot_of((size_t)n);
-        for (int64_t sl = 0; sl < n; ++sl) slot_of[slot_row[sl]] = sl;
-        for (int64_t s = 0; s < n; ++s) {
-            int r = slot_row[s];
-            int32_t len = rp[r + 1] - rp[r];
-            rp2[s + 1] = rp2[s] + len;
-            for (int32_t k = 0; k < len; ++k) {
-                col2[rp2[s] + k] = (int32_t)slot_of[col[rp[r] + k]];
-                val2[rp2[s] + k] = val[rp[r] + k];
-            }
-        }
-    }
-    LevelSets &lv = T->lv;
-    lv.n_levels = n_levels;
-    lv.n_slots = n;
-    lv.level_start = start;
-    int rc = 0;
-    rc |= dev_alloc(&lv.d_slot_row, (size_t)n);
-    rc |= dev_alloc(&lv.d_slot_level, (size_t)n);
-    rc |= dev_alloc(&lv.d_slot_gate, (size_t)n * 4 + 4);
-    rc |= dev_alloc(&lv.d_level_size, (size_t)n_levels);
-    rc |= dev_alloc(&lv.d_level_done, (size_t)n_levels);
-    rc |= dev_alloc(&lv.d_ticket, 1);
-    rc |= dev_alloc(&lv.d_w, (size_t)n);
-    rc |= dev_alloc(&lv.d_rp, (size_t)n + 1);
-    rc |= dev_alloc(&lv.d_col, (size_t)nnz);
-    rc |= dev_alloc(&lv.d_val, (size_t)nnz);
-    if (rc) {
-        free_matrix_storage(T);
-        delete T;
-        return 1;
-    }
-    auto h2d = [&](void *d, const void *h, size_t bytes) {
-        return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
-    };
-    BIS_CUDA(h2d(lv.d_slot_row, slot_row.data(), sizeof(int) * (size_t)n));
-    BIS_CUDA(h2d(lv.d_slot_level, slot_level.data(), sizeof(int) * (size_t)n));
-    BIS_CUDA(h2d(lv.d_slot_gate, slot_gate.data(), sizeof(int) * (size_t)n * 4));
-    BIS_CUDA(h2d(lv.d_level_size, level_size.data(), sizeof(int) * (size_t)n_levels));
-    BIS_CUDA(h2d(lv.d_rp, rp2.data(), sizeof(int64_t) * ((size_t)n + 1)));
-    BIS_CUDA(h2d(lv.d_col, col2.data(), sizeof(int32_t) * (size_t)nnz));
-    BIS_CUDA(h2d(lv.d_val, val2.data(), sizeof(double) * (size_t)nnz));
-    BIS_CUDA(cudaStreamSynchronize(c->stream));
     *out = T;
     return 0;
 }
@@ -611,6 +478,8 @@ __global__ void extract_diag_kernel(int64_t n, const RP *rp, const int *col, con
             if (col[k] == r) {   // local column id == local row id on the diagonal
                 double d = val[k];
                 D[r] = d;
+                if (fabs(d) < 1e-16)   // SanityChecker::zero_diag (LU_factors.hpp:842-845)
+                    atomicExch(missing + 1, (int)(r + 1 > 0x7fffffff ? 0x7fffffff : r + 1));
                 if (D_inv) D_inv[r] = div_rn(1.0, d);
                 found = true;   // peel_diag_crs_new keeps the LAST match (LU_factors.hpp:836-850)
             }
@@ -624,59 +493,20 @@ extern "C" int bis_matrix_extract_diagonal(bis_context *c, const bis_matrix *A, 
     BIS_REQUIRE(c && A && D, "null argument");
     BIS_CUDA(cudaSetDevice(c->device));
     int *d_missing = nullptr;
-    BIS_CHECK(dev_alloc(&d_missing, 1));
-    BIS_CUDA(cudaMemsetAsync(d_missing, 0, sizeof(int), c->stream));
+    BIS_CHECK(dev_alloc(&d_missing, 2));
+    BIS_CUDA(cudaMemsetAsync(d_missing, 0, 2 * sizeof(int), c->stream));
     const int blocks = bis_blocks_for(A->n_rows, 256, c->sm_count * 8);
     if (A->rp_bytes == 8)
         extract_diag_kernel<int64_t><<<blocks, 256, 0, c->stream>>>(A->n_rows, static_cast<const int64_t *>(A->d_rp), A->d_col, A->d_val, D, D_inv, d_missing);
     else
         extract_diag_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(A->n_rows, static_cast<const int32_t *>(A->d_rp), A->d_col, A->d_val, D, D_inv, d_missing);
     BIS_LAUNCH_CHECK(c);
-    int missing = 0;
-    BIS_CUDA(cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int missing[2] = {0, 0};
+    BIS_CUDA(cudaMemcpyAsync(missing, d_missing, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     BIS_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_missing);
-    // SanityChecker::no_diag (common.hpp:393-396) is fatal in the reference
-    BIS_REQUIRE(missing == 0, "No diagonal to extract at row index %d", missing - 1);
-    return 0;
-}
-
-// split_LU_new (LU_factors.hpp:122-309), strict parts.  Host round trip for
-// now (device-side split + level analysis is SURVEY.md 8(f) "next").
-extern "C" int bis_matrix_split_triangular(bis_context *c, const bis_matrix *A, bis_matrix **L,
-                                           bis_matrix **U) {
-    BIS_REQUIRE(c && A && L && U, "null argument");
-    BIS_REQUIRE(!A->distributed && c->nranks == 1, "bis_matrix_split_triangular: single-GPU only");
-    BIS_REQUIRE(A->nnz < INT32_MAX, "bis_matrix_split_triangular: nnz exceeds 32-bit row_ptr");
-    const int64_t n = A->n_rows;
-    std::vector<int64_t> rp((size_t)n + 1);
-    std::vector<int32_t> col((size_t)A->nnz);
-    std::vector<double> val((size_t)A->nnz);
-    BIS_CHECK(bis_matrix_download_crs(c, A, rp.data(), col.data(), val.data()));
-    std::vector<int32_t> lrp((size_t)n + 1, 0), urp((size_t)n + 1, 0);
-    for (int64_t r = 0; r < n; ++r) {
-        int32_t nl = 0, nu = 0;
-        for (int64_t k = rp[r]; k < rp[r + 1]; ++k) {
-            if (col[k] < r) ++nl;
-            else if (col[k] > r) ++nu;
-        }
-        lrp[r + 1] = lrp[r] + nl;
-        urp[r + 1] = urp[r] + nu;
-    }
-    std::vector<int32_t> lcol((size_t)lrp[n]), ucol((size_t)urp[n]);
-    std::vector<double> lval((size_t)lrp[n]), uval((size_t)urp[n]);
-    for (int64_t r = 0; r < n; ++r) {
-        int32_t pl = lrp[r], pu = urp[r];
-        for (int64_t k = rp[r]; k < rp[r + 1]; ++k) {
-            if (col[k] < r) { lcol[pl] = col[k]; lval[pl++] = val[k]; }
-            else if (col[k] > r) { ucol[pu] = col[k]; uval[pu++] = val[k]; }
-        }
-    }
-    BIS_CHECK(bis_matrix_upload_triangular(c, n, lrp[n], lrp.data(), lcol.data(), lval.data(), 0, L));
-    if (bis_matrix_upload_triangular(c, n, urp[n], urp.data(), ucol.data(), uval.data(), 1, U) != 0) {
-        bis_matrix_free(c, *L);
-        *L = nullptr;
-        return 1;
-    }
+    // SanityChecker::no_diag / zero_diag (common.hpp:388-396) are fatal in the reference
+    BIS_REQUIRE(missing[0] == 0, "No diagonal to extract at row index %d", missing[0] - 1);
+    BIS_REQUIRE(missing[1] == 0, "Zero detected on diagonal at row index %d", missing[1] - 1);
     return 0;
 }

@@ -1,6 +1,7 @@
 // host/host_capi.cpp -- C entry points of the HOST library (libbis_host.so):
 // the reference-shaped Solver/harness stack driven from plain C (ctypes in the
 // tests and bench.py).  Device work goes through the C-ABI of libbis_b200.so.
+#include "lu_factors.hpp"
 #include "run.hpp"
 
 #include <cstring>
@@ -68,7 +69,7 @@ int bis_host_matrix_begin(const char *name, int *n, int *nnz) {
         Args a;
         a.matrix_file_name = name;
         std::unique_ptr<DeviceCRS> none;
-        obtain_matrix(&a, nullptr, true, g_mat, none);
+        obtain_matrix(&a, nullptr, g_mat, none, /*on_host=*/true);
         *n = g_mat->n_rows;
         *nnz = g_mat->nnz;
         return 0;
@@ -131,7 +132,7 @@ int bis_host_solve(bis_context *dev, const char *matrix_name, int n, const int *
             std::memcpy(A->col, col, sizeof(int) * rp[n]);
             std::memcpy(A->val, val, sizeof(double) * rp[n]);
         } else {
-            obtain_matrix(&args, dev, solver->needs_triangular_factors(), A, dA);
+            obtain_matrix(&args, dev, A, dA);
         }
         int64_t info0[8];
         BIS_OK(bis_context_info(dev, info0));
@@ -231,7 +232,7 @@ int bis_host_bench_e2e(void *h, int steps, const double *b_host, const double *x
         solver->tolerance = 0.0;   // never stop early: exactly `steps` iterations
         std::unique_ptr<MatrixCRS> A;
         std::unique_ptr<DeviceCRS> dA;
-        obtain_matrix(&s->args, s->dev, solver->needs_triangular_factors(), A, dA);
+        obtain_matrix(&s->args, s->dev, A, dA);
         BIS_OK(bis_context_synchronize(s->dev));
         int64_t i0[8], i1[8];
         BIS_OK(bis_context_info(s->dev, i0));
@@ -267,7 +268,7 @@ int bis_host_bench_prepare(void *h, int warmup, int64_t *info) {
         solver->tolerance = 0.0;
         std::unique_ptr<MatrixCRS> A;
         std::unique_ptr<DeviceCRS> dA;
-        obtain_matrix(&s->args, s->dev, solver->needs_triangular_factors(), A, dA);
+        obtain_matrix(&s->args, s->dev, A, dA);
         preprocessing(&s->args, solver, &s->timers, A, std::move(dA));
         for (int i = 0; i < warmup; ++i) {
             s->timers.per_iteration_time.start();

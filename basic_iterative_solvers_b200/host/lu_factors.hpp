@@ -1,12 +1,13 @@
-// host/lu_factors.hpp -- host preprocessing that feeds the device triangular
-// solves: strict L/U split + diagonal (split_LU_new / peel_diag_crs_new,
+// host/lu_factors.hpp -- HOST restatement of the factor step: strict L/U split + diagonal (split_LU_new / peel_diag_crs_new,
 // reference utilities/LU_factors.hpp:122-309, 827-869) and ILU(0)
 // (factor_ILU0_old, LU_factors.hpp:320-539 -- the working pure-C++ routine;
 // the stock dispatcher picks an SMAX-only stub).
 //
 // Only what the native kernels consume is produced:
-// L_strict, U_strict, A_D, A_D_inv, L_D, U_D.  Results are uploaded once and
-// stay on the device (preprocessing.hpp).
+// L_strict, U_strict, A_D, A_D_inv, L_D, U_D.  The solver stack no longer calls this: preprocessing()
+// splits / factors on the device (csrc/bis_factor.cu).  It stays as the CPU-testable statement of the
+// rules (bis_host_factor; pinned bit for bit to the compiled reference's factors by
+// tests/test_host_cpu.py) that the device factorisation is checked against on the GPU.
 #pragma once
 
 #include "common.hpp"

@@ -1,7 +1,8 @@
 // host/preprocessing.hpp -- preprocessing() of the reference
 // (preprocessing.hpp:26-100): allocate/init the solver vectors, hand A over,
-// factor on the host, then -- new in the build -- upload A, L_strict, U_strict
-// and the diagonals ONCE; they stay device-resident for the whole solve.
+// upload A ONCE (or adopt a device-generated A), then -- new in the build -- split / ILU(0)-factor
+// and level-analyse it ON THE DEVICE (csrc/bis_factor.cu); everything stays device-resident for the
+// whole solve.
 //
 // Deviations, both stated in DESIGN.md: (1) the triangular copies are only
 // built when the method or preconditioner uses them (the reference always
@@ -11,7 +12,6 @@
 #pragma once
 
 #include "common.hpp"
-#include "lu_factors.hpp"
 #include "solver.hpp"
 
 // A: host CRS (consumed), or nullptr when dA was generated on the device.
@@ -44,24 +44,19 @@ inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
     solver->A = std::move(A);
 
     timers->preprocessing_factor_time.start();
+    // peel_diag_crs on the device: A_D and 1/A_D (LU_factors.hpp:827-869); fatal on a missing or zero diagonal
+    BIS_OK(bis_matrix_extract_diagonal(dev, solver->dA->handle, solver->A_D, solver->A_D_inv));
     if (solver->needs_triangular_factors()) {
-        if (!solver->A) bis_fatal("this method/preconditioner needs L/U factors: the matrix must be host-resident");
-        MatrixCRS L_strict, U_strict;
-        const MatrixCRS *Ah = solver->A.get();
-        std::vector<double> A_D(n, 1.0), A_D_inv(n, 0.0), L_D(n, 1.0), U_D(n, 1.0);
-        factor_LU(Ah, A_D.data(), A_D_inv.data(), &L_strict, L_D.data(), &U_strict, U_D.data(),
-                  solver->preconditioner);
-        timers->preprocessing_upload_time.start();
-        solver->dL_strict = upload_triangular(dev, &L_strict, false);
-        solver->dU_strict = upload_triangular(dev, &U_strict, true);
-        BIS_OK(bis_vector_upload(dev, solver->A_D, A_D.data(), n));
-        BIS_OK(bis_vector_upload(dev, solver->A_D_inv, A_D_inv.data(), n));
-        BIS_OK(bis_vector_upload(dev, solver->L_D, L_D.data(), n));
-        BIS_OK(bis_vector_upload(dev, solver->U_D, U_D.data(), n));
-        timers->preprocessing_upload_time.stop();
-    } else {
-        // peel_diag_crs on the device: A_D and 1/A_D (LU_factors.hpp:827-869)
-        BIS_OK(bis_matrix_extract_diagonal(dev, solver->dA->handle, solver->A_D, solver->A_D_inv));
+        // factor_LU (LU_factors.hpp:900-934) on the device-resident matrix: strict split, or ILU(0)
+        // (factor_ILU0_old) when it is the preconditioner; level analysis included.  L_D = U_D = 1 unless ILU(0).
+        bis_matrix *l = nullptr, *u = nullptr;
+        if (solver->preconditioner == PrecondType::ILU0)
+            BIS_OK(bis_matrix_ilu0(dev, solver->dA->handle, ILU0_PIVOT_TOLERANCE, ILU0_PIVOT_REPLACEMENT, &l, &u,
+                                   solver->L_D, solver->U_D));
+        else
+            BIS_OK(bis_matrix_split_triangular(dev, solver->dA->handle, &l, &u));
+        solver->dL_strict = adopt_device_matrix(dev, l);
+        solver->dU_strict = adopt_device_matrix(dev, u);
     }
     solver->A.reset();   // the host copy is not needed during the solve
     timers->preprocessing_factor_time.stop();

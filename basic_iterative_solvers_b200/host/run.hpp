@@ -25,11 +25,13 @@ inline std::unique_ptr<Solver> make_solver(const Args *cli_args, Interface *dev)
     bis_fatal("Error: Unknown or unsupported solver type.");
 }
 
-// Matrix by name: built-in generators or a MatrixMarket file.  Matrices whose
-// factors are needed, or that fit the host container, are built on the host;
-// HPCG sizes beyond 32-bit nnz are generated on the device (Jacobi/none only).
-inline void obtain_matrix(const Args *cli_args, Interface *dev, bool need_host,
-                          std::unique_ptr<MatrixCRS> &A, std::unique_ptr<DeviceCRS> &dA) {
+// Matrix by name: a MatrixMarket file (read and converted on the host, uploaded by preprocessing) or
+// a built-in generator, which runs on the device.  Splitting, ILU(0) and the level analysis happen on
+// the device too (csrc/bis_factor.cu), so no method needs a host copy of a generated matrix.
+// on_host: build a generated matrix in host memory instead (the CPU-only tests and the reference leg
+// of the benchmarks feed the same CRS to the oracle).
+inline void obtain_matrix(const Args *cli_args, Interface *dev, std::unique_ptr<MatrixCRS> &A,
+                          std::unique_ptr<DeviceCRS> &dA, bool on_host = false) {
     const MatrixSpec spec = parse_matrix_spec(cli_args->matrix_file_name);
     if (spec.kind == MatrixSpec::File) {
         MatrixCOO coo;
@@ -38,7 +40,7 @@ inline void obtain_matrix(const Args *cli_args, Interface *dev, bool need_host,
         convert_coo_to_crs(&coo, A.get());
         return;
     }
-    if (need_host) {
+    if (on_host) {
         A = spec.kind == MatrixSpec::Hpcg ? generate_hpcg(spec.nx, spec.ny, spec.nz)
                                           : generate_anderson(spec.nx, spec.ny, spec.nz, spec.ranpot, spec.t,
                                                               spec.seed, spec.periodic);
@@ -58,7 +60,7 @@ inline void run(Args *cli_args, Timers *timers, Interface *dev) {
     std::unique_ptr<Solver> solver = make_solver(cli_args, dev);
     std::unique_ptr<MatrixCRS> A;
     std::unique_ptr<DeviceCRS> dA;
-    obtain_matrix(cli_args, dev, solver->needs_triangular_factors(), A, dA);
+    obtain_matrix(cli_args, dev, A, dA);
     TIME(timers->preprocessing, preprocessing(cli_args, solver.get(), timers, A, std::move(dA)))
     TIME(timers->solve, solve(cli_args, solver.get(), timers))
     TIME(timers->postprocessing, postprocessing(cli_args, solver.get(), timers))

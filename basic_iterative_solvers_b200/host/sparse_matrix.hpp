@@ -79,6 +79,15 @@ inline std::unique_ptr<DeviceCRS> upload_triangular(bis_context *dev, const Matr
     return d;
 }
 
+// takes ownership of a matrix the device library created (split / ILU(0) on the device)
+inline std::unique_ptr<DeviceCRS> adopt_device_matrix(bis_context *dev, bis_matrix *handle) {
+    auto d = std::make_unique<DeviceCRS>();
+    d->dev = dev;
+    d->handle = handle;
+    d->refresh_info();
+    return d;
+}
+
 struct MatrixCOO {
     long n_rows{};
     long n_cols{};

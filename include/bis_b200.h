@@ -164,6 +164,18 @@ int bis_matrix_extract_diagonal(bis_context *ctx, const bis_matrix *A,
  * sets (split_LU_new, LU_factors.hpp:122-309), single-GPU contexts only. */
 int bis_matrix_split_triangular(bis_context *ctx, const bis_matrix *A,
                                 bis_matrix **L_strict, bis_matrix **U_strict);
+/* ILU(0) of the device matrix A, on the device (factor_ILU0_old,
+ * LU_factors.hpp:320-539: row-wise IKJ on A's pattern, pivots |u_kk| < 1e-16
+ * skipped :370, updates only where the working value is != 0.0 :384, diagonals
+ * |u_ii| < pivot_tolerance replaced by +-pivot_replacement :410-412).  Rows are
+ * factored in dependency order by one launch; the result is bit-identical to
+ * the sequential routine.  Returns the strict factors (columns ascending, as
+ * the reference stores them) with their level sets, L_D = 1 (optional) and
+ * U_D = diag(U).  Single-GPU contexts only. */
+int bis_matrix_ilu0(bis_context *ctx, const bis_matrix *A,
+                    double pivot_tolerance, double pivot_replacement,
+                    bis_matrix **L_strict, bis_matrix **U_strict,
+                    double *L_D /* [dev] or NULL */, double *U_D /* [dev] */);
 
 /* ---- kernels.hpp seam: one entry per reference kernel ------------------- */
 /* spmv / native_spmv, kernels.hpp:22-52.  x may be offset by the caller

@@ -530,6 +530,109 @@ def test_extract_diagonal_and_split(ctx):
     B.free()
 
 
+def _host_levels(rp, col, upper):
+    n = len(rp) - 1
+    lev = np.zeros(n, np.int64)
+    for r in (range(n - 1, -1, -1) if upper else range(n)):
+        c = col[rp[r]:rp[r + 1]]
+        lev[r] = (lev[c].max() + 1) if c.size else 0
+    return lev
+
+
+def _random_general(n, seed, zero_fraction=0.05):
+    """Unsorted columns, a diagonal in every row, some stored zeros and some tiny diagonals: the cases the
+    ILU(0) rules treat specially (LU_factors.hpp:370, 384, 410-412)."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for r in range(n):
+        k = int(rng.integers(1, 9))
+        c = set(int(v) for v in rng.integers(max(0, r - 12), min(n, r + 13), size=k))
+        c.add(r)
+        c = np.array(sorted(c))
+        rng.shuffle(c)
+        v = rng.uniform(-1.0, 1.0, size=c.size)
+        v[rng.uniform(size=c.size) < zero_fraction] = 0.0
+        d = np.where(c == r)[0][0]
+        v[d] = 4.0 + rng.uniform()
+        if r % 37 == 5:
+            v[d] = 1e-12      # below ILU0_PIVOT_TOLERANCE: replaced
+        if r % 53 == 7:
+            v[d] = -3e-9
+        rows.append((c, v))
+    rp = np.zeros(n + 1, np.int32)
+    rp[1:] = np.cumsum([len(c) for c, _ in rows])
+    return rp, np.concatenate([c for c, _ in rows]).astype(np.int32), np.concatenate([v for _, v in rows])
+
+
+@pytest.mark.parametrize("case", ["hpcg", "anderson", "random", "random_big"])
+def test_device_ilu0_matches_host_factorisation(ctx, case):
+    """bis_matrix_ilu0 (one dataflow launch) against the sequential host routine that tests/test_host_cpu.py
+    pins to the compiled reference's factor_ILU0_old: every factor entry bit for bit."""
+    if case == "hpcg":
+        rp, col, val = matgen.hpcg(9, 7, 6)
+    elif case == "anderson":
+        rp, col, val = matgen.anderson(9, 8, 7, 5.0, 1.0, 3, True)
+    else:
+        rp, col, val = _random_general(300 if case == "random" else 20000, 11)
+    rp = rp.astype(np.int32)
+    n = len(rp) - 1
+    f = port.factor(rp, col, val, "ilu0")
+    A = ctx.upload_crs(rp, col, val)
+    L, U, dLD, dUD = ctx.ilu0(A, n)
+    lrp, lcol, lval = L.download()
+    urp, ucol, uval = U.download()
+    assert np.array_equal(lrp, f.l_rp) and np.array_equal(lcol, f.l_col)
+    assert np.array_equal(urp, f.u_rp) and np.array_equal(ucol, f.u_col)
+    assert np.array_equal(lval.view(np.int64), f.l_val.view(np.int64))
+    assert np.array_equal(uval.view(np.int64), f.u_val.view(np.int64))
+    assert np.array_equal(ctx.download(dUD, n).view(np.int64), f.U_D.view(np.int64))
+    assert np.array_equal(ctx.download(dLD, n), f.L_D)
+    assert L.info()["n_levels"] == int(_host_levels(f.l_rp, f.l_col, False).max()) + 1
+    assert U.info()["n_levels"] == int(_host_levels(f.u_rp, f.u_col, True).max()) + 1
+    # and the factors solve: apply the preconditioner through the device level sets
+    y = np.linspace(-1.0, 1.0, n)
+    want = port.apply_preconditioner("ilu0", f, y)
+    dy, dout, dtmp = ctx.upload(y), ctx.alloc(n), ctx.alloc(n)
+    dAD = ctx.upload(f.A_D)
+    ctx.call("bis_apply_preconditioner", capi.PRECOND["ilu0"], n, L.h, U.h, dAD, None, dLD, dUD, dout, dy, dtmp, None)
+    assert np.array_equal(ctx.download(dout, n).view(np.int64), want.view(np.int64))
+    for v in (dy, dout, dtmp, dAD, dLD, dUD):
+        ctx.free(v)
+    L.free(), U.free(), A.free()
+
+
+def test_device_level_analysis_matches_host(ctx):
+    rp, col, val = _random_general(5000, 5, zero_fraction=0.0)
+    f = port.factor(rp, col, val, "sgs")
+    A = ctx.upload_crs(rp, col, val)
+    L, U = ctx.split_triangular(A)
+    assert L.info()["n_levels"] == int(_host_levels(f.l_rp, f.l_col, False).max()) + 1
+    assert U.info()["n_levels"] == int(_host_levels(f.u_rp, f.u_col, True).max()) + 1
+    lrp, lcol, lval = L.download()
+    assert np.array_equal(lrp, f.l_rp) and np.array_equal(lcol, f.l_col) and np.array_equal(lval, f.l_val)
+    # both sweeps through the device-built level sets, bit for bit against the sequential oracle
+    n = len(rp) - 1
+    b = np.cos(np.arange(n))
+    dD, db, dx = ctx.upload(f.A_D), ctx.upload(b), ctx.alloc(n)
+    ctx.call("bis_sptrsv", L.h, dx, dD, db)
+    assert np.array_equal(ctx.download(dx, n).view(np.int64), port.sptrsv(f.l_rp, f.l_col, f.l_val, f.A_D, b).view(np.int64))
+    ctx.call("bis_bsptrsv", U.h, dx, dD, db)
+    assert np.array_equal(ctx.download(dx, n).view(np.int64), port.sptrsv(f.u_rp, f.u_col, f.u_val, f.A_D, b, backward=True).view(np.int64))
+    for v in (dD, db, dx):
+        ctx.free(v)
+    L.free(), U.free(), A.free()
+
+
+def test_zero_diagonal_is_fatal(ctx):
+    # SanityChecker::zero_diag (common.hpp:388-391, LU_factors.hpp:842-845)
+    B = ctx.upload_crs(i32(0, 2, 4), i32(0, 1, 0, 1), f64(1e-17, 1, 1, 2))
+    d = ctx.alloc(2)
+    with pytest.raises(capi.BisError, match="Zero detected on diagonal at row index 0"):
+        ctx.call("bis_matrix_extract_diagonal", B.h, d, None)
+    ctx.free(d)
+    B.free()
+
+
 def test_hpcg_levels_follow_wavefront(ctx):
     # HPCG natural ordering: level(x,y,z) = x + 2y + 4z  =>  7n - 6 levels (SURVEY.md 7)
     n = 12
