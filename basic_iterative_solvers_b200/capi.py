@@ -61,6 +61,7 @@ _SIGS = {
     "bis_matrix_download_crs": ([c_ctx, c_mat, C.c_void_p, C.c_void_p, C.c_void_p], cint),
     "bis_matrix_extract_diagonal": ([c_ctx, c_mat, c_dev, c_dev], cint),
     "bis_matrix_split_triangular": ([c_ctx, c_mat, C.POINTER(c_mat), C.POINTER(c_mat)], cint),
+    "bis_matrix_scale_symmetric": ([c_ctx, c_mat, c_dev], cint),
     "bis_matrix_ilu0": ([c_ctx, c_mat, C.c_double, C.c_double, C.POINTER(c_mat), C.POINTER(c_mat), c_dev, c_dev], cint),
     "bis_spmv": ([c_ctx, c_mat, c_dev, c_dev], cint),
     "bis_sptrsv": ([c_ctx, c_mat, c_dev, c_dev, c_dev], cint),

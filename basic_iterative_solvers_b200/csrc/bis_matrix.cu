@@ -510,3 +510,64 @@ extern "C" int bis_matrix_extract_diagonal(bis_context *c, const bis_matrix *A, 
     BIS_REQUIRE(missing[1] == 0, "Zero detected on diagonal at row index %d", missing[1] - 1);
     return 0;
 }
+
+// ---- -scale: symmetric diagonal scaling (preprocessing.hpp:8-24,39-50, LU_factors.hpp:880-898) ----
+namespace {
+template <typename RP>
+__global__ void scale_extract_kernel(int64_t n, const RP *rp, const int *col, const double *val, double *s, int *zero) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double sr = 0.0;   // A_D_scale starts at 0.0 (solver.hpp:105) and keeps it for a row without diagonal
+        for (RP k = rp[r]; k < rp[r + 1]; ++k)
+            if (col[k] == r) {
+                const double d = val[k];
+                if (fabs(d) < 1e-16) atomicExch(zero, (int)(r + 1 > 0x7fffffff ? 0x7fffffff : r + 1));
+                sr = div_rn(1.0, sqrt(fabs(d)));
+            }
+        s[r] = sr;
+    }
+}
+template <typename RP>
+__global__ void scale_apply_kernel(int64_t n, const RP *rp, const int *col, double *val, const double *s,
+                                   const double *ghost, int64_t n_owned) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const double sr = s[r];
+        for (RP k = rp[r]; k < rp[r + 1]; ++k) {
+            const int c = col[k];
+            const double sc = c < n_owned ? s[c] : ghost[c - n_owned];
+            val[k] = mul_rn(val[k], mul_rn(sr, sc));   // A->val[i] *= (s_row * s_col)
+        }
+    }
+}
+} // namespace
+
+extern "C" int bis_matrix_scale_symmetric(bis_context *c, bis_matrix *A, double *D_scale) {
+    BIS_REQUIRE(c && A && D_scale, "null argument");
+    BIS_REQUIRE(A->triangular == 0, "bis_matrix_scale_symmetric: general matrices only");
+    BIS_CUDA(cudaSetDevice(c->device));
+    const int64_t n = A->n_rows;
+    int *d_zero = nullptr;
+    BIS_CHECK(dev_alloc(&d_zero, 1));
+    BIS_CUDA(cudaMemsetAsync(d_zero, 0, sizeof(int), c->stream));
+    const int blocks = bis_blocks_for(n, 256, c->sm_count * 8);
+    if (A->rp_bytes == 8)
+        scale_extract_kernel<int64_t><<<blocks, 256, 0, c->stream>>>(n, static_cast<const int64_t *>(A->d_rp), A->d_col, A->d_val, D_scale, d_zero);
+    else
+        scale_extract_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(n, static_cast<const int32_t *>(A->d_rp), A->d_col, A->d_val, D_scale, d_zero);
+    BIS_LAUNCH_CHECK(c);
+    int zero = 0;
+    BIS_CUDA(cudaMemcpyAsync(&zero, d_zero, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_zero);
+    BIS_REQUIRE(zero == 0, "Zero detected on diagonal at row index %d", zero - 1);
+    // the column factors of ghost columns come from their owners
+    if (A->distributed) {
+        BIS_CHECK(bis_halo_exchange_begin(c, A, D_scale));
+        BIS_CHECK(bis_halo_exchange_end(c, A));
+    }
+    if (A->rp_bytes == 8)
+        scale_apply_kernel<int64_t><<<blocks, 256, 0, c->stream>>>(n, static_cast<const int64_t *>(A->d_rp), A->d_col, A->d_val, D_scale, A->halo.cur_ghost, A->n_cols);
+    else
+        scale_apply_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(n, static_cast<const int32_t *>(A->d_rp), A->d_col, A->d_val, D_scale, A->halo.cur_ghost, A->n_cols);
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}

@@ -45,7 +45,7 @@ def load() -> C.CDLL:
     lib.bis_host_gmres_update_g.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_double]
     lib.bis_host_gmres_update_g.restype = C.c_double
     lib.bis_host_solve.argtypes = ([C.c_void_p, C.c_char_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 3 +
-                                   [C.c_void_p] * 2 + [C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 5)
+                                   [C.c_void_p] * 2 + [C.c_int, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 5)
     lib.bis_host_bench_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.bis_host_bench_open.restype = C.c_void_p
     lib.bis_host_bench_close.argtypes = [C.c_void_p]
@@ -155,7 +155,7 @@ class SolveResult:
 
 def solve(ctx: capi.Context, method: str, precond: str = "none", *, crs=None, matrix_name=None,
           restart_len: int = 10, b=None, x0=None, max_iters: int = 0, tol: float = 0.0,
-          quiet: bool = True, want_x: bool = True) -> SolveResult:
+          quiet: bool = True, want_x: bool = True, num_scale: bool = False) -> SolveResult:
     """preprocessing() + solve() of the host stack on the device behind `ctx`.
 
     crs = (row_ptr, col, val) host arrays, or matrix_name = generator / file
@@ -183,7 +183,7 @@ def solve(ctx: capi.Context, method: str, precond: str = "none", *, crs=None, ma
     # x_star length: local rows; for a named matrix ask for it afterwards
     xs = np.zeros(n) if (want_x and crs is not None) else None
     rc = lib.bis_host_solve(ctx.h, name, n, _p(rp), _p(col), _p(val), METHOD[method], PRECOND[precond],
-                            restart_len, _p(bb), _p(xx), int(max_iters), float(tol), int(quiet),
+                            restart_len, _p(bb), _p(xx), int(max_iters), float(tol), int(quiet), int(num_scale),
                             _p(hist), _p(itime), _p(xs), oi, od)
     if rc != 0:
         raise capi.BisError(_err())

@@ -108,7 +108,7 @@ double bis_host_gmres_update_g(int k, int m, double *Q, double *g, double *g_tmp
 // seconds, mean seconds per iteration (harness table, first iteration excluded).
 int bis_host_solve(bis_context *dev, const char *matrix_name, int n, const int *rp, const int *col,
                    const double *val, int method, int precond, int restart_len, const double *b,
-                   const double *x0, int max_iters, double tol, int quiet, double *history,
+                   const double *x0, int max_iters, double tol, int quiet, int num_scale, double *history,
                    double *iter_time, double *x_star, int *out_int, double *out_dbl) {
     try {
         Args args;
@@ -117,6 +117,7 @@ int bis_host_solve(bis_context *dev, const char *matrix_name, int n, const int *
         args.preconditioner = static_cast<PrecondType>(precond);
         args.restart_length = restart_len;
         args.quiet = quiet != 0;
+        args.num_scale = num_scale != 0;
         Timers timers;
         std::unique_ptr<Solver> solver = make_solver(&args, dev);
         if (max_iters > 0) {

@@ -7,8 +7,7 @@
 // Deviations, both stated in DESIGN.md: (1) the triangular copies are only
 // built when the method or preconditioner uses them (the reference always
 // builds all four, preprocessing.hpp:70-81; at HPCG-512 they would not fit);
-// (2) -scale (preprocessing.hpp:39-50) is outside the hot-path scope and is
-// rejected.
+// (2) the factor step works on the device-resident matrix.
 #pragma once
 
 #include "common.hpp"
@@ -21,7 +20,6 @@
 inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
                           std::unique_ptr<MatrixCRS> &A, std::unique_ptr<DeviceCRS> dA = nullptr,
                           const double *b_host = nullptr, const double *x0_host = nullptr) {
-    if (cli_args->num_scale) bis_fatal("-scale 1 is not supported by the device path (out of hot-path scope)");
     Interface *dev = solver->dev;
 
     timers->preprocessing_upload_time.start();
@@ -42,6 +40,13 @@ inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
     solver->init_structs(n);
     timers->preprocessing_init_time.stop();
     solver->A = std::move(A);
+
+    if (solver->num_scale) {
+        // preprocessing.hpp:39-50: solve A'x' = b' with A' = D^-1/2 A D^-1/2, b' = D^-1/2 b, x_0' = D^-1/2 x_0
+        BIS_OK(bis_matrix_scale_symmetric(dev, solver->dA->handle, solver->A_D_scale));
+        BIS_OK(bis_elemwise_mult_vectors(dev, solver->x_0, solver->A_D_scale, solver->x_0, n, 1.0));
+        BIS_OK(bis_elemwise_mult_vectors(dev, solver->b, solver->A_D_scale, solver->b, n, 1.0));
+    }
 
     timers->preprocessing_factor_time.start();
     // peel_diag_crs on the device: A_D and 1/A_D (LU_factors.hpp:827-869); fatal on a missing or zero diagonal

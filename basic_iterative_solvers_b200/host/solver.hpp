@@ -55,7 +55,7 @@ class Solver {
     // common vectors [dev]
     double *x_star = nullptr, *x_0 = nullptr, *b = nullptr, *tmp = nullptr, *work = nullptr;
     double *residual = nullptr, *residual_0 = nullptr;
-    double *A_D = nullptr, *A_D_inv = nullptr, *L_D = nullptr, *U_D = nullptr;
+    double *A_D = nullptr, *A_D_inv = nullptr, *L_D = nullptr, *U_D = nullptr, *A_D_scale = nullptr;
 
     // bookkeeping [host]
     double *collected_residual_norms = nullptr;
@@ -96,6 +96,7 @@ class Solver {
         A_D_inv = dev_new(dev, n);
         L_D = dev_new(dev, n);
         U_D = dev_new(dev, n);
+        A_D_scale = dev_new(dev, n);
         if (!gmres_restarted) {
             init_vector(dev, x_star, 0.0, n);
             init_vector(dev, x_0, INIT_X_VAL, n);
@@ -104,6 +105,7 @@ class Solver {
             init_vector(dev, A_D_inv, 0.0, n);
             init_vector(dev, L_D, 1.0, n);
             init_vector(dev, U_D, 1.0, n);
+            init_vector(dev, A_D_scale, 0.0, n);
         }
     }
 
@@ -119,7 +121,7 @@ class Solver {
     virtual void get_explicit_x() {}
 
     virtual ~Solver() {
-        for (double **p : {&x_star, &x_0, &b, &tmp, &work, &residual, &residual_0, &A_D, &A_D_inv, &L_D, &U_D})
+        for (double **p : {&x_star, &x_0, &b, &tmp, &work, &residual, &residual_0, &A_D, &A_D_inv, &L_D, &U_D, &A_D_scale})
             dev_delete(dev, *p);
         delete[] collected_residual_norms;
         delete[] time_per_iteration;

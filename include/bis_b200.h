@@ -160,6 +160,14 @@ int bis_matrix_download_crs(bis_context *ctx, const bis_matrix *A,
 int bis_matrix_extract_diagonal(bis_context *ctx, const bis_matrix *A,
                                 double *D /* [dev] */,
                                 double *D_inv /* [dev] or NULL */);
+/* -scale: A <- D^-1/2 A D^-1/2 in place with D_scale[r] = 1/sqrt(|A[r][r]|)
+ * (extract_scale + scale_mat, LU_factors.hpp:880-898, preprocessing.hpp:15-24;
+ * 0.0 for a row without diagonal as solver.hpp:105 leaves it, fatal on a zero
+ * diagonal).  D_scale is written; the caller scales b and x_0 with it
+ * (preprocessing.hpp:48-49).  Distributed matrices fetch the factors of their
+ * ghost columns from the owners. */
+int bis_matrix_scale_symmetric(bis_context *ctx, bis_matrix *A,
+                               double *D_scale /* [dev] out */);
 /* Device split of A into strictly lower / upper triangular matrices with level
  * sets (split_LU_new, LU_factors.hpp:122-309), single-GPU contexts only. */
 int bis_matrix_split_triangular(bis_context *ctx, const bis_matrix *A,

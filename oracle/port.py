@@ -161,3 +161,21 @@ def solve(rp, col, val, method, precond="none", restart_len=10, b=None, x0=None,
     cnt = int(oi[1])
     return SolveResult(hist[:cnt].copy(), float(od[1]), int(oi[0]), bool(oi[2]), int(oi[3]),
                        float(od[0]), xs, np.zeros(0), 0.0, 0.0, 0.0, 0.0)
+
+
+def scale_symmetric(rp, col, val):
+    """-scale 1 restated in numpy (test infrastructure): extract_scale + scale_mat of the reference
+    (utilities/LU_factors.hpp:880-898, preprocessing.hpp:15-24).  Returns (val', s) with
+    s[r] = 1 / sqrt(|A[r][r]|) (0.0 for a row without diagonal, solver.hpp:105) and
+    val'[k] = val[k] * (s[row] * s[col]), every operation rounded separately as the scalar code does.
+    The reference then solves with b' = s * b and -- because init_structs copied x_0 before the scaling
+    (preprocessing.hpp:33 vs :48) -- still starts from the UNSCALED initial guess."""
+    rp = np.asarray(rp, np.int64)
+    col = np.asarray(col, np.int64)
+    val = np.asarray(val, np.float64)
+    n = rp.size - 1
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    s = np.zeros(n)
+    diag = rows == col
+    s[rows[diag]] = 1.0 / np.sqrt(np.abs(val[diag]))      # last match wins, as in the reference's loop
+    return val * (s[rows] * s[col]), s

@@ -33,10 +33,10 @@ SOLVES = [("j", "none"), ("gs", "none"), ("sgs", "none"), ("cg", "none"), ("gm",
           ("bi", "j"), ("bi", "gs"), ("bi", "bgs"), ("bi", "sgs"), ("bi", "ilu0")]
 
 
-def solves(rp, col, val, which, restart_len=10):
+def solves(rp, col, val, which, restart_len=10, num_scale=False):
     out = {}
     for method, pre in which:
-        r = refshim.solve(rp, col, val, method, pre, restart_len=restart_len, threads=1)
+        r = refshim.solve(rp, col, val, method, pre, restart_len=restart_len, threads=1, num_scale=num_scale)
         key = f"{method}__{pre}"
         out[key + "__history"] = r.history
         out[key + "__meta"] = np.array([r.iter_count, int(r.converged), r.restarts], np.int64)
@@ -46,7 +46,8 @@ def solves(rp, col, val, which, restart_len=10):
         # OpenMP threads and with the pinned-codegen flavour, against the 1-thread run above.
         noise, its_lo, its_hi = 0.0, r.iter_count, r.iter_count
         for thr, det in ((8, False), (4, False), (1, True)):
-            q = refshim.solve(rp, col, val, method, pre, restart_len=restart_len, threads=thr, det=det)
+            q = refshim.solve(rp, col, val, method, pre, restart_len=restart_len, threads=thr, det=det,
+                              num_scale=num_scale)
             k = min(q.history.size, r.history.size)
             with np.errstate(invalid="ignore"):
                 dmax = np.nanmax(np.abs(q.history[:k] - r.history[:k])) / r.history[0]
@@ -138,5 +139,29 @@ def main():
     np.savez_compressed(os.path.join(OUT, "anderson_dd_12_10_8.npz"), **d)
 
 
+def scale_fixtures():
+    """-scale 1 (preprocessing.hpp:39-50): the reference solves D^-1/2 A D^-1/2 x' = D^-1/2 b."""
+    assert refshim.available(), "build oracle/_ref first: make -C oracle ref"
+    refshim.load().ref_omp_set_threads(1)
+    print("fdm2d16, -scale 1")
+    rp, col, val = refshim.read_mtx(os.path.join(REF_DATA, "FDM-2d-16.mtx"))
+    d = {"rp": rp, "col": col, "val": val}
+    d.update(solves(rp, col, val, [("cg", "none"), ("cg", "j"), ("cg", "sgs"), ("gm", "ilu0"), ("bi", "j"),
+                                   ("j", "none"), ("sgs", "none")], num_scale=True))
+    np.savez_compressed(os.path.join(OUT, "fdm2d16_scale.npz"), **d)
+    print("anderson-dd 12x10x8, -scale 1 (non-constant diagonal)")
+    rp, col, val = matgen.anderson(12, 10, 8, ranpot=5.0, t=1.0, seed=1, periodic=False)
+    val2 = val.copy()
+    rows = np.repeat(np.arange(rp.size - 1), np.diff(rp))
+    val2[rows == col] += 8.0
+    d = {"rp": rp.astype(np.int32), "col": col, "val": val2}
+    d.update(solves(rp, col, val2, [("cg", "none"), ("gm", "ilu0"), ("bi", "sgs")], num_scale=True))
+    np.savez_compressed(os.path.join(OUT, "anderson_dd_12_10_8_scale.npz"), **d)
+
+
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "scale":
+        scale_fixtures()
+        raise SystemExit(0)
     main()

@@ -213,3 +213,19 @@ def test_live_reference_random_matrix():
         b = port.solve(rp, col, val, method, pre)
         assert a.iter_count == b.iter_count
         assert np.max(np.abs(a.history - b.history)) <= HIST_TOL * a.history[0]
+
+
+@pytest.mark.parametrize("name", ["fdm2d16_scale", "anderson_dd_12_10_8_scale"])
+def test_scale_restatement_against_reference_fixtures(name):
+    """-scale 1: the numpy restatement of extract_scale/scale_mat (oracle/port.py) feeding the oracle
+    reproduces the compiled reference's scaled solves (tests/golden/make_golden.py scale)."""
+    g = golden(name)
+    val_s, sc = port.scale_symmetric(g["rp"], g["col"], g["val"])
+    n = len(g["rp"]) - 1
+    for key in sorted(k[:-len("__history")] for k in g.files if k.endswith("__history")):
+        method, pre = key.split("__")
+        r = port.solve(g["rp"], g["col"], val_s, method, pre, b=sc * np.ones(n), x0=np.full(n, 0.1))
+        want = g[key + "__history"]
+        k = min(want.size, r.history.size)
+        assert np.max(np.abs(r.history[:k] - want[:k])) <= 1e-10 * want[0], key
+        assert r.iter_count == int(g[key + "__meta"][0]), key

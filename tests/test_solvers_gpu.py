@@ -85,6 +85,26 @@ def test_solve_matches_reference_fixture(ctx, name, key):
     assert got.launches > 0
 
 
+SCALE_CASES = [(n, k) for n in ("fdm2d16_scale", "anderson_dd_12_10_8_scale") for k in _keys(golden(n))]
+
+
+@pytest.mark.parametrize("name,key", SCALE_CASES)
+def test_scaled_solve_matches_reference_fixture(ctx, name, key):
+    """-scale 1 (preprocessing.hpp:39-50) through the device path against the compiled reference."""
+    g = golden(name)
+    method, pre = key.split("__")
+    got = host.solve(ctx, method, pre, crs=(g["rp"], g["col"], g["val"]), num_scale=True)
+    stable = check_against_fixture(got, g, key)
+    if stable and got.converged:
+        x_ref = g[key + "__x"]
+        assert np.max(np.abs(got.x_star - x_ref)) <= 1e-9 * max(np.max(np.abs(x_ref)), 1.0)
+    # the same system, scaled in numpy and handed to the oracle unscaled-API: identical bar
+    val_s, sc = port.scale_symmetric(g["rp"], g["col"], g["val"])
+    n = len(g["rp"]) - 1
+    want = port.solve(g["rp"], g["col"], val_s, method, pre, b=sc * np.ones(n), x0=np.full(n, 0.1))
+    check(got, want, exact_count=False)
+
+
 @pytest.mark.parametrize("method,pre", [("cg", "none"), ("cg", "j"), ("bi", "none"), ("bi", "j"),
                                         ("j", "none"), ("gs", "none"), ("sgs", "none"), ("gm", "none"),
                                         ("gm", "j")])
