@@ -80,6 +80,8 @@ _SIGS = {
     "bis_apply_preconditioner": ([c_ctx, cint, i64, c_mat, c_mat] + [c_dev] * 8, cint),
     "bis_scalar_set": ([c_ctx, cint, dbl], cint),
     "bis_scalar_get": ([c_ctx, cint, cint, C.POINTER(dbl)], cint),
+    "bis_scalar_read_begin": ([c_ctx, cint, cint], cint),
+    "bis_scalar_read_end": ([c_ctx, cint, cint, C.POINTER(dbl)], cint),
     "bis_scalar_copy": ([c_ctx, cint, cint], cint),
     "bis_dot_to_slot": ([c_ctx, c_dev, c_dev, i64, cint], cint),
     "bis_sumsq_to_slot": ([c_ctx, c_dev, i64, cint], cint),

@@ -42,6 +42,7 @@ static int context_init(bis_context *c, int device) {
     BIS_CUDA(cudaEventCreate(&c->ev_timer1));
     BIS_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     BIS_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    BIS_CUDA(cudaEventCreateWithFlags(&c->ev_scalar, cudaEventDisableTiming));
     BIS_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * BIS_NUM_SCALARS));
     BIS_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * BIS_NUM_SCALARS));
     BIS_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * BIS_NUM_SCALARS));
@@ -140,6 +141,7 @@ extern "C" int bis_context_destroy(bis_context *c) {
     cudaEventDestroy(c->ev_timer1);
     cudaEventDestroy(c->ev_main);
     cudaEventDestroy(c->ev_comm);
+    cudaEventDestroy(c->ev_scalar);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->comm_stream);
     delete c;
@@ -353,6 +355,26 @@ extern "C" int bis_scalar_get(bis_context *c, int first_slot, int count, double 
     BIS_CUDA(cudaMemcpyAsync(c->h_scalars + first_slot, c->d_scalars + first_slot,
                              sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
     BIS_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(values, c->h_scalars + first_slot, sizeof(double) * count);
+    return 0;
+}
+
+// Split read: begin() enqueues the copy behind everything queued so far and returns at once, end()
+// waits for THAT copy only -- work queued in between (the next iteration) keeps the device busy
+// while the host looks at the value.  One read may be outstanding per context.
+extern "C" int bis_scalar_read_begin(bis_context *c, int first_slot, int count) {
+    BIS_REQUIRE(c && first_slot >= 0 && count > 0 && first_slot + count <= BIS_NUM_SCALARS,
+                "bis_scalar_read_begin: bad range [%d,+%d)", first_slot, count);
+    BIS_CUDA(cudaMemcpyAsync(c->h_scalars + first_slot, c->d_scalars + first_slot, sizeof(double) * count,
+                             cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaEventRecord(c->ev_scalar, c->stream));
+    return 0;
+}
+
+extern "C" int bis_scalar_read_end(bis_context *c, int first_slot, int count, double *values) {
+    BIS_REQUIRE(c && values && first_slot >= 0 && count > 0 && first_slot + count <= BIS_NUM_SCALARS,
+                "bis_scalar_read_end: bad range [%d,+%d)", first_slot, count);
+    BIS_CUDA(cudaEventSynchronize(c->ev_scalar));
     memcpy(values, c->h_scalars + first_slot, sizeof(double) * count);
     return 0;
 }

@@ -117,7 +117,7 @@ struct bis_context {
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_timer0 = nullptr, ev_timer1 = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_comm = nullptr, ev_scalar = nullptr;
     double *d_scalars = nullptr;         // BIS_NUM_SCALARS
     double *h_scalars = nullptr;         // pinned staging
     double *d_partials = nullptr;

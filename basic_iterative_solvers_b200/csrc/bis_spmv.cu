@@ -250,6 +250,7 @@ int launch_tma(bis_context *c, const tma::Plan &p, SpmvTmaIn in, const Epi &epi,
 struct Segment {
     int64_t lo, cnt;
     bool ghost;
+    int64_t lo2 = 0, cnt2 = 0;   // variant 3 only: a second range handled by the same launch
 };
 
 // One contiguous row range with either variant.
@@ -371,7 +372,8 @@ bool win_plan(const bis_context *c, const bis_matrix *A, WinPlan *p) {
 
 template <typename RP, class Epi>
 int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const double *x, int64_t tile_lo,
-               int64_t tile_cnt, const Epi &epi, RedArgs &ra, int *nb) {
+               int64_t tile_cnt1, int64_t tile_lo2, int64_t tile_cnt2, const Epi &epi, RedArgs &ra, int *nb) {
+    const int64_t tile_cnt = tile_cnt1 + tile_cnt2;
     auto kern = spmv_win_kernel<RP, Epi>;
     static size_t configured = 0;
     if (configured < p.smem_bytes) {
@@ -390,7 +392,7 @@ int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const doub
     in.rp = A->d_rp; in.val = A->d_val; in.lidx = w.d_lidx;
     in.seg_start = w.d_seg_start; in.seg_len = w.d_seg_len; in.seg_off = w.d_seg_off; in.nseg = w.d_nseg;
     in.x = x; in.ghost = A->halo.cur_ghost; in.n_rows = A->n_rows;
-    in.tile_lo = tile_lo; in.tile_cnt = tile_cnt;
+    in.tile_lo = tile_lo; in.tile_cnt = tile_cnt; in.tile_split = tile_cnt1; in.tile_lo2 = tile_lo2;
     in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.stage_bytes = p.stage_bytes;
     in.debug = c->opt_spmv_debug;
     *nb = (int)grid;
@@ -444,8 +446,16 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
             seg[nseg++] = {0, n_units, false};
         } else if (ie > ib) {
             seg[nseg++] = {ib, ie - ib, false};
-            if (ib > 0) seg[nseg++] = {0, ib, true};
-            if (n_units > ie) seg[nseg++] = {ie, n_units - ie, true};
+            if (use_win && ib > 0 && n_units > ie) {
+                // both boundary strips in ONE launch (one ramp-up and one tail instead of two)
+                seg[nseg] = {0, ib, true};
+                seg[nseg].lo2 = ie;
+                seg[nseg].cnt2 = n_units - ie;
+                ++nseg;
+            } else {
+                if (ib > 0) seg[nseg++] = {0, ib, true};
+                if (n_units > ie) seg[nseg++] = {ie, n_units - ie, true};
+            }
         } else {
             seg[nseg++] = {0, n_units, true};
         }
@@ -456,9 +466,9 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
         ra.finalize = (i == nseg - 1) ? 1 : 0;
         if (use_win) {
             if (A->rp_bytes == 8)
-                BIS_CHECK((launch_win<int64_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, epi, ra, &nb)));
+                BIS_CHECK((launch_win<int64_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, seg[i].lo2, seg[i].cnt2, epi, ra, &nb)));
             else
-                BIS_CHECK((launch_win<int32_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, epi, ra, &nb)));
+                BIS_CHECK((launch_win<int32_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, seg[i].lo2, seg[i].cnt2, epi, ra, &nb)));
         } else {
             BIS_CHECK(launch_segment(c, A, x, seg[i], epi, ra, &nb));
         }

@@ -178,7 +178,8 @@ struct SpmvWinIn {
     const double *x;
     const double *ghost;
     int64_t n_rows;
-    int64_t tile_lo, tile_cnt;    // tiles handled by this launch
+    int64_t tile_lo, tile_cnt;    // tiles handled by this launch: tile_lo + v for v < tile_split,
+    int64_t tile_split, tile_lo2; // tile_lo2 + (v - tile_split) above (both boundary strips of a row block in one launch)
     int R;                        // rows per tile == consumer threads
     int cap;                      // nonzeros per stage (multiple of 8)
     int xcap;                     // window doubles per stage (even)
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn 
         const uint32_t off_rp = off_xw + (uint32_t)in.xcap * 8u;
         const uint32_t off_li = off_rp + (uint32_t)(R + 4) * 8u;
         auto tile_rows = [&](int64_t j, int64_t &tile, int64_t &r0, int64_t &r1) {
-            tile = in.tile_lo + blockIdx.x + j * gridDim.x;
+            const int64_t v = blockIdx.x + j * gridDim.x;
+            tile = v < in.tile_split ? in.tile_lo + v : in.tile_lo2 + (v - in.tile_split);
             r0 = tile * R;
             r1 = r0 + R;
             if (r1 > in.n_rows) r1 = in.n_rows;
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn 
     } else {
         for (int64_t j = group; j < my_tiles; j += in.nstage) {
             const int st = group;
-            const int64_t tile = in.tile_lo + blockIdx.x + j * gridDim.x;
+            const int64_t v = blockIdx.x + j * gridDim.x;
+            const int64_t tile = v < in.tile_split ? in.tile_lo + v : in.tile_lo2 + (v - in.tile_split);
             const int64_t row = tile * R + tid_g;
             const unsigned char *sb = stages + (size_t)st * in.stage_bytes;
             const double *__restrict__ sval = reinterpret_cast<const double *>(sb);

@@ -271,14 +271,8 @@ int bis_host_bench_prepare(void *h, int warmup, int64_t *info) {
         std::unique_ptr<DeviceCRS> dA;
         obtain_matrix(&s->args, s->dev, A, dA);
         preprocessing(&s->args, solver, &s->timers, A, std::move(dA));
-        for (int i = 0; i < warmup; ++i) {
-            s->timers.per_iteration_time.start();
-            solver->iterate(&s->timers);
-            ++solver->iter_count;
-            solver->sample_residual(&s->timers.per_iteration_time);
-            solver->exchange();
-            solver->check_restart(&s->timers);
-        }
+        bool ahead = false;
+        for (int i = 0; i < warmup; ++i) harness_step(solver, &s->timers, ahead, i + 1 < warmup);
         BIS_OK(bis_context_synchronize(s->dev));
         bench_fill_info(solver, info);
         return 0;
@@ -303,14 +297,10 @@ int bis_host_bench_run(void *h, int steps, double *out) {
         Stopwatch w;
         w.start();
         BIS_OK(bis_timer_start(s->dev));
-        for (int i = 0; i < steps; ++i) {
-            s->timers.per_iteration_time.start();
-            solver->iterate(&s->timers);
-            ++solver->iter_count;
-            solver->sample_residual(&s->timers.per_iteration_time);
-            solver->exchange();
-            solver->check_restart(&s->timers);
-        }
+        // the loop body of solve(); the last timed step does not run ahead, so exactly `steps` iterations
+        // are enqueued between the two timer events
+        bool ahead = false;
+        for (int i = 0; i < steps; ++i) harness_step(solver, &s->timers, ahead, i + 1 < steps);
         double ms = 0.0;
         BIS_OK(bis_timer_stop(s->dev, &ms));
         out[1] = w.check() * 1e3;

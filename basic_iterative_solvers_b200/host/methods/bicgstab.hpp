@@ -68,6 +68,8 @@ class BiCGSTABSolver : public Solver {
         std::swap(x_old, x_star);
         Solver::save_x_star();
     }
+    bool can_run_ahead() const override { return true; }
+    int norm_slot() const override { return S_RR_BI; }
     // bicgstab.hpp:220-223: ||residual||_2 == (r_new,r_new) reduced in bis_bicgstab_xr
     void record_residual_norm() override {
         residual_norm = std::sqrt(scalar(dev, S_RR_BI));

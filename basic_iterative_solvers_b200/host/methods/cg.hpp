@@ -74,6 +74,7 @@ class ConjugateGradientSolver : public Solver {
         std::swap(x_old, x_star);
         Solver::save_x_star();
     }
+    bool can_run_ahead() const override { return true; }   // x_new / x_old are double-buffered
     // cg.hpp:162-166: ||residual_new||_2, already reduced by bis_cg_update
     void record_residual_norm() override {
         residual_norm = std::sqrt(scalar(dev, S_RR));

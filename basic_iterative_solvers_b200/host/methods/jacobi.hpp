@@ -41,6 +41,10 @@ class JacobiSolver : public Solver {
         std::swap(x_old, x_star);
         Solver::save_x_star();
     }
+    bool can_run_ahead() const override { return true; }
+    void enqueue_residual_norm() override {
+        BIS_OK(bis_spmv_residual(dev, dA->handle, x_new, b, residual, tmp, S_RR));
+    }
     void record_residual_norm() override {
         BIS_OK(bis_spmv_residual(dev, dA->handle, x_new, b, residual, tmp, S_RR));
         residual_norm = std::sqrt(scalar(dev, S_RR));

@@ -145,6 +145,32 @@ class Solver {
         collected_residual_norms[collected_residual_norms_count++] = residual_norm;
     }
 
+    // ---- run-ahead (new in the build) ------------------------------------------------------------
+    // Methods whose iterate() never touches the vector that would become x_star (double-buffered
+    // x_new / x_old) let the harness enqueue iteration k+1 BEHIND the residual-norm readback of
+    // iteration k and only then wait for the value: the device works while the host decides.  When
+    // the decision is "stop", the iteration that ran ahead has only written the buffers a further
+    // iteration would have overwritten anyway.  norm_slot(): the device scalar holding ||r||^2.
+    virtual bool can_run_ahead() const { return false; }
+    virtual int norm_slot() const { return S_RR; }
+    virtual void enqueue_residual_norm() {}   // kernels that produce the norm, if iterate() did not
+
+    void sample_residual_begin() {
+        if (iter_count % residual_check_len == 0) {
+            enqueue_residual_norm();
+            BIS_OK(bis_scalar_read_begin(dev, norm_slot(), 1));
+        }
+    }
+    void sample_residual_end(Stopwatch *per_iteration_time) {
+        if (iter_count % residual_check_len == 0) {
+            double rr = 0.0;
+            BIS_OK(bis_scalar_read_end(dev, norm_slot(), 1, &rr));
+            residual_norm = std::sqrt(rr);
+            Solver::record_residual_norm();
+            time_per_iteration[collected_residual_norms_count] = per_iteration_time->check();
+        }
+    }
+
     void sample_residual(Stopwatch *per_iteration_time) {
         if (iter_count % residual_check_len == 0) {
             record_residual_norm();

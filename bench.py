@@ -234,6 +234,9 @@ def main():
         print(json.dumps(out), flush=True)
         return
 
+    # NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     from basic_iterative_solvers_b200 import capi, host

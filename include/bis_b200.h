@@ -240,6 +240,14 @@ int bis_apply_preconditioner(bis_context *ctx, int precond, int64_t n,
 int bis_scalar_set(bis_context *ctx, int slot, double value);
 int bis_scalar_get(bis_context *ctx, int first_slot, int count,
                    double *values /* [host] */); /* synchronises */
+/* Split read (the harness samples the residual norm every iteration,
+ * solver_harness.hpp:24): _begin enqueues the copy behind the work queued so far
+ * and returns; _end waits for that copy only, so kernels queued in between (the
+ * next iteration, run ahead by the host) keep the device busy meanwhile.  One
+ * read may be outstanding per context. */
+int bis_scalar_read_begin(bis_context *ctx, int first_slot, int count);
+int bis_scalar_read_end(bis_context *ctx, int first_slot, int count,
+                        double *values /* [host] */);
 int bis_scalar_copy(bis_context *ctx, int dst_slot, int src_slot);
 /* slot <- sum a*b ; slot <- sum v*v (NOT the square root) */
 int bis_dot_to_slot(bis_context *ctx, const double *a, const double *b,
