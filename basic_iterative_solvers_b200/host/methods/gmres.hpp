@@ -5,7 +5,8 @@
 // get_explicit_x's N x k product.  Host side, restated literally: the Givens
 // least-squares update on the (m+1) x m Hessenberg matrix (gmres.hpp:55-148) and
 // the k x k back-substitution (gmres.hpp:335-349).  One host<->device sync per
-// iteration fetches the new Hessenberg column.
+// iteration fetches the new Hessenberg column; the next iteration's device work is
+// already enqueued behind it.
 //
 // the reference's get_explicit_x reads y[k] one past the end of
 // `y` when k == m; the term is defined here as 0 (sum over j < k).
@@ -117,26 +118,40 @@ class GMRESSolver : public Solver {
         }
     }
 
-    // gmres.hpp:150-196
-    void iterate(Timers *) override {
-        const int m = gmres_restart_len;
-        const int k = iter_count - gmres_restart_count * m;
+    // Device part of gmres_separate_iteration (gmres.hpp:150-183) for basis index k: everything it
+    // needs (V[k]) is produced on the device, so it can be enqueued before the host has looked at
+    // iteration k-1.  h_0k..h_kk land in slots S_H..S_H+k, ||w||^2 in S_H+k+1.
+    void enqueue_iteration(const int k) {
         spmv(dev, dA.get(), V + (int64_t)k * N, w);
         precondition(w, w);
         // orthogonalize_V: h_jk = (w, v_j) ; w -= h_jk v_j, j = 0..k ; h_{k+1,k} = ||w||
         BIS_OK(bis_dot_to_slot(dev, w, V, N, S_H));
         for (int j = 0; j <= k; ++j)
             BIS_OK(bis_mgs_step(dev, N, w, V + (int64_t)j * N, j < k ? V + (int64_t)(j + 1) * N : nullptr,
-                                S_H + j, j < k ? S_H + j + 1 : S_HN));
-        BIS_OK(bis_scale_inv_norm(dev, N, V + (int64_t)(k + 1) * N, w, S_HN));
-        double col[80];
-        BIS_OK(bis_scalar_get(dev, S_H, k + 1, col));
-        for (int j = 0; j <= k; ++j) H[k + j * m] = col[j];
-        const double hn = std::sqrt(scalar(dev, S_HN));
-        H[(k + 1) * m + k] = hn;
-        if (!(hn > 0.0) && !(hn <= 0.0)) {
-            // NaN norm: the reference continues and stops on the NaN residual
+                                S_H + j, S_H + j + 1));
+        BIS_OK(bis_scale_inv_norm(dev, N, V + (int64_t)(k + 1) * N, w, S_H + k + 1));
+    }
+
+    // gmres.hpp:150-196.  One split read fetches the Hessenberg column; inside a restart cycle the
+    // device part of the NEXT iteration is enqueued behind that read, so the Givens update below runs
+    // on the host while the device already works (it only writes w, V[k+2] and the scalar slots the
+    // read has captured: harmless if this iteration turns out to be the last).
+    bool ahead_ = false;
+    void iterate(Timers *) override {
+        const int m = gmres_restart_len;
+        const int k = iter_count - gmres_restart_count * m;
+        if (!ahead_) enqueue_iteration(k);
+        ahead_ = false;
+        BIS_OK(bis_scalar_read_begin(dev, S_H, k + 2));
+        if (k + 1 < m && iter_count + 1 < max_iters - gmres_restart_count) {
+            enqueue_iteration(k + 1);
+            ahead_ = true;
         }
+        double col[80];
+        BIS_OK(bis_scalar_read_end(dev, S_H, k + 2, col));
+        for (int j = 0; j <= k; ++j) H[k + j * m] = col[j];
+        const double hn = std::sqrt(col[k + 1]);
+        H[(k + 1) * m + k] = hn;   // a NaN norm is kept: the reference continues and stops on the NaN residual
         least_squares(k, m, J.data(), H.data(), H_tmp.data(), Q.data(), Q_tmp.data(), R.data());
         update_g(k, m, Q.data(), g.data(), g_tmp.data(), residual_norm, beta);
     }
@@ -171,6 +186,7 @@ class GMRESSolver : public Solver {
         bool restart_cycle_reached = (iter_count % gmres_restart_len == 0) && (iter_count != 0);
         if (!norm_convergence && !over_max_iters && restart_cycle_reached) {
             gmres_restarted = true;
+            ahead_ = false;
             get_explicit_x();
             copy_vector(dev, x_old, x, N);
             init_structs(N);
