@@ -22,6 +22,32 @@ extern "C" int bis_device_count(int *count) {
     return 0;
 }
 
+// every live context, for bis_cuda_malloc's out-of-memory retry
+static std::vector<bis_context *> g_contexts;
+
+static void vector_cache_release(bis_context *c) {
+    if (c->vec_cache.empty()) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &e : c->vec_cache) cudaFree(e.second);
+    c->vec_cache.clear();
+    c->vec_cache_bytes = 0;
+    cudaSetDevice(cur);
+}
+
+// called where a matrix is about to be built (thrust scratch does not go through bis_cuda_malloc)
+void bis_vector_cache_trim(bis_context *c) {
+    size_t fr = 0, tot = 0;
+    if (c->vec_cache.empty() || cudaMemGetInfo(&fr, &tot) != cudaSuccess) return;
+    if (fr < tot / 3) vector_cache_release(c);
+}
+
+void bis_vector_cache_release_all() {
+    for (bis_context *c : g_contexts) vector_cache_release(c);
+}
+
 static int context_init(bis_context *c, int device) {
     int ndev = 0;
     BIS_CUDA(cudaGetDeviceCount(&ndev));
@@ -43,13 +69,13 @@ static int context_init(bis_context *c, int device) {
     BIS_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     BIS_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
     BIS_CUDA(cudaEventCreateWithFlags(&c->ev_scalar, cudaEventDisableTiming));
-    BIS_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * BIS_NUM_SCALARS));
+    BIS_CUDA(bis_cuda_malloc(&c->d_scalars, sizeof(double) * BIS_NUM_SCALARS));
     BIS_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * BIS_NUM_SCALARS));
     BIS_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * BIS_NUM_SCALARS));
-    BIS_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * BIS_MAX_RED * BIS_MAX_RED_BLOCKS));
-    BIS_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+    BIS_CUDA(bis_cuda_malloc(&c->d_partials, sizeof(double) * BIS_MAX_RED * BIS_MAX_RED_BLOCKS));
+    BIS_CUDA(bis_cuda_malloc(&c->d_counter, sizeof(unsigned int)));
     BIS_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int)));
-    BIS_CUDA(cudaMalloc(&c->d_errflag, sizeof(int)));
+    BIS_CUDA(bis_cuda_malloc(&c->d_errflag, sizeof(int)));
     BIS_CUDA(cudaMemset(c->d_errflag, 0, sizeof(int)));
     BIS_CUDA(cudaDeviceSynchronize());
     return 0;
@@ -62,6 +88,7 @@ extern "C" int bis_context_create(int device, bis_context **ctx) {
         delete c;
         return 1;
     }
+    g_contexts.push_back(c);
     *ctx = c;
     return 0;
 }
@@ -118,6 +145,7 @@ extern "C" int bis_context_create_distributed(int device, int rank, int nranks,
             return 1;
         }
     }
+    g_contexts.push_back(c);
     *ctx = c;
     return 0;
 }
@@ -126,6 +154,12 @@ extern "C" int bis_context_destroy(bis_context *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    vector_cache_release(c);
+    for (size_t i = 0; i < g_contexts.size(); ++i)
+        if (g_contexts[i] == c) {
+            g_contexts.erase(g_contexts.begin() + (long)i);
+            break;
+        }
     bis_peer_link_teardown(c);
     if (c->comm_halo) ncclCommDestroy(c->comm_halo);
     if (c->comm) ncclCommDestroy(c->comm);
@@ -264,7 +298,7 @@ extern "C" int bis_flush_l2(bis_context *c) {
     BIS_REQUIRE(c, "null context");
     if (!c->d_flush) {
         c->flush_bytes = c->l2_bytes ? 2 * c->l2_bytes : ((size_t)256 << 20);
-        BIS_CUDA(cudaMalloc(&c->d_flush, c->flush_bytes));
+        BIS_CUDA(bis_cuda_malloc(&c->d_flush, c->flush_bytes));
     }
     BIS_CUDA(cudaMemsetAsync(c->d_flush, 1, c->flush_bytes, c->stream));
     return 0;
@@ -274,6 +308,7 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     BIS_REQUIRE(c && key, "null argument");
     std::string k(key);
     if (k == "spmv_variant") c->opt_spmv_variant = value;
+    else if (k == "spmv_fused") c->opt_spmv_fused = value;
     else if (k == "dist_p2p") {
         // the transport must change on all ranks at the same point of the stream
         BIS_CUDA(cudaStreamSynchronize(c->stream));
@@ -282,6 +317,10 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
     else if (k == "trsv_variant") c->opt_trsv_variant = value;
     else if (k == "trsv_debug") c->opt_trsv_debug = value;
+    else if (k == "vector_cache") {
+        c->opt_vector_cache = value;
+        if (!value) vector_cache_release(c);
+    }
     else if (k == "trsv_gates") c->opt_trsv_gates = value;
     else if (k == "trsv_sleep1") c->opt_trsv_sleep[0] = value;
     else if (k == "trsv_sleep2") c->opt_trsv_sleep[1] = value;
@@ -308,7 +347,16 @@ extern "C" int bis_vector_alloc(bis_context *c, int64_t n, double **v) {
     BIS_CUDA(cudaSetDevice(c->device));
     // +2: the x windows of SpMV variant 3 are copied in 16-byte units and may overrun an odd length
     size_t bytes = sizeof(double) * ((size_t)(n > 0 ? n : 1) + 2);
-    BIS_CUDA(cudaMalloc(v, bytes));
+    *v = nullptr;
+    for (size_t i = c->vec_cache.size(); i-- > 0;)
+        if (c->vec_cache[i].first == bytes) {
+            *v = static_cast<double *>(c->vec_cache[i].second);
+            c->vec_cache.erase(c->vec_cache.begin() + (long)i);
+            c->vec_cache_bytes -= bytes;
+            break;
+        }
+    if (!*v) BIS_CUDA(bis_cuda_malloc(v, bytes));
+    c->vec_bytes[*v] = bytes;
     BIS_CUDA(cudaMemsetAsync(*v, 0, bytes, c->stream));
     return 0;
 }
@@ -317,6 +365,16 @@ extern "C" int bis_vector_free(bis_context *c, double *v) {
     BIS_REQUIRE(c, "null context");
     if (!v) return 0;
     BIS_CUDA(cudaStreamSynchronize(c->stream));
+    auto it = c->vec_bytes.find(v);
+    if (it != c->vec_bytes.end()) {
+        const size_t bytes = it->second;
+        c->vec_bytes.erase(it);
+        if (c->opt_vector_cache && c->vec_cache_bytes + bytes <= ((size_t)48 << 30) && c->vec_cache.size() < 256) {
+            c->vec_cache.emplace_back(bytes, v);
+            c->vec_cache_bytes += bytes;
+            return 0;
+        }
+    }
     BIS_CUDA(cudaFree(v));
     return 0;
 }

@@ -171,7 +171,7 @@ static int peer_map_try(bis_context *c, void *mine, void **out, int *ok) {
     if (!good) { cudaGetLastError(); memset(&hmine, 0, sizeof hmine); }
     unsigned char *d_h = nullptr;
     const size_t hb = sizeof(cudaIpcMemHandle_t);
-    BIS_CUDA(cudaMalloc(&d_h, hb * (size_t)(P + 1)));
+    BIS_CUDA(bis_cuda_malloc(&d_h, hb * (size_t)(P + 1)));
     BIS_CUDA(cudaMemcpyAsync(d_h + hb * P, &hmine, hb, cudaMemcpyHostToDevice, st));
     BIS_NCCL(ncclAllGather(d_h + hb * P, d_h, hb, ncclUint8, c->comm, st));
     std::vector<cudaIpcMemHandle_t> all(P);
@@ -194,7 +194,7 @@ static int peer_map_try(bis_context *c, void *mine, void **out, int *ok) {
     }
     // agree: the link is used only if it is up everywhere
     int *d_ok = nullptr;
-    BIS_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+    BIS_CUDA(bis_cuda_malloc(&d_ok, sizeof(int)));
     BIS_CUDA(cudaMemcpyAsync(d_ok, &good, sizeof(int), cudaMemcpyHostToDevice, st));
     BIS_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, st));
     int all_good = 0;
@@ -222,9 +222,9 @@ int bis_peer_link_setup(bis_context *c) {
     if (c->nranks <= 1 || c->nranks > BIS_MAX_PEERS) return 0;
     const char *env = getenv("BIS_P2P");
     if (env && env[0] == '0') return 0;   // must be set on every rank alike
-    BIS_CUDA(cudaMalloc(&c->d_bank, BIS_BANK_BYTES));
+    BIS_CUDA(bis_cuda_malloc(&c->d_bank, BIS_BANK_BYTES));
     BIS_CUDA(cudaMemset(c->d_bank, 0, BIS_BANK_BYTES));
-    BIS_CUDA(cudaMalloc(&c->d_pack_ticket, sizeof(unsigned int)));
+    BIS_CUDA(bis_cuda_malloc(&c->d_pack_ticket, sizeof(unsigned int)));
     BIS_CUDA(cudaMemset(c->d_pack_ticket, 0, sizeof(unsigned int)));
     BIS_CUDA(cudaDeviceSynchronize());   // banks are zero before the allgather below lets anyone write
     void *banks[BIS_MAX_PEERS] = {};
@@ -258,7 +258,7 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
 
     // (a) who owns what: allgather {row_begin, n_rows, nnz}
     int64_t *d_meta = nullptr;
-    BIS_CUDA(cudaMalloc(&d_meta, sizeof(int64_t) * 3 * (size_t)(P + 1)));
+    BIS_CUDA(bis_cuda_malloc(&d_meta, sizeof(int64_t) * 3 * (size_t)(P + 1)));
     int64_t mine[3] = {A->row_begin, A->n_rows, A->nnz};
     BIS_CUDA(cudaMemcpyAsync(d_meta + 3 * P, mine, sizeof mine, cudaMemcpyHostToDevice, st));
     BIS_NCCL(ncclAllGather(d_meta + 3 * P, d_meta, 3, ncclInt64, c->comm, st));
@@ -286,7 +286,7 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
     // upper bound on candidates is nnz; collect in chunks to bound the scratch
     const int64_t chunk = 1 << 26;
     std::vector<int> ghost_h;
-    BIS_CUDA(cudaMalloc(&d_tmp, sizeof(int) * (size_t)std::min<int64_t>(std::max<int64_t>(A->nnz, 1), chunk)));
+    BIS_CUDA(bis_cuda_malloc(&d_tmp, sizeof(int) * (size_t)std::min<int64_t>(std::max<int64_t>(A->nnz, 1), chunk)));
     for (int64_t off = 0; off < A->nnz; off += chunk) {
         const int64_t len = std::min<int64_t>(chunk, A->nnz - off);
         int *e = thrust::copy_if(pol, A->d_col + off, A->d_col + off + len, d_tmp, OutsideRange{lo, hi});
@@ -304,12 +304,12 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
     ghost_h.erase(std::unique(ghost_h.begin(), ghost_h.end()), ghost_h.end());
     HaloPlan &h = A->halo;
     h.n_ghost = (int64_t)ghost_h.size();
-    BIS_CUDA(cudaMalloc(&h.d_ghost_global, sizeof(int) * std::max<size_t>(ghost_h.size(), 1)));
+    BIS_CUDA(bis_cuda_malloc(&h.d_ghost_global, sizeof(int) * std::max<size_t>(ghost_h.size(), 1)));
     h.ghost_stride = (int64_t)((ghost_h.size() + 2 + 15) & ~(size_t)15);
     {
         size_t bytes = sizeof(double) * 2 * (size_t)h.ghost_stride;
         bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
-        BIS_CUDA(cudaMalloc(&h.d_ghost, bytes));
+        BIS_CUDA(bis_cuda_malloc(&h.d_ghost, bytes));
         BIS_CUDA(cudaMemsetAsync(h.d_ghost, 0, bytes, st));
     }
     h.cur_ghost = h.d_ghost;
@@ -331,7 +331,7 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
 
     // (e) tell every owner how many of its rows we need: allgather the count rows
     int64_t *d_cnt = nullptr;
-    BIS_CUDA(cudaMalloc(&d_cnt, sizeof(int64_t) * (size_t)P * (P + 1)));
+    BIS_CUDA(bis_cuda_malloc(&d_cnt, sizeof(int64_t) * (size_t)P * (P + 1)));
     std::vector<int64_t> my_cnt(P);
     for (int p = 0; p < P; ++p) my_cnt[p] = h.recv_off[p + 1] - h.recv_off[p];
     BIS_CUDA(cudaMemcpyAsync(d_cnt + (size_t)P * P, my_cnt.data(), sizeof(int64_t) * P, cudaMemcpyHostToDevice, st));
@@ -343,8 +343,8 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
     h.send_off.assign(P + 1, 0);
     for (int q = 0; q < P; ++q) h.send_off[q + 1] = h.send_off[q] + all_cnt[(size_t)q * P + me];
     h.n_send = h.send_off[P];
-    BIS_CUDA(cudaMalloc(&h.d_send_idx, sizeof(int) * std::max<int64_t>(h.n_send, 1)));
-    BIS_CUDA(cudaMalloc(&h.d_sendbuf, sizeof(double) * std::max<int64_t>(h.n_send, 1)));
+    BIS_CUDA(bis_cuda_malloc(&h.d_send_idx, sizeof(int) * std::max<int64_t>(h.n_send, 1)));
+    BIS_CUDA(bis_cuda_malloc(&h.d_sendbuf, sizeof(double) * std::max<int64_t>(h.n_send, 1)));
 
     // (f) exchange the index lists (global ids), then make them local
     BIS_NCCL(ncclGroupStart());
@@ -363,7 +363,7 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
 
     // (g) rows that touch no ghost: [interior_begin, interior_end)
     unsigned long long *d_range = nullptr;
-    BIS_CUDA(cudaMalloc(&d_range, 2 * sizeof(unsigned long long)));
+    BIS_CUDA(bis_cuda_malloc(&d_range, 2 * sizeof(unsigned long long)));
     unsigned long long init[2] = {0ull, (unsigned long long)A->n_rows};
     BIS_CUDA(cudaMemcpyAsync(d_range, init, sizeof init, cudaMemcpyHostToDevice, st));
     const int n_low = (int)h.recv_off[me];
@@ -389,7 +389,7 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
         int ok = 0;
         BIS_CHECK(peer_map_try(c, h.d_ghost, pg, &ok));
         int64_t *d_ro = nullptr;
-        BIS_CUDA(cudaMalloc(&d_ro, sizeof(int64_t) * (size_t)(P + 1) * (P + 2)));
+        BIS_CUDA(bis_cuda_malloc(&d_ro, sizeof(int64_t) * (size_t)(P + 1) * (P + 2)));
         std::vector<int64_t> mine_ro(P + 2);
         for (int p = 0; p <= P; ++p) mine_ro[p] = h.recv_off[p];
         mine_ro[P + 1] = ok ? h.ghost_stride : -1;
@@ -470,6 +470,44 @@ int bis_halo_exchange_begin(bis_context *c, const bis_matrix *A, const double *x
     }
     BIS_NCCL(ncclGroupEnd());
     BIS_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+    return 0;
+}
+
+int bis_halo_fuse_args(bis_context *c, const bis_matrix *A, HaloFuse *hf) {
+    const HaloPlan &h = A->halo;
+    BIS_REQUIRE(c->peer_on && c->opt_dist_p2p && h.peer_ready, "internal: fused halo exchange without the peer-memory link");
+    const unsigned long long e = ++c->halo_epoch;
+    const int par = (int)(e & 1ull);
+    h.cur_ghost = h.d_ghost + (size_t)par * h.ghost_stride;
+    HaloFuse &a = *hf;
+    a.n_dst = 0; a.n_src = 0; a.n_ranks = c->nranks; a.me = c->rank;
+    a.seg_off[0] = 0;
+    unsigned long long *mybank = reinterpret_cast<unsigned long long *>(c->d_bank);
+    for (int p = 0; p < BIS_MAX_PEERS; ++p) {
+        a.ack_out[p] = nullptr; a.dst[p] = nullptr; a.dst_flag[p] = nullptr; a.dst_rank[p] = 0; a.src_rank[p] = 0;
+    }
+    for (int p = 0; p < c->nranks; ++p) {
+        unsigned long long *pb = reinterpret_cast<unsigned long long *>(c->peer_bank[p]);
+        a.ack_out[p] = pb + BIS_BANK_HALO_ACK + c->rank;
+        if (p == c->rank) continue;
+        if (h.recv_off[p + 1] > h.recv_off[p]) a.src_rank[a.n_src++] = p;
+        const int64_t ns = h.send_off[p + 1] - h.send_off[p];
+        if (ns == 0) continue;
+        const int d = a.n_dst++;
+        a.dst_rank[d] = p;
+        a.seg_off[d] = h.send_off[p];
+        a.seg_off[d + 1] = h.send_off[p + 1];
+        a.dst[d] = h.peer_ghost[p] + (size_t)par * h.peer_stride[p] + h.peer_recv_off[p];
+        a.dst_flag[d] = pb + BIS_BANK_HALO_FLAG + c->rank;
+    }
+    for (int d = a.n_dst; d < BIS_MAX_PEERS; ++d) a.seg_off[d + 1] = a.seg_off[a.n_dst];
+    a.ack_in = mybank + BIS_BANK_HALO_ACK;
+    a.flag_in = mybank + BIS_BANK_HALO_FLAG;
+    a.send_idx = h.d_send_idx;
+    a.ticket = c->d_pack_ticket;
+    a.epoch = e;
+    a.errflag = c->d_errflag;
+    a.ghost_from = 0; a.tile_split2 = 0; a.tile_lo3 = 0;   // set by the SpMV driver
     return 0;
 }
 

@@ -31,7 +31,7 @@ namespace {
 constexpr int FB = 256;   // threads per block of the row-parallel kernels
 
 template <typename T> int dalloc(T **p, size_t count) {
-    BIS_CUDA(cudaMalloc(p, sizeof(T) * (count > 0 ? count : 1)));
+    BIS_CUDA(bis_cuda_malloc(p, sizeof(T) * (count > 0 ? count : 1)));
     return 0;
 }
 
@@ -426,6 +426,7 @@ extern "C" int bis_matrix_split_triangular(bis_context *c, const bis_matrix *A, 
     BIS_REQUIRE(c && A && L && U, "null argument");
     BIS_REQUIRE(!A->distributed && c->nranks == 1, "bis_matrix_split_triangular: single-GPU only");
     BIS_CUDA(cudaSetDevice(c->device));
+    bis_vector_cache_trim(c);
     bis_matrix *l = nullptr, *u = nullptr;
     if (A->rp_bytes == 8) BIS_CHECK(split_device<int64_t>(c, A, 0, nullptr, &l, &u));
     else BIS_CHECK(split_device<int32_t>(c, A, 0, nullptr, &l, &u));
@@ -445,6 +446,7 @@ extern "C" int bis_matrix_ilu0(bis_context *c, const bis_matrix *A, double pivot
     BIS_REQUIRE(c && A && L && U && U_D, "null argument");
     BIS_REQUIRE(!A->distributed && c->nranks == 1, "bis_matrix_ilu0: single-GPU only");
     BIS_CUDA(cudaSetDevice(c->device));
+    bis_vector_cache_trim(c);
     const int64_t n = A->n_rows;
     bis_matrix *l = nullptr, *u = nullptr;
     if (A->rp_bytes == 8) BIS_CHECK(split_device<int64_t>(c, A, 1, U_D, &l, &u));

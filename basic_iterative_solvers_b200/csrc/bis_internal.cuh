@@ -11,6 +11,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 // ---- error plumbing -------------------------------------------------------
@@ -137,6 +139,13 @@ struct bis_context {
     std::vector<void *> ipc_opened;                 // mappings to close
     int64_t launches = 0;
     // options
+    // freed vectors are kept for the next allocation of the same size (a solver allocates ~20 vectors of
+    // one length; cudaMalloc + cudaFree of a gigabyte each is milliseconds); emptied when memory runs short
+    std::vector<std::pair<size_t, void *>> vec_cache;
+    size_t vec_cache_bytes = 0;
+    std::unordered_map<void *, size_t> vec_bytes;   // live vectors of bis_vector_alloc
+    int opt_vector_cache = 1;
+    int opt_spmv_fused = 1;     // distributed SpMV over peer memory as ONE kernel (0: pack / interior / wait / strips launches)
     int opt_dist_p2p = 1;       // 0: NCCL transport even when the peer-memory link is up
     int opt_spmv_variant = 0;
     int opt_spmv_lanes = 0;
@@ -192,6 +201,24 @@ struct HaloPlan {
     bool peer_ready = false;
 };
 
+// Kernel arguments of the fused distributed SpMV (bis_spmv_win.cuh); filled by bis_halo_fuse_args (bis_dist.cu)
+struct HaloFuse {
+    int n_dst, n_src, n_ranks, me;
+    int dst_rank[BIS_MAX_PEERS], src_rank[BIS_MAX_PEERS];
+    int64_t seg_off[BIS_MAX_PEERS + 1];            // segments of the send list, one per destination
+    double *dst[BIS_MAX_PEERS];                    // where that segment lands in the destination's ghost copy
+    unsigned long long *dst_flag[BIS_MAX_PEERS];   // destination's bank: HALO_FLAG + me
+    unsigned long long *ack_out[BIS_MAX_PEERS];    // rank p's bank: HALO_ACK + me
+    const unsigned long long *ack_in;              // my bank: HALO_ACK
+    const unsigned long long *flag_in;             // my bank: HALO_FLAG
+    const int *send_idx;
+    unsigned int *ticket;
+    unsigned long long epoch;
+    int64_t ghost_from;                            // virtual tile index from which tiles read ghosts
+    int64_t tile_split2, tile_lo3;                 // third tile range: tile_lo3 + (v - tile_split2) for v >= tile_split2
+    int *errflag;
+};
+
 // Acceleration structure of SpMV variant 3 (bis_spmv_win.cuh), derived lazily from the CRS arrays.
 struct WinFormat {
     int state = 0;                 // 0 not built, 1 usable, -1 not representable (fall back)
@@ -231,6 +258,8 @@ int bis_reduce_finish(bis_context *ctx, int slot_a, int slot_b);
 RedArgs bis_red_args(bis_context *ctx, int slot_a, int slot_b);
 int bis_halo_exchange_begin(bis_context *ctx, const bis_matrix *A, const double *x);
 int bis_halo_exchange_end(bis_context *ctx, const bis_matrix *A);
+// starts a halo exchange that the SpMV kernel itself performs: advances the epoch, selects the ghost copy
+int bis_halo_fuse_args(bis_context *ctx, const bis_matrix *A, HaloFuse *hf);
 int bis_peer_link_setup(bis_context *ctx);
 void bis_peer_link_teardown(bis_context *ctx);
 // maps a cudaMalloc'ed buffer of every rank into this process (collective); out[p] for p == rank is `mine`
@@ -243,6 +272,19 @@ int bis_matrix_stats(bis_context *ctx, bis_matrix *A);
 int bis_spmv_prepare(bis_context *ctx, const bis_matrix *A);
 int bis_prof_begin(bis_context *ctx, int tag);
 int bis_prof_end(bis_context *ctx, int tag);
+
+// cudaMalloc that empties the contexts' vector caches and retries once when the device is out of memory
+void bis_vector_cache_release_all();
+void bis_vector_cache_trim(bis_context *ctx);
+template <typename T> static inline cudaError_t bis_cuda_malloc(T **p, size_t bytes) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        bis_vector_cache_release_all();
+        e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+    }
+    return e;
+}
 
 static inline int bis_blocks_for(int64_t n, int per_block, int cap) {
     int64_t b = (n + per_block - 1) / per_block;

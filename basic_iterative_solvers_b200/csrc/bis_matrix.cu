@@ -17,7 +17,7 @@
 namespace {
 
 template <typename T> int dev_alloc(T **p, size_t count) {
-    BIS_CUDA(cudaMalloc(p, sizeof(T) * (count > 0 ? count : 1)));
+    BIS_CUDA(bis_cuda_malloc(p, sizeof(T) * (count > 0 ? count : 1)));
     return 0;
 }
 
@@ -56,6 +56,7 @@ int upload_common(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz, c
                 (long long)rp[n_rows], (long long)nnz);
     BIS_REQUIRE(n_rows < INT32_MAX && n_cols < INT32_MAX, "matrix upload: more than 2^31-1 rows");
     BIS_CUDA(cudaSetDevice(c->device));
+    bis_vector_cache_trim(c);
     bis_matrix *A = new bis_matrix;
     A->n_rows = n_rows;
     A->n_cols = n_cols;
@@ -320,6 +321,7 @@ extern "C" int bis_matrix_generate_hpcg(bis_context *c, int nx, int ny, int nz, 
     const int64_t n = (int64_t)nx * ny * nz;
     BIS_REQUIRE(n < INT32_MAX, "bis_matrix_generate_hpcg: %lld rows exceed 32-bit column ids", (long long)n);
     BIS_CUDA(cudaSetDevice(c->device));
+    bis_vector_cache_trim(c);
     int64_t rb = 0, re = n;
     slab(n, c->rank, c->nranks, (int64_t)nx * ny, &rb, &re);
     const int64_t n_local = re - rb;
@@ -362,6 +364,7 @@ extern "C" int bis_matrix_generate_anderson(bis_context *c, int lx, int ly, int 
     const int64_t n = (int64_t)lx * ly * lz;
     BIS_REQUIRE(n < INT32_MAX / 8, "bis_matrix_generate_anderson: lattice too large for 32-bit ids");
     BIS_CUDA(cudaSetDevice(c->device));
+    bis_vector_cache_trim(c);
     int64_t rb = 0, re = n;
     slab(n, c->rank, c->nranks, (int64_t)lx * ly, &rb, &re);
     const int64_t n_local = re - rb;

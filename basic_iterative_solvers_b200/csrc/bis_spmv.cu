@@ -306,13 +306,13 @@ int win_build(bis_context *c, const bis_matrix *A) {
     while (sort_cap < R * A->max_row) sort_cap <<= 1;
     const int64_t n_tiles = (A->n_rows + R - 1) / R;
     int *d_status = nullptr;
-    BIS_CUDA(cudaMalloc(&d_status, 2 * sizeof(int)));
+    BIS_CUDA(bis_cuda_malloc(&d_status, 2 * sizeof(int)));
     BIS_CUDA(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), c->stream));
-    BIS_CUDA(cudaMalloc(&w.d_seg_start, sizeof(int) * (size_t)n_tiles * WIN_MAXSEG));
-    BIS_CUDA(cudaMalloc(&w.d_seg_len, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
-    BIS_CUDA(cudaMalloc(&w.d_seg_off, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
-    BIS_CUDA(cudaMalloc(&w.d_nseg, sizeof(int) * (size_t)n_tiles));
-    BIS_CUDA(cudaMalloc(&w.d_lidx, sizeof(unsigned short) * ((size_t)A->nnz + 8)));
+    BIS_CUDA(bis_cuda_malloc(&w.d_seg_start, sizeof(int) * (size_t)n_tiles * WIN_MAXSEG));
+    BIS_CUDA(bis_cuda_malloc(&w.d_seg_len, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
+    BIS_CUDA(bis_cuda_malloc(&w.d_seg_off, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
+    BIS_CUDA(bis_cuda_malloc(&w.d_nseg, sizeof(int) * (size_t)n_tiles));
+    BIS_CUDA(bis_cuda_malloc(&w.d_lidx, sizeof(unsigned short) * ((size_t)A->nnz + 8)));
     WinBuildArgs a;
     a.rp = A->d_rp; a.col = A->d_col; a.n_rows = A->n_rows; a.n_owned = A->n_cols; a.R = R; a.sort_cap = sort_cap;
     a.seg_start = w.d_seg_start; a.seg_len = w.d_seg_len; a.seg_off = w.d_seg_off; a.nseg = w.d_nseg;
@@ -397,7 +397,50 @@ int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const doub
     in.debug = c->opt_spmv_debug;
     *nb = (int)grid;
     if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + (int)grid;
-    kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra);
+    kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra, NoHaloFuse{});
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}
+
+// The whole distributed SpMV in one launch: pack + publish, interior tiles, halo wait, boundary tiles,
+// fused reduction and its sum over ranks (bis_spmv_win.cuh, DIST = true).
+template <typename RP, class Epi>
+int launch_win_fused(bis_context *c, const bis_matrix *A, const WinPlan &p, const double *x, const Epi &epi,
+                     RedArgs &ra) {
+    auto kern = spmv_win_kernel<RP, Epi, true>;
+    static size_t configured = 0;
+    if (configured < p.smem_bytes) {
+        BIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        configured = p.smem_bytes;
+    }
+    const WinFormat &w = A->win;
+    const int threads = w.R * p.nstage + 32;
+    int occ = 1;
+    BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, p.smem_bytes));
+    if (occ < 1) occ = 1;
+    const int64_t n_tiles = w.n_tiles;
+    int64_t grid = (int64_t)c->sm_count * occ;   // all CTAs are resident: the pack phase counts them in
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    HaloFuse hf;
+    BIS_CHECK(bis_halo_fuse_args(c, A, &hf));
+    // tile order: interior [ib, ie), then the low strip [0, ib), then the high strip [ie, n_tiles)
+    int64_t ib = (A->halo.interior_begin + w.R - 1) / w.R, ie = A->halo.interior_end / w.R;
+    if (A->halo.n_ghost == 0) { ib = 0; ie = n_tiles; }
+    if (ie < ib) ie = ib;
+    SpmvWinIn in;
+    in.rp = A->d_rp; in.val = A->d_val; in.lidx = w.d_lidx;
+    in.seg_start = w.d_seg_start; in.seg_len = w.d_seg_len; in.seg_off = w.d_seg_off; in.nseg = w.d_nseg;
+    in.x = x; in.ghost = A->halo.cur_ghost; in.n_rows = A->n_rows;
+    in.tile_lo = ib; in.tile_cnt = n_tiles; in.tile_split = ie - ib; in.tile_lo2 = 0;
+    hf.tile_split2 = (ie - ib) + ib; hf.tile_lo3 = ie;
+    hf.ghost_from = ie - ib;
+    in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.stage_bytes = p.stage_bytes;
+    in.debug = c->opt_spmv_debug;
+    ra.finalize = 1;
+    ra.block_offset = 0;
+    if (Epi::NRED > 0) ra.total_blocks = (int)grid;
+    kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra, hf);
     BIS_LAUNCH_CHECK(c);
     return 0;
 }
@@ -427,6 +470,13 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     BIS_REQUIRE(use_win || c->opt_spmv_variant != 3,
                 "spmv_variant=3 forced, but the matrix has no window representation or x is not 16-byte aligned");
     BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPMV));
+    if (use_win && A->distributed && c->opt_spmv_fused && c->peer_on && c->opt_dist_p2p && A->halo.peer_ready) {
+        if (A->rp_bytes == 8) BIS_CHECK((launch_win_fused<int64_t, Epi>(c, A, wplan, x, epi, ra)));
+        else BIS_CHECK((launch_win_fused<int32_t, Epi>(c, A, wplan, x, epi, ra)));
+        BIS_CHECK(bis_prof_end(c, BIS_PROF_SPMV));
+        if (Epi::NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));
+        return 0;
+    }
     // work list: row ranges (variants 1, 2) or tile ranges (variant 3); `ghost` = needs the halo
     Segment seg[3];
     int nseg = 0;

@@ -20,6 +20,8 @@
 // more than WIN_MAXSEG windows (unstructured sparsity) keep using variant 2.
 #pragma once
 
+#include <type_traits>
+
 #include "bis_device.cuh"
 #include "bis_spmv_tma.cuh"
 
@@ -167,6 +169,14 @@ __global__ void __launch_bounds__(WIN_BUILD_THREADS) win_build_kernel(WinBuildAr
 }
 
 // ---- SpMV ----------------------------------------------------------------------------------------
+// Distributed SpMV as ONE kernel (peer-memory transport, bis_dist.cu): every CTA first packs its share
+// of the boundary values of x and stores them straight into the neighbours' ghost buffers (the CTA
+// that finishes last publishes the exchange's epoch in their banks), then the grid sweeps the interior
+// tiles, and a CTA's producer warp looks at the senders' flags only when it reaches its first tile that
+// reads ghosts -- by then the values have long arrived.  The fused dot product and its sum over ranks
+// (block_reduce_finish) close the same kernel.
+struct NoHaloFuse {};
+
 struct SpmvWinIn {
     const void *rp;
     const double *val;
@@ -191,8 +201,9 @@ struct SpmvWinIn {
 // stage layout: [val cap*8][xwin xcap*8][rp (R+4)*8][lidx cap*2], every part 16-byte aligned
 constexpr int WIN_MAX_THREADS = 320;   // consumer groups (R x nstage) + the producer warp
 
-template <typename RP, class Epi>
-__global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra) {
+template <typename RP, class Epi, bool DIST = false>
+__global__ void __launch_bounds__(WIN_MAX_THREADS, 2)
+spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIST, HaloFuse, NoHaloFuse>::type hf) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);            // [MAX_STAGES]
     uint64_t *empty = full + tma::MAX_STAGES;                           // [MAX_STAGES]
@@ -223,6 +234,42 @@ __global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn 
     }
     __syncthreads();
 
+    if constexpr (DIST) {
+        // pack + publish (the protocol of pack_peer_kernel, bis_dist.cu)
+        __shared__ bool s_last;
+        const int t = threadIdx.x;
+        if (blockIdx.x == 0 && t < hf.n_ranks && t != hf.me)
+            *reinterpret_cast<volatile unsigned long long *>(hf.ack_out[t]) = hf.epoch;
+        if (t < hf.n_dst && hf.epoch >= 2) {
+            const volatile unsigned long long *ack = hf.ack_in + hf.dst_rank[t];
+            const unsigned long long t0 = bis_globaltimer();
+            while (*ack + 1 < hf.epoch) {
+                if (bis_globaltimer() - t0 > BIS_PEER_TIMEOUT_NS) {
+                    atomicExch(hf.errflag, 30 + hf.dst_rank[t]);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        const int64_t n_send = hf.seg_off[hf.n_dst];
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < n_send; i += (int64_t)gridDim.x * blockDim.x) {
+            int d = 0;
+            while (i >= hf.seg_off[d + 1]) ++d;
+            hf.dst[d][i - hf.seg_off[d]] = in.x[hf.send_idx[i]];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) s_last = (atomicAdd(hf.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            if (t < hf.n_dst) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long *>(hf.dst_flag[t]) = hf.epoch;
+            }
+            if (t == 0) *hf.ticket = 0u;
+        }
+    }
+
     if (producer) {
         const RP *__restrict__ rp = static_cast<const RP *>(in.rp);
         const uint64_t pol_stream = tma::policy_evict_first();
@@ -246,6 +293,9 @@ __global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn 
         auto tile_rows = [&](int64_t j, int64_t &tile, int64_t &r0, int64_t &r1) {
             const int64_t v = blockIdx.x + j * gridDim.x;
             tile = v < in.tile_split ? in.tile_lo + v : in.tile_lo2 + (v - in.tile_split);
+            if constexpr (DIST) {
+                if (v >= hf.tile_split2) tile = hf.tile_lo3 + (v - hf.tile_split2);
+            }
             r0 = tile * R;
             r1 = r0 + R;
             if (r1 > in.n_rows) r1 = in.n_rows;
@@ -270,7 +320,27 @@ __global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn 
                 d.off = in.seg_off[q];
             }
         };
+        [[maybe_unused]] bool halo_seen = false;
         auto issue = [&](int64_t j, const Desc &d) {
+            if constexpr (DIST) {
+                // first tile of this CTA that reads ghosts: the senders' values must have landed
+                if (!halo_seen && (int64_t)blockIdx.x + j * gridDim.x >= hf.ghost_from) {
+                    for (int q = 0; q < hf.n_src; ++q) {
+                        const volatile unsigned long long *f = hf.flag_in + hf.src_rank[q];
+                        const unsigned long long t0 = bis_globaltimer();
+                        while (*f < hf.epoch) {
+                            if (bis_globaltimer() - t0 > BIS_PEER_TIMEOUT_NS) {
+                                atomicExch(hf.errflag, 40 + hf.src_rank[q]);
+                                break;
+                            }
+                        }
+                    }
+                    __threadfence_system();
+                    // the bulk copies below read the ghosts through the async proxy
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    halo_seen = true;
+                }
+            }
             const int st = (int)(j % in.nstage);
             int64_t tile, r0, r1;
             tile_rows(j, tile, r0, r1);
@@ -326,7 +396,10 @@ __global__ void __launch_bounds__(WIN_MAX_THREADS, 2) spmv_win_kernel(SpmvWinIn 
         for (int64_t j = group; j < my_tiles; j += in.nstage) {
             const int st = group;
             const int64_t v = blockIdx.x + j * gridDim.x;
-            const int64_t tile = v < in.tile_split ? in.tile_lo + v : in.tile_lo2 + (v - in.tile_split);
+            int64_t tile = v < in.tile_split ? in.tile_lo + v : in.tile_lo2 + (v - in.tile_split);
+            if constexpr (DIST) {
+                if (v >= hf.tile_split2) tile = hf.tile_lo3 + (v - hf.tile_split2);
+            }
             const int64_t row = tile * R + tid_g;
             const unsigned char *sb = stages + (size_t)st * in.stage_bytes;
             const double *__restrict__ sval = reinterpret_cast<const double *>(sb);

@@ -337,7 +337,7 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.dbg = nullptr;
     a.poll_ns = c->opt_trsv_poll_ns > 0 ? (unsigned int)c->opt_trsv_poll_ns : (c->opt_trsv_poll_ns < 0 ? 0u : 20u);   // < 0: spin without sleeping
     const char *dbg_file = c->opt_trsv_debug ? getenv("BIS_TRSV_DEBUG_FILE") : nullptr;
-    if (dbg_file) BIS_CUDA(cudaMalloc(&a.dbg, sizeof(unsigned long long) * 4 * (size_t)lv.n_slots));
+    if (dbg_file) BIS_CUDA(bis_cuda_malloc(&a.dbg, sizeof(unsigned long long) * 4 * (size_t)lv.n_slots));
     a.x = x;
     a.D = D;
     a.b = b;

@@ -214,7 +214,10 @@ class BenchSession:
         if self.lib.bis_host_bench_e2e(self.h, steps, b_ptr, x0_ptr, x_out_ptr, out, info) != 0:
             raise capi.BisError(_err())
         return {"wall_ms": out[0], "iters": int(out[1]), "launches": int(out[2]), "res_last": out[3],
-                "res0": out[4], "res_true": out[5], **self._info(info)}
+                "res0": out[4], "res_true": out[5],
+                "breakdown_ms": {"allocate_init_upload": out[6], "r0_and_factor": out[7],
+                                 "iterations": info[6] / 1e3, "x_star_download": info[7] / 1e3},
+                **self._info(info)}
 
     def prepare(self, warmup: int):
         info = (C.c_int64 * 8)()

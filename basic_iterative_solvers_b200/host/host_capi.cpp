@@ -239,11 +239,19 @@ int bis_host_bench_e2e(void *h, int steps, const double *b_host, const double *x
         BIS_OK(bis_context_info(s->dev, i0));
         Stopwatch w;
         w.start();
+        s->timers = Timers();
         preprocessing(&s->args, solver, &s->timers, A, std::move(dA), b_host, x0_host);
+        const double t_pre = w.check();
         solve(&s->args, solver, &s->timers);
+        const double t_solve = w.check();
         if (x_star_host) BIS_OK(bis_vector_download(s->dev, x_star_host, solver->x_star, solver->N));
         BIS_OK(bis_context_synchronize(s->dev));
         out[0] = w.check() * 1e3;
+        // breakdown of the wall time (ms): allocate + init + uploads | r0 and factor step | loop | x_star download
+        out[6] = s->timers.preprocessing_init_time.get_wtime() * 1e3;
+        out[7] = (t_pre - s->timers.preprocessing_init_time.get_wtime()) * 1e3;
+        info[6] = (int64_t)((t_solve - t_pre) * 1e6);
+        info[7] = (int64_t)((w.check() - t_solve) * 1e6);
         BIS_OK(bis_context_info(s->dev, i1));
         out[1] = solver->iter_count;
         out[2] = (double)(i1[3] - i0[3]);

@@ -351,7 +351,7 @@ def main():
                 "h2d_bytes_per_step": 16 * n_local / K, "d2h_bytes_per_step": 8 * n_local / K + 8,
                 "note": "preprocessing (allocate, upload b/x0 from pinned host memory, r0) + K harness "
                         "iterations with the residual norm read back each + x_star download, / K",
-                "x_star_check": e2e_check},
+                "x_star_check": e2e_check, "breakdown_ms_rank0": e["breakdown_ms"]},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "spmv_win_kernel<long, EpiDot> (y = A p fused with (y,p); val, 16-bit local column ids, row_ptr slice and x windows by TMA)",

@@ -46,6 +46,19 @@ if peer:
         ok &= err <= 1e-10
     ctx.set_option("dist_p2p", 1)
     dist.barrier()
+    # peer-memory transport with separate pack / interior / wait / strip launches instead of the fused kernel
+    ctx.set_option("spmv_fused", 0)
+    dist.barrier()
+    for (method, pre), r in list(results.items()):
+        q = host.solve(ctx, method, pre, matrix_name=name, want_x=False, max_iters=300)
+        k = min(q.history.size, r.history.size)
+        err = float(np.max(np.abs(q.history[:k] - r.history[:k])) / r.history[0])
+        if rank == 0:
+            print(f"{name} -{method} -p {pre}: fused SpMV kernel vs separate launches: its {r.iter_count} vs {q.iter_count}, "
+                  f"max |dr|/r0 = {err:.2e}", flush=True)
+        ok &= err <= 1e-10
+    ctx.set_option("spmv_fused", 1)
+    dist.barrier()
 if rank == 0:
     with capi.Context(local) as solo:
         for (method, pre), r in results.items():
