@@ -183,15 +183,15 @@ extern "C" int bis_cg_update(bis_context *c, int precond, int64_t n, double *x_n
     const EwIn<4> in{{x_old, p_old, r_old, Ap}};
     if (precond == BIS_PRECOND_NONE) {
         REQ_SLOT(slot_rz_new);
-        // z_new = r_new (copy_vector, kernels.hpp:396-399); (r,z) == (r,r)
-        BIS_CHECK((launch_ew2<1, 4>(c, n, prep, in, [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+        // z_new = r_new (copy_vector, kernels.hpp:396-399); (r,z) == (r,r): the same sum lands in both slots
+        return launch_ew2<2, 4>(c, n, prep, in, [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
             x_new[i] = fma(alpha, v[1], v[0]);
             double r = fma(-alpha, v[3], v[2]);
             r_new[i] = r;
             z_new[i] = r;
             acc[0] = fma(r, r, acc[0]);
-        }, slot_rr)));
-        return bis_scalar_copy(c, slot_rz_new, slot_rr);
+            acc[1] = acc[0];
+        }, slot_rr, slot_rz_new);
     }
     if (precond == BIS_PRECOND_JACOBI) {
         REQ_SLOT(slot_rz_new);

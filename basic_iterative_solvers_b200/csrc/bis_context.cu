@@ -2,6 +2,7 @@
 // C-ABI: include/bis_b200.h ("context", "vectors", "device scalars").
 #include "bis_internal.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 static thread_local char g_err[1024] = "";
@@ -78,6 +79,8 @@ static int context_init(bis_context *c, int device) {
     BIS_CUDA(bis_cuda_malloc(&c->d_errflag, sizeof(int)));
     BIS_CUDA(cudaMemset(c->d_errflag, 0, sizeof(int)));
     BIS_CUDA(cudaDeviceSynchronize());
+    // experiment switches (must be set alike on every rank)
+    if (const char *e = getenv("BIS_SPMV_FUSED")) c->opt_spmv_fused = atoi(e);
     return 0;
 }
 

@@ -21,6 +21,8 @@ class BiCGSTABSolver : public Solver {
     double *residual_old = nullptr, *residual_new = nullptr;
     double rho_old = 0.0, rho_new = 0.0;   // host mirrors (diagnostics only)
 
+    int s_rho_old = S_RHO_OLD, s_rho_new = S_RHO_NEW;   // device scalar slots, swapped in exchange()
+
     BiCGSTABSolver(const Args *cli_args, Interface *device) : Solver(cli_args, device) {}
 
     void allocate_structs(const int64_t n) override {
@@ -41,7 +43,7 @@ class BiCGSTABSolver : public Solver {
         residual_norm = std::sqrt(scalar(dev, S_RR));
         precondition(residual, residual);   // in place: residual_0 is the PRECONDITIONED r0
         copy_vector(dev, p_old, residual, N);
-        BIS_OK(bis_dot_to_slot(dev, residual_old, residual, N, S_RHO_OLD));
+        BIS_OK(bis_dot_to_slot(dev, residual_old, residual, N, s_rho_old));
         Solver::init_residual();
         if (fused_precond()) precondition(y, p_old);   // y of the first iteration (:24-27)
     }
@@ -49,20 +51,20 @@ class BiCGSTABSolver : public Solver {
         const int pc = static_cast<int>(preconditioner);
         if (!fused_precond()) precondition(y, p_old);
         BIS_OK(bis_spmv_dot(dev, dA->handle, y, v, residual_0, S_R0V, -1));
-        BIS_OK(bis_bicgstab_s(dev, pc, N, s, s_tmp, residual_old, v, A_D, S_RHO_OLD, S_R0V));
+        BIS_OK(bis_bicgstab_s(dev, pc, N, s, s_tmp, residual_old, v, A_D, s_rho_old, S_R0V));
         if (!fused_precond()) precondition(s_tmp, s);
         BIS_OK(bis_spmv_dot(dev, dA->handle, s_tmp, z, s, S_ZS, S_ZZ));
         BIS_OK(bis_bicgstab_xr(dev, N, nullptr, x_new, x_old, y, s_tmp, residual_new, s, z, residual_0,
-                               S_RHO_OLD, S_R0V, S_ZS, S_ZZ, S_RHO_NEW, S_RR_BI));
+                               s_rho_old, S_R0V, S_ZS, S_ZZ, s_rho_new, S_RR_BI));
         BIS_OK(bis_bicgstab_p(dev, pc, N, nullptr, p_new, p_old, v, residual_new,
-                              fused_precond() ? y : nullptr, A_D, S_RHO_NEW, S_RHO_OLD, S_R0V, S_ZS, S_ZZ));
+                              fused_precond() ? y : nullptr, A_D, s_rho_new, s_rho_old, S_R0V, S_ZS, S_ZZ));
         std::swap(residual, residual_new);   // bicgstab.hpp:177
     }
     void exchange() override {
         std::swap(p_old, p_new);
         std::swap(residual_old, residual);   // bicgstab.hpp:183
         std::swap(x_old, x_new);
-        BIS_OK(bis_scalar_copy(dev, S_RHO_OLD, S_RHO_NEW));   // std::swap(rho_old, rho_new)
+        std::swap(s_rho_old, s_rho_new);   // std::swap(rho_old, rho_new), bicgstab.hpp:185: the slots trade places
     }
     void save_x_star() override {
         std::swap(x_old, x_star);

@@ -18,22 +18,24 @@ inline void cg_separate_iteration(Interface *dev, const PrecondType precondition
                                   double *A_D, double *A_D_inv, double *L_D, double *U_D,
                                   double *x_new, double *x_old, double *tmp, double *work,
                                   double *p_new, double *p_old, double *r_new, double *r_old,
-                                  double *z_new, double *z_old) {
+                                  double *z_new, double *z_old, const int s_rz, const int s_rz_new) {
     (void)z_old;
     BIS_OK(bis_spmv_dot(dev, A->handle, p_old, tmp, p_old, S_PAP, -1));
     BIS_OK(bis_cg_update(dev, static_cast<int>(preconditioner), N, x_new, x_old, p_old, r_new, r_old,
-                         tmp, z_new, A_D, S_RZ, S_PAP, S_RR, S_RZ_NEW));
+                         tmp, z_new, A_D, s_rz, S_PAP, S_RR, s_rz_new));
     if (preconditioner != PrecondType::None && preconditioner != PrecondType::Jacobi) {
         apply_preconditioner(dev, preconditioner, N, L, U, A_D, A_D_inv, L_D, U_D, z_new, r_new, tmp, work);
-        BIS_OK(bis_dot_to_slot(dev, r_new, z_new, N, S_RZ_NEW));
+        BIS_OK(bis_dot_to_slot(dev, r_new, z_new, N, s_rz_new));
     }
-    BIS_OK(bis_cg_direction(dev, N, p_new, z_new, p_old, S_RZ_NEW, S_RZ));
+    BIS_OK(bis_cg_direction(dev, N, p_new, z_new, p_old, s_rz_new, s_rz));
 }
 
 class ConjugateGradientSolver : public Solver {
   public:
     double *x_new = nullptr, *x_old = nullptr, *p_old = nullptr, *p_new = nullptr;
     double *z_old = nullptr, *z_new = nullptr, *residual_old = nullptr, *residual_new = nullptr;
+    // device scalar slots of (r_old,z_old) and (r_new,z_new): swapped in exchange() like the vectors
+    int s_rz = S_RZ, s_rz_new = S_RZ_NEW;
 
     ConjugateGradientSolver(const Args *cli_args, Interface *device) : Solver(cli_args, device) {}
 
@@ -54,21 +56,21 @@ class ConjugateGradientSolver : public Solver {
         precondition(z_old, residual);
         copy_vector(dev, p_old, z_old, N);
         copy_vector(dev, residual_old, residual, N);
-        BIS_OK(bis_dot_to_slot(dev, residual_old, z_old, N, S_RZ));   // first (r_old, z_old)
+        BIS_OK(bis_dot_to_slot(dev, residual_old, z_old, N, s_rz));   // first (r_old, z_old)
         residual_norm = std::sqrt(scalar(dev, S_RR));
         Solver::init_residual();
     }
     void iterate(Timers *) override {
         cg_separate_iteration(dev, preconditioner, N, dA.get(), dL_strict.get(), dU_strict.get(), A_D,
                               A_D_inv, L_D, U_D, x_new, x_old, tmp, work, p_new, p_old, residual_new,
-                              residual_old, z_new, z_old);
+                              residual_old, z_new, z_old, s_rz, s_rz_new);
     }
     void exchange() override {
         std::swap(p_old, p_new);
         std::swap(z_old, z_new);
         std::swap(residual_old, residual_new);
         std::swap(x_old, x_new);
-        BIS_OK(bis_scalar_copy(dev, S_RZ, S_RZ_NEW));   // (r_old,z_old) of the next iteration
+        std::swap(s_rz, s_rz_new);   // (r_old,z_old) of the next iteration is this one's (r_new,z_new)
     }
     void save_x_star() override {
         std::swap(x_old, x_star);
