@@ -8,8 +8,8 @@ reference: iterate, residual-norm sample read back by the host, pointer exchange
 Jacobi-preconditioned CG (`-cg -p j`) on the HPCG-n 27-point matrix (default n = 512:
 134 M rows, 3.6 G nonzeros, device-generated, 64-bit row_ptr), b = 1, x0 = 0.1.
 For N > 1 (launched by torchrun, one rank per GPU) the rows are partitioned into N z-slabs
-(strong scaling: the global problem is fixed); NCCL carries the halo planes and the dot-product
-allreduces.  `value` is milliseconds per iteration with all state resident in HBM (CUDA events,
+(strong scaling: the global problem is fixed; `--weak` keeps an HPCG-n slab per GPU instead); halo planes and
+dot-product sums move over peer memory from inside the kernels (NCCL sets the link up and is the fallback).  `value` is milliseconds per iteration with all state resident in HBM (CUDA events,
 max over ranks); `e2e` is the same metric through the host stack from HOST buffers (b, x0 uploaded,
 x_star downloaded, residual norm read back every iteration); `roofline` is the SpMV kernel
 (the dominant kernel) against the measured HBM peak; `cpu_baseline` is the unmodified reference
@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", dest="n", type=int, default=512, help="HPCG grid edge (BASELINE: 512)")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: every GPU keeps an HPCG-<grid> sized slab (global grid n x n x n*N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="HPCG edge of the CPU sample (0: auto)")
     args = ap.parse_args()
@@ -209,11 +211,15 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     n = args.n
-    workload = f"HPCG-{n} -cg -p j (27-point, {n**3} rows, {(3*n-2)**3} nnz, fp64 CRS, b=1, x0=0.1)"
-    config = {"workload": workload, "rows": n ** 3, "nnz": (3 * n - 2) ** 3,
+    nz = n * world if args.weak else n
+    n_rows_g, nnz_g = n * n * nz, (3 * n - 2) ** 2 * (3 * nz - 2)
+    scaling = "weak" if args.weak else "strong"
+    gname = f"HPCG-{n}-{n}-{nz}" if args.weak else f"HPCG-{n}"
+    workload = f"{gname} -cg -p j (27-point, {n_rows_g} rows, {nnz_g} nnz, fp64 CRS, b=1, x0=0.1)"
+    config = {"workload": workload, "rows": n_rows_g, "nnz": nnz_g,
               "partition": f"{world} z-slab(s)" if world > 1 else "single GPU",
               "l2": "inputs larger than L2 (no flush): CRS alone is %.1f GB per GPU" %
-                    (12 * (3 * n - 2) ** 3 / world / 1e9)}
+                    (12 * nnz_g / world / 1e9)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -226,7 +232,7 @@ def main():
             vals.append(leg["value"])
         out = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["value"],
-               "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config,
                "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
                "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -271,8 +277,8 @@ def main():
                                 "pack / reducing kernels, CUDA IPC)" if ctx.info()["peer_memory"]
                                 else ", NCCL halo send/recv + allreduce")
     K, W = args.steps, args.warmup
-    name = f"HPCG-{n}"
-    r_lo, r_hi = slab_rows(n ** 3, n, n * n, rank, world)
+    name = gname
+    r_lo, r_hi = slab_rows(n_rows_g, nz, n * n, rank, world)
     n_local = r_hi - r_lo
 
     # ---- e2e: host buffers in, host buffer out (pinned), through the host stack -----------------
@@ -345,7 +351,7 @@ def main():
 
     out = {
         "metric": METRIC, "value": ms_iter, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_iter, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_iter, "higher_is_better": False, "scaling": scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_ms, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * n_local / K, "d2h_bytes_per_step": 8 * n_local / K + 8,
