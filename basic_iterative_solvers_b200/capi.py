@@ -91,6 +91,7 @@ _SIGS = {
     "bis_spmv_sub": ([c_ctx, c_mat, c_dev, c_dev, c_dev], cint),
     "bis_cg_update": ([c_ctx, cint, i64] + [c_dev] * 8 + [cint] * 4, cint),
     "bis_cg_direction": ([c_ctx, i64, c_dev, c_dev, c_dev, cint, cint], cint),
+    "bis_cg_direction_x": ([c_ctx, i64, c_dev, c_dev, c_dev, c_dev, c_dev, cint, cint, cint], cint),
     "bis_bicgstab_s": ([c_ctx, cint, i64] + [c_dev] * 5 + [cint] * 2, cint),
     "bis_bicgstab_xr": ([c_ctx, i64] + [c_dev] * 9 + [cint] * 6, cint),
     "bis_bicgstab_p": ([c_ctx, cint, i64] + [c_dev] * 7 + [cint] * 5, cint),

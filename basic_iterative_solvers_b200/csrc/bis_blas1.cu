@@ -180,13 +180,26 @@ extern "C" int bis_cg_update(bis_context *c, int precond, int64_t n, double *x_n
     const double *S = c->d_scalars;
     // alpha <- (r_old, z_old) / (Ap_old, p_old), cg.hpp:19-23
     auto prep = [=] __device__() { return div_rn(S[slot_rz], S[slot_pAp]); };
-    const EwIn<4> in{{x_old, p_old, r_old, Ap}};
+    // x_new == NULL: the x update is left to bis_cg_direction_x, which reads p_old anyway (one pass
+    // over p_old less per iteration); the inputs x_old / p_old are then not touched here
+    const bool with_x = x_new != nullptr;
+    const double *xo = with_x ? x_old : r_old, *po = with_x ? p_old : r_old;
+    const EwIn<4> in{{xo, po, r_old, Ap}};
     if (precond == BIS_PRECOND_NONE) {
         REQ_SLOT(slot_rz_new);
         // z_new = r_new (copy_vector, kernels.hpp:396-399); (r,z) == (r,r): the same sum lands in both slots
-        return launch_ew2<2, 4>(c, n, prep, in, [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
-            x_new[i] = fma(alpha, v[1], v[0]);
+        auto body = [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+            if (with_x) x_new[i] = fma(alpha, v[1], v[0]);
             double r = fma(-alpha, v[3], v[2]);
+            r_new[i] = r;
+            z_new[i] = r;
+            acc[0] = fma(r, r, acc[0]);
+            acc[1] = acc[0];
+        };
+        if (with_x) return launch_ew2<2, 4>(c, n, prep, in, body, slot_rr, slot_rz_new);
+        return launch_ew2<2, 2>(c, n, prep, EwIn<2>{{r_old, Ap}},
+                                [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+            double r = fma(-alpha, v[1], v[0]);
             r_new[i] = r;
             z_new[i] = r;
             acc[0] = fma(r, r, acc[0]);
@@ -195,20 +208,37 @@ extern "C" int bis_cg_update(bis_context *c, int precond, int64_t n, double *x_n
     }
     if (precond == BIS_PRECOND_JACOBI) {
         REQ_SLOT(slot_rz_new);
-        return launch_ew2<2, 5>(c, n, prep, EwIn<5>{{x_old, p_old, r_old, Ap, A_D}},
+        if (with_x)
+            return launch_ew2<2, 5>(c, n, prep, EwIn<5>{{x_old, p_old, r_old, Ap, A_D}},
+                                    [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+                x_new[i] = fma(alpha, v[1], v[0]);
+                double r = fma(-alpha, v[3], v[2]);
+                r_new[i] = r;
+                double z = div_rn(r, v[4]);   // elemwise_div_vectors with scale = 1.0 (1.0*d == d)
+                z_new[i] = z;
+                acc[0] = fma(r, r, acc[0]);
+                acc[1] = fma(r, z, acc[1]);
+            }, slot_rr, slot_rz_new);
+        return launch_ew2<2, 3>(c, n, prep, EwIn<3>{{r_old, Ap, A_D}},
                                 [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
-            x_new[i] = fma(alpha, v[1], v[0]);
-            double r = fma(-alpha, v[3], v[2]);
+            double r = fma(-alpha, v[1], v[0]);
             r_new[i] = r;
-            double z = div_rn(r, v[4]);   // elemwise_div_vectors with scale = 1.0 (1.0*d == d)
+            double z = div_rn(r, v[2]);
             z_new[i] = z;
             acc[0] = fma(r, r, acc[0]);
             acc[1] = fma(r, z, acc[1]);
         }, slot_rr, slot_rz_new);
     }
-    return launch_ew2<1, 4>(c, n, prep, in, [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
-        x_new[i] = fma(alpha, v[1], v[0]);
-        double r = fma(-alpha, v[3], v[2]);
+    if (with_x)
+        return launch_ew2<1, 4>(c, n, prep, in, [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+            x_new[i] = fma(alpha, v[1], v[0]);
+            double r = fma(-alpha, v[3], v[2]);
+            r_new[i] = r;
+            acc[0] = fma(r, r, acc[0]);
+        }, slot_rr);
+    return launch_ew2<1, 2>(c, n, prep, EwIn<2>{{r_old, Ap}},
+                            [=] __device__(int64_t i, const double *v, double *acc, double alpha) {
+        double r = fma(-alpha, v[1], v[0]);
         r_new[i] = r;
         acc[0] = fma(r, r, acc[0]);
     }, slot_rr);
@@ -224,6 +254,26 @@ extern "C" int bis_cg_direction(bis_context *c, int64_t n, double *p_new, const 
                             [=] __device__(int64_t i, const double *v, double *, double beta) {
                                 p_new[i] = fma(beta, v[1], v[0]);
                             });
+}
+
+// cg.hpp:27-28 and :47-52 in one pass over p_old: x_new = x_old + alpha p_old ; p_new = z_new + beta p_old
+extern "C" int bis_cg_direction_x(bis_context *c, int64_t n, double *p_new, const double *z_new,
+                                  const double *p_old, double *x_new, const double *x_old,
+                                  int slot_rz_new, int slot_rz, int slot_pAp) {
+    REQ_CTX(c);
+    REQ_SLOT(slot_rz_new); REQ_SLOT(slot_rz); REQ_SLOT(slot_pAp);
+    BIS_REQUIRE(x_new && x_old, "bis_cg_direction_x: null x");
+    const double *S = c->d_scalars;
+    return launch_ew2<0, 3>(c, n, [=] __device__() {
+        Sc3 sc;
+        sc.a = div_rn(S[slot_rz], S[slot_pAp]);       // alpha of this iteration (cg.hpp:19-23)
+        sc.b = div_rn(S[slot_rz_new], S[slot_rz]);    // beta (cg.hpp:47)
+        sc.c = 0.0;
+        return sc;
+    }, EwIn<3>{{z_new, p_old, x_old}}, [=] __device__(int64_t i, const double *v, double *, Sc3 sc) {
+        x_new[i] = fma(sc.a, v[1], v[2]);
+        p_new[i] = fma(sc.b, v[1], v[0]);
+    });
 }
 
 // ---- BiCGSTAB: methods/bicgstab.hpp:8-83 ----------------------------------------

@@ -1,9 +1,11 @@
 // host/methods/cg.hpp -- ConjugateGradientSolver (reference methods/cg.hpp).
 // One iteration (cg.hpp:6-54) is enqueued without a host round trip:
 //   tmp = A p_old ; (tmp,p_old)                         bis_spmv_dot      :16,:23
-//   alpha ; x_new ; r_new ; (r_new,r_new) ; z_new ;     bis_cg_update     :23-41,:47
+//   alpha ; r_new ; (r_new,r_new) ; z_new ;             bis_cg_update      :23-41,:47
 //   (r_new,z_new)   [None / Jacobi fused; other M^-1 via apply_preconditioner]
-//   beta ; p_new                                        bis_cg_direction  :47-52
+//   beta ; p_new ; x_new = x_old + alpha p_old          bis_cg_direction_x :27-28, :47-52
+// (10 vector passes per iteration with the Jacobi preconditioner instead of the 18 of the
+// reference's separate kernels)
 // alpha and beta are formed on the device from the scalar slots.  (r_old,z_old)
 // (:19) is carried over from the previous iteration's (r_new,z_new): same
 // numbers, same deterministic reduction, so the value is bit-identical to
@@ -21,13 +23,14 @@ inline void cg_separate_iteration(Interface *dev, const PrecondType precondition
                                   double *z_new, double *z_old, const int s_rz, const int s_rz_new) {
     (void)z_old;
     BIS_OK(bis_spmv_dot(dev, A->handle, p_old, tmp, p_old, S_PAP, -1));
-    BIS_OK(bis_cg_update(dev, static_cast<int>(preconditioner), N, x_new, x_old, p_old, r_new, r_old,
+    // the x update (cg.hpp:27-28) rides with the direction update below: one pass over p_old less
+    BIS_OK(bis_cg_update(dev, static_cast<int>(preconditioner), N, nullptr, x_old, p_old, r_new, r_old,
                          tmp, z_new, A_D, s_rz, S_PAP, S_RR, s_rz_new));
     if (preconditioner != PrecondType::None && preconditioner != PrecondType::Jacobi) {
         apply_preconditioner(dev, preconditioner, N, L, U, A_D, A_D_inv, L_D, U_D, z_new, r_new, tmp, work);
         BIS_OK(bis_dot_to_slot(dev, r_new, z_new, N, s_rz_new));
     }
-    BIS_OK(bis_cg_direction(dev, N, p_new, z_new, p_old, s_rz_new, s_rz));
+    BIS_OK(bis_cg_direction_x(dev, N, p_new, z_new, p_old, x_new, x_old, s_rz_new, s_rz, S_PAP));
 }
 
 class ConjugateGradientSolver : public Solver {

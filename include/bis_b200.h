@@ -279,7 +279,7 @@ int bis_spmv_sub(bis_context *ctx, const bis_matrix *T, const double *x,
  * s[rr] <- (r_new,r_new); precond NONE: z_new = r_new; JACOBI: z_new =
  * r_new / A_D; both: s[rz_new] <- (r_new,z_new).  Other preconditioners:
  * z_new untouched, s[rz_new] untouched (caller applies M^-1 then
- * bis_dot_to_slot). */
+ * bis_dot_to_slot).  x_new == NULL: no x update (see bis_cg_direction_x). */
 int bis_cg_update(bis_context *ctx, int precond, int64_t n, double *x_new,
                   const double *x_old, const double *p_old, double *r_new,
                   const double *r_old, const double *Ap, double *z_new,
@@ -289,6 +289,13 @@ int bis_cg_update(bis_context *ctx, int precond, int64_t n, double *x_new,
 int bis_cg_direction(bis_context *ctx, int64_t n, double *p_new,
                      const double *z_new, const double *p_old, int slot_rz_new,
                      int slot_rz);
+/* The same plus the x update of cg.hpp:27-28 (x_new = x_old + alpha p_old,
+ * alpha = s[rz]/s[pAp]) in one pass over p_old; pair it with bis_cg_update
+ * called with x_new == NULL, which then skips the x update. */
+int bis_cg_direction_x(bis_context *ctx, int64_t n, double *p_new,
+                       const double *z_new, const double *p_old, double *x_new,
+                       const double *x_old, int slot_rz_new, int slot_rz,
+                       int slot_pAp);
 
 /* BiCGSTAB, methods/bicgstab.hpp:8-83.
  * alpha = s[rho_old]/s[r0v]; s = r_old - alpha v; JACOBI: s_tmp = s / A_D,

@@ -415,6 +415,19 @@ def test_cg_fused_kernels_match_unfused_sequence(ctx):
     ctx.call("bis_cg_direction", n, pn, zn, d["p"], 1, 2)
     ctx.call("bis_sum_vectors", t, zn, d["p"], n, 0.9 / 0.4)
     assert np.array_equal(ctx.download(pn, n), ctx.download(t, n))
+    # the pair the host stack uses: update without x, then direction + x in one pass over p_old
+    ctx.call("bis_scalar_set", 2, rz)
+    ctx.call("bis_scalar_set", 3, pAp)
+    rn2, zn2, xn2, pn2 = (ctx.alloc(n) for _ in range(4))
+    ctx.call("bis_cg_update", capi.PRECOND["j"], n, None, None, None, rn2, d["r"], d["Ap"], zn2, dD, 2, 3, 0, 1)
+    ctx.call("bis_cg_update", capi.PRECOND["j"], n, xn, d["x"], d["p"], rn, d["r"], d["Ap"], zn, dD, 2, 3, 4, 5)
+    assert np.array_equal(ctx.download(rn2, n), ctx.download(rn, n)) and np.array_equal(ctx.download(zn2, n), ctx.download(zn, n))
+    assert np.array_equal(ctx.scalars(0, 2), ctx.scalars(4, 2))
+    ctx.call("bis_cg_direction_x", n, pn2, zn2, d["p"], xn2, d["x"], 1, 2, 3)
+    beta = ctx.scalars(1, 1)[0] / rz
+    ctx.call("bis_sum_vectors", t, zn2, d["p"], n, beta)
+    assert np.array_equal(ctx.download(pn2, n), ctx.download(t, n))
+    assert np.array_equal(ctx.download(xn2, n), ctx.download(xn, n))
 
 
 def test_bicgstab_and_gmres_fused_kernels(ctx):
