@@ -193,6 +193,17 @@ def solve(ctx: capi.Context, method: str, precond: str = "none", *, crs=None, ma
                        float(od[4]), int(oi[4]))
 
 
+def harness_trace(run_ahead: bool, max_iters: int, tol: float, decay: float):
+    """solve() of host/solver_harness.hpp on a device-free recording solver (CPU-only test aid)."""
+    lib = load()
+    lib.bis_host_harness_trace.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_char_p, C.c_int, C.c_void_p]
+    buf = C.create_string_buffer(1 << 16)
+    out = (C.c_int * 4)()
+    if lib.bis_host_harness_trace(int(run_ahead), max_iters, tol, decay, buf, len(buf), out) != 0:
+        raise capi.BisError(_err())
+    return buf.value.decode(), {"iter_count": out[0], "iterates": out[1], "converged": bool(out[2]), "history": out[3]}
+
+
 class BenchSession:
     """Measurement session of bench.py (host/host_capi.cpp, "measurement sessions")."""
 

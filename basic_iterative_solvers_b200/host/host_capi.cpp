@@ -87,6 +87,64 @@ int bis_host_matrix_fetch(int *rp, int *col, double *val) {
     return 0;
 }
 
+// The harness loop driven by a device-free solver that only records the order of the calls (CPU-only
+// test of solve() / harness_step: run-ahead order, no speculation past max_iters, stop decisions).
+// The k-th residual norm is r0 * decay^k.  trace: 'I' iterate, 'b' norm readback enqueued, 'e' norm
+// waited for, 's' synchronous sample, 'X' exchange, 'R' check_restart, '|' end of a loop pass.
+namespace {
+class TraceSolver : public Solver {
+  public:
+    std::string trace;
+    bool ahead_ok;
+    double r0, decay;
+    int iterates = 0;
+    TraceSolver(const Args *a, bool run_ahead, double r0_, double decay_)
+        : Solver(a, nullptr), ahead_ok(run_ahead), r0(r0_), decay(decay_) {}
+    void iterate(Timers *) override { trace += 'I'; ++iterates; }
+    void exchange() override { trace += 'X'; }
+    void check_restart(Timers *) override { trace += "R|"; }
+    bool can_run_ahead() const override { return ahead_ok; }
+    void read_norm_begin() override { trace += 'b'; }
+    double read_norm_end() override {
+        trace += 'e';
+        const double r = r0 * std::pow(decay, iter_count);
+        return r * r;
+    }
+    void record_residual_norm() override {
+        trace += 's';
+        residual_norm = r0 * std::pow(decay, iter_count);
+        Solver::record_residual_norm();
+    }
+    void save_x_star() override {}
+};
+} // namespace
+
+int bis_host_harness_trace(int run_ahead, int max_iters, double tol, double decay, char *trace, int trace_cap,
+                           int *out) {
+    try {
+        Args args;
+        args.quiet = true;
+        TraceSolver s(&args, run_ahead != 0, 1.0, decay);
+        if (max_iters > MAX_ITERS) bis_fatal("max_iters exceeds MAX_ITERS");
+        s.max_iters = max_iters;
+        s.tolerance = tol;
+        s.residual_norm = 1.0;
+        s.collected_residual_norms[s.collected_residual_norms_count++] = 1.0;   // init_residual
+        s.init_stopping_criteria();
+        Timers timers;
+        solve(&args, &s, &timers);
+        std::snprintf(trace, (size_t)trace_cap, "%s", s.trace.c_str());
+        out[0] = s.iter_count;
+        out[1] = s.iterates;
+        out[2] = s.convergence_flag ? 1 : 0;
+        out[3] = s.collected_residual_norms_count;
+        return 0;
+    } catch (const std::exception &e) {
+        g_host_err = e.what();
+        return 1;
+    }
+}
+
 // GMRES host pieces (CPU-only testable against the oracle).
 void bis_host_gmres_least_squares(int k, int m, double *J, double *H, double *H_tmp, double *Q,
                                   double *Q_tmp, double *R) {

@@ -155,16 +155,23 @@ class Solver {
     virtual int norm_slot() const { return S_RR; }
     virtual void enqueue_residual_norm() {}   // kernels that produce the norm, if iterate() did not
 
+    // the split read of ||r||^2 (virtual so that the CPU tests can drive the harness without a device)
+    virtual void read_norm_begin() { BIS_OK(bis_scalar_read_begin(dev, norm_slot(), 1)); }
+    virtual double read_norm_end() {
+        double rr = 0.0;
+        BIS_OK(bis_scalar_read_end(dev, norm_slot(), 1, &rr));
+        return rr;
+    }
+
     void sample_residual_begin() {
         if (iter_count % residual_check_len == 0) {
             enqueue_residual_norm();
-            BIS_OK(bis_scalar_read_begin(dev, norm_slot(), 1));
+            read_norm_begin();
         }
     }
     void sample_residual_end(Stopwatch *per_iteration_time) {
         if (iter_count % residual_check_len == 0) {
-            double rr = 0.0;
-            BIS_OK(bis_scalar_read_end(dev, norm_slot(), 1, &rr));
+            const double rr = read_norm_end();
             residual_norm = std::sqrt(rr);
             Solver::record_residual_norm();
             time_per_iteration[collected_residual_norms_count] = per_iteration_time->check();

@@ -52,5 +52,5 @@ inline void solve(Args *cli_args, Solver *solver, Timers *timers) {
     if (solver->residual_norm < solver->stopping_criteria) solver->convergence_flag = true;
     TIME(timers->save_x_star, solver->save_x_star())
     // a watchdog trip inside a triangular solve surfaces here as a fatal error
-    BIS_OK(bis_context_synchronize(solver->dev));
+    if (solver->dev) BIS_OK(bis_context_synchronize(solver->dev));
 }

@@ -147,3 +147,23 @@ def test_host_gmres_givens_matches_oracle(built):
         rh = host.gmres_update_g(k, m, state_h[3], g_h, gt_h, beta)
         ro = lib.o_gmres_update_g(k, m, state_o[3], g_o, gt_o, beta)
         assert rh == ro and np.array_equal(g_h, g_o)
+
+
+def test_harness_run_ahead_order_and_stop_decisions():
+    """solve() / harness_step (host/solver_harness.hpp) on a device-free recording solver: with run-ahead the
+    next iterate() is enqueued between the norm readback's begin and end, the decisions are those of the
+    reference's order (solver_harness.hpp:17-50), and nothing is enqueued past max_iters."""
+    # reference order: iterate, sample, exchange, check_restart
+    t, r = host.harness_trace(False, 50, 1e-3, 0.5)
+    assert r == {"iter_count": 10, "iterates": 10, "converged": True, "history": 11}      # 0.5^10 < 1e-3
+    assert t == "IsXR|" * 10
+    # run-ahead: one iterate in flight behind every readback; the last one is the discarded speculation
+    t, r = host.harness_trace(True, 50, 1e-3, 0.5)
+    assert r == {"iter_count": 10, "iterates": 11, "converged": True, "history": 11}
+    assert t == "IbXIeR|" + "bXIeR|" * 9
+    # does not converge: exactly max_iters iterates, the last pass does not speculate
+    t, r = host.harness_trace(True, 7, 1e-30, 0.9)
+    assert r == {"iter_count": 7, "iterates": 7, "converged": False, "history": 8}
+    assert t == "IbXIeR|" + "bXIeR|" * 5 + "bXeR|"
+    t, r = host.harness_trace(False, 7, 1e-30, 0.9)
+    assert r["iterates"] == 7 and t == "IsXR|" * 7
