@@ -325,6 +325,7 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
         if (!value) vector_cache_release(c);
     }
     else if (k == "trsv_gates") c->opt_trsv_gates = value;
+    else if (k == "trsv_block") c->opt_trsv_block = value;
     else if (k == "trsv_sleep1") c->opt_trsv_sleep[0] = value;
     else if (k == "trsv_sleep2") c->opt_trsv_sleep[1] = value;
     else if (k == "trsv_sleep3") c->opt_trsv_sleep[2] = value;

@@ -151,6 +151,7 @@ struct bis_context {
     int opt_spmv_lanes = 0;
     int opt_trsv_variant = 0;
     int opt_trsv_poll_ns = 0;   // sleep between polls in the triangular solve (0: default)
+    int opt_trsv_block = 256;   // triangular solve: rows per block (64, 128, 256)
     int opt_trsv_gates = 1;     // triangular solve: staged waiting on the per-row gates (0: poll all operands)
     int opt_trsv_sleep[4] = {0, 60, 250, 1000};   // ns between polls of a gate 1, 2, 3, >= 4 levels back (>= 6: twice the last)
     int opt_trsv_debug = 0;     // dump per-row timestamps of each solve to $BIS_TRSV_DEBUG_FILE

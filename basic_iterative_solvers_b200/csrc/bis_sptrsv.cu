@@ -160,11 +160,12 @@ __global__ void __launch_bounds__(256) trsv_fill_sentinel_kernel(int64_t n, doub
         reinterpret_cast<unsigned long long *>(w)[i] = TRSV_SENTINEL;
 }
 
-__global__ void __launch_bounds__(TRSV_THREADS) sptrsv_flag_kernel(TrsvArgs a, double *w) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) sptrsv_flag_kernel(TrsvArgs a, double *w) {
     __shared__ unsigned int s_chunk;
     if (threadIdx.x == 0) s_chunk = atomicAdd(a.ticket, 1u);
     __syncthreads();
-    const int64_t slot = (int64_t)s_chunk * TRSV_THREADS + threadIdx.x;
+    const int64_t slot = (int64_t)s_chunk * THREADS + threadIdx.x;
     const bool live = slot < a.n_slots;
 
     int row = 0, lvl = 0x7fffffff;
@@ -357,7 +358,15 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     if (c->opt_trsv_variant != 2) {
         trsv_fill_sentinel_kernel<<<bis_blocks_for(lv.n_slots, 1024, c->sm_count * 8), 256, 0, c->stream>>>(lv.n_slots, lv.d_w);
         BIS_LAUNCH_CHECK(c);
-        sptrsv_flag_kernel<<<(unsigned int)blocks, TRSV_THREADS, 0, c->stream>>>(a, lv.d_w);
+        // rows per block (opt "trsv_block"): a block retires when its last row is done, so smaller blocks
+        // hand their registers to rows further down the list sooner
+        const int tb = c->opt_trsv_block;
+        if (tb == 64)
+            sptrsv_flag_kernel<64><<<(unsigned int)((lv.n_slots + 63) / 64), 64, 0, c->stream>>>(a, lv.d_w);
+        else if (tb == 128)
+            sptrsv_flag_kernel<128><<<(unsigned int)((lv.n_slots + 127) / 128), 128, 0, c->stream>>>(a, lv.d_w);
+        else
+            sptrsv_flag_kernel<256><<<(unsigned int)blocks, 256, 0, c->stream>>>(a, lv.d_w);
         BIS_LAUNCH_CHECK(c);
         if (a.dbg) {   // debug aid (tools/trsv_trace.py): per-row timestamps of the last solve
             std::vector<unsigned long long> h(4 * (size_t)lv.n_slots);
