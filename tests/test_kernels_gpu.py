@@ -577,11 +577,11 @@ def _random_general(n, seed, zero_fraction=0.05):
     return rp, np.concatenate([c for c, _ in rows]).astype(np.int32), np.concatenate([v for _, v in rows])
 
 
-@pytest.mark.parametrize("case", ["hpcg", "anderson", "random", "random_big"])
+@pytest.mark.parametrize("case", ["hpcg", "hpcg_rp64", "anderson", "random", "random_big"])
 def test_device_ilu0_matches_host_factorisation(ctx, case):
     """bis_matrix_ilu0 (one dataflow launch) against the sequential host routine that tests/test_host_cpu.py
     pins to the compiled reference's factor_ILU0_old: every factor entry bit for bit."""
-    if case == "hpcg":
+    if case in ("hpcg", "hpcg_rp64"):
         rp, col, val = matgen.hpcg(9, 7, 6)
     elif case == "anderson":
         rp, col, val = matgen.anderson(9, 8, 7, 5.0, 1.0, 3, True)
@@ -590,7 +590,8 @@ def test_device_ilu0_matches_host_factorisation(ctx, case):
     rp = rp.astype(np.int32)
     n = len(rp) - 1
     f = port.factor(rp, col, val, "ilu0")
-    A = ctx.upload_crs(rp, col, val)
+    # 64-bit row_ptr: the layout HPCG-512 needs on one GPU (bis_matrix_upload_crs64)
+    A = ctx.upload_crs(rp.astype(np.int64) if case.endswith("rp64") else rp, col, val)
     L, U, dLD, dUD = ctx.ilu0(A, n)
     lrp, lcol, lval = L.download()
     urp, ucol, uval = U.download()
