@@ -81,6 +81,7 @@ static int context_init(bis_context *c, int device) {
     BIS_CUDA(cudaDeviceSynchronize());
     // experiment switches (must be set alike on every rank)
     if (const char *e = getenv("BIS_SPMV_FUSED")) c->opt_spmv_fused = atoi(e);
+    if (const char *e = getenv("BIS_TRSV_VARIANT")) c->opt_trsv_variant = atoi(e);
     return 0;
 }
 
@@ -218,6 +219,7 @@ extern "C" int bis_context_info(bis_context *c, int64_t info[8]) {
     info[2] = (int64_t)tot;
     info[3] = c->launches;
     info[4] = (int64_t)c->l2_bytes;
+    info[6] = c->chain_solves;
     info[5] = (c->peer_on && c->opt_dist_p2p) ? 1 : 0;   // 1: collectives run over peer memory, 0: NCCL
     return 0;
 }

@@ -218,7 +218,7 @@ int build_levels(bis_context *c, bis_matrix *T) {
     BIS_CUDA(cudaStreamSynchronize(st));
     lv.level_start.assign((size_t)lv.n_levels + 1, 0);
     for (int l = 0; l < lv.n_levels; ++l) lv.level_start[l + 1] = lv.level_start[l] + level_size[l];
-    cudaFree(d_level);
+    lv.d_level = d_level;   // kept: the chain format (bis_sptrsv_chain.cuh) is built from it on demand
     cudaFree(d_slot_of);
     return 0;
 }

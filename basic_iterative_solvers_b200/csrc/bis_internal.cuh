@@ -138,6 +138,7 @@ struct bis_context {
     unsigned int *d_pack_ticket = nullptr;
     std::vector<void *> ipc_opened;                 // mappings to close
     int64_t launches = 0;
+    int64_t chain_solves = 0;   // triangular solves that ran as variant 4 (bis_sptrsv_chain.cuh)
     // options
     // freed vectors are kept for the next allocation of the same size (a solver allocates ~20 vectors of
     // one length; cudaMalloc + cudaFree of a gigabyte each is milliseconds); emptied when memory runs short
@@ -166,10 +167,23 @@ struct bis_context {
     ProfTag prof[BIS_PROF_NTAGS];
 };
 
+// Variant 4 of the triangular solve (bis_sptrsv_chain.cuh): sliced-ELL records of 32 chains per warp
+struct ChainFormat {
+    int state = 0;                 // 0 not built, 1 usable, -1 not representable (fall back to the dataflow solve)
+    int K = 0;                     // nonzeros per record row (max row length)
+    int n_groups = 0;              // warps
+    long long n_recs = 0;          // warp steps over all groups
+    unsigned char *d_recs = nullptr;
+    long long *d_slice_off = nullptr;   // [n_groups + 1]
+    double *d_w = nullptr;              // [32 * n_recs] working vector, record-major
+};
+
 struct LevelSets {
     int n_levels = 0;
     int64_t n_slots = 0;              // == n_rows: position in the level-ordered row list
     int *d_slot_row = nullptr;        // [n_slots] original row
+    int *d_level = nullptr;           // [n_rows] level of every row (kept for the chain format)
+    mutable ChainFormat chain;
     int *d_slot_level = nullptr;      // [n_slots] level of that row (non-decreasing)
     int *d_slot_gate = nullptr;       // [4*n_slots] three gate columns + their packed level distances (bis_matrix.cu)
     int *d_level_size = nullptr;      // [n_levels] rows per level

@@ -27,6 +27,10 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->d_val);
     cudaFree(A->lv.d_slot_row);
     cudaFree(A->lv.d_slot_level);
+    cudaFree(A->lv.d_level);
+    cudaFree(A->lv.chain.d_recs);
+    cudaFree(A->lv.chain.d_slice_off);
+    cudaFree(A->lv.chain.d_w);
     cudaFree(A->lv.d_slot_gate);
     cudaFree(A->lv.d_level_size);
     cudaFree(A->lv.d_level_done);

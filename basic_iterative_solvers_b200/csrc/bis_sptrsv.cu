@@ -21,6 +21,7 @@
 // n_levels x (L2 round trip + fence): latency-bound for stencil orderings
 // (HPCG-n has 7n-6 levels).
 #include "bis_device.cuh"
+#include "bis_sptrsv_chain.cuh"
 
 #include <cstdlib>
 
@@ -309,6 +310,106 @@ sptrsv_one_level_kernel(TrsvArgs a, double *w, int64_t slot_begin, int64_t slot_
 
 } // namespace
 
+// ---- variant 4: chains (bis_sptrsv_chain.cuh) ---------------------------------------------------------
+template <typename RP>
+static int chain_build_t(bis_context *c, const bis_matrix *T) {
+    ChainFormat &cf = T->lv.chain;
+    cf.state = -1;
+    const int64_t n = T->n_rows;
+    const int upper = T->triangular == 2 ? 1 : 0;
+    // record width: the smallest instantiated kernel width that holds the longest row
+    const int K = T->max_row <= 4 ? 4 : T->max_row <= 8 ? 8 : T->max_row <= 14 ? 14 : 16;
+    if (n < 64 || T->max_row < 1 || T->max_row > chain::KMAX || !T->lv.d_level) return 0;
+    cudaStream_t st = c->stream;
+    auto pol = thrust::cuda::par.on(st);
+    const RP *rp = static_cast<const RP *>(T->d_rp);
+    const int grid = bis_blocks_for(n, 256, c->sm_count * 16);
+    int *head = nullptr, *cid = nullptr, *chain_start = nullptr, *lmin = nullptr, *pos = nullptr;
+    long long *steps = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(head); cudaFree(cid); cudaFree(chain_start); cudaFree(lmin); cudaFree(pos);
+    };
+    BIS_CUDA(bis_cuda_malloc(&head, sizeof(int) * (size_t)n));
+    BIS_CUDA(bis_cuda_malloc(&cid, sizeof(int) * (size_t)n));
+    chain::head_kernel<RP><<<grid, 256, 0, st>>>(n, rp, T->d_col, upper, head);
+    BIS_LAUNCH_CHECK(c);
+    thrust::inclusive_scan(pol, thrust::device_pointer_cast(head), thrust::device_pointer_cast(head) + n,
+                           thrust::device_pointer_cast(cid));
+    int n_chains = 0;
+    BIS_CUDA(cudaMemcpyAsync(&n_chains, cid + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    BIS_CUDA(cudaStreamSynchronize(st));
+    const int n_groups = (n_chains + 31) / 32;
+    BIS_CUDA(bis_cuda_malloc(&chain_start, sizeof(int) * ((size_t)n_chains + 1)));
+    BIS_CUDA(bis_cuda_malloc(&lmin, sizeof(int) * (size_t)n_groups));
+    BIS_CUDA(bis_cuda_malloc(&steps, sizeof(long long) * ((size_t)n_groups + 1)));
+    chain::chain_start_kernel<<<grid, 256, 0, st>>>(n, head, cid, chain_start, n_chains);
+    BIS_LAUNCH_CHECK(c);
+    BIS_CUDA(cudaMemsetAsync(steps, 0, sizeof(long long) * ((size_t)n_groups + 1), st));
+    chain::group_steps_kernel<<<bis_blocks_for(n_groups, 128, c->sm_count * 8), 128, 0, st>>>(
+        n_groups, n_chains, n, upper, chain_start, T->lv.d_level, lmin, steps);
+    BIS_LAUNCH_CHECK(c);
+    thrust::exclusive_scan(pol, thrust::device_pointer_cast(steps), thrust::device_pointer_cast(steps) + n_groups + 1,
+                           thrust::device_pointer_cast(steps));
+    long long n_recs = 0;
+    BIS_CUDA(cudaMemcpyAsync(&n_recs, steps + n_groups, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    BIS_CUDA(cudaStreamSynchronize(st));
+    // idle lane-steps are padding: give up when the chains of a warp are too unlike (or too short) to be
+    // worth it, and when positions would not fit 31 bits
+    if (n_recs * 32 > (long long)(2.5 * (double)n) || n_recs * 32 >= (1ll << 31)) {
+        cleanup();
+        cudaFree(steps);
+        return 0;
+    }
+    const size_t rb = chain::rec_bytes(K);
+    unsigned char *recs = nullptr;
+    double *w = nullptr;
+    BIS_CUDA(bis_cuda_malloc(&recs, rb * (size_t)n_recs));
+    BIS_CUDA(bis_cuda_malloc(&w, sizeof(double) * 32 * (size_t)n_recs));
+    BIS_CUDA(bis_cuda_malloc(&pos, sizeof(int) * (size_t)n));
+    chain::rec_init_kernel<<<c->sm_count * 16, 256, 0, st>>>(n_recs, K, recs);
+    BIS_LAUNCH_CHECK(c);
+    chain::pos_kernel<<<grid, 256, 0, st>>>(n, upper, cid, T->lv.d_level, lmin, steps, pos);
+    BIS_LAUNCH_CHECK(c);
+    chain::rec_fill_kernel<RP><<<grid, 256, 0, st>>>(n, rp, T->d_col, T->d_val, upper, K, cid, T->lv.d_level, lmin, pos, recs);
+    BIS_LAUNCH_CHECK(c);
+    BIS_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+    cf.K = K;
+    cf.n_groups = n_groups;
+    cf.n_recs = n_recs;
+    cf.d_recs = recs;
+    cf.d_slice_off = steps;
+    cf.d_w = w;
+    cf.state = 1;
+    return 0;
+}
+
+static int chain_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, const double *b) {
+    const ChainFormat &cf = T->lv.chain;
+    chain::Args a;
+    a.n_groups = cf.n_groups;
+    a.K = cf.K;
+    a.recs = cf.d_recs;
+    a.slice_off = cf.d_slice_off;
+    a.ticket = T->lv.d_ticket;
+    a.errflag = c->d_errflag;
+    a.x = x;
+    a.D = D;
+    a.b = b;
+    const size_t per_warp = chain::NST * chain::rec_bytes(cf.K) + 32 * 8 * sizeof(double) + 64;
+    const size_t smem = per_warp * chain::WARPS;
+    void (*kern)(chain::Args, double *) = cf.K == 4 ? chain::chain_kernel<4> : cf.K == 8 ? chain::chain_kernel<8>
+                                           : cf.K == 14 ? chain::chain_kernel<14> : chain::chain_kernel<16>;
+    BIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BIS_CUDA(cudaMemsetAsync(T->lv.d_ticket, 0, sizeof(unsigned int), c->stream));
+    chain::fill_sentinel_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(32 * cf.n_recs, cf.d_w);
+    BIS_LAUNCH_CHECK(c);
+    const int blocks = (cf.n_groups + chain::WARPS - 1) / chain::WARPS;
+    kern<<<blocks, chain::WARPS * 32, smem, c->stream>>>(a, cf.d_w);
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}
+
 static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const double *D,
                       const double *b, int want_kind) {
     BIS_REQUIRE(c && T && x && D && b, "sptrsv: null argument");
@@ -342,7 +443,16 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.x = x;
     a.D = D;
     a.b = b;
+    if (c->opt_trsv_variant == 4 && T->lv.chain.state == 0) {
+        if (T->rp_bytes == 8) BIS_CHECK(chain_build_t<int64_t>(c, T));
+        else BIS_CHECK(chain_build_t<int32_t>(c, T));
+    }
     BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPTRSV));
+    if (c->opt_trsv_variant == 4 && T->lv.chain.state == 1) {
+        BIS_CHECK(chain_solve(c, T, x, D, b));
+        c->chain_solves++;
+        return bis_prof_end(c, BIS_PROF_SPTRSV);
+    }
     if (c->opt_trsv_variant == 1) {
         const std::vector<int64_t> &ls = lv.level_start;
         for (int l = 0; l < lv.n_levels; ++l) {

@@ -77,7 +77,8 @@ int bis_context_rank(const bis_context *ctx, int *rank, int *nranks);
 /* info[0]=SM count, info[1]=free bytes, info[2]=total bytes, info[3]=kernel
  * launches issued by this context so far, info[4]=L2 bytes, info[5]=1 when
  * the reductions and halo exchanges of a distributed context run over peer
- * memory (CUDA IPC + NVLink stores inside the kernels), 0 when over NCCL */
+ * memory (CUDA IPC + NVLink stores inside the kernels), 0 when over NCCL,
+ * info[6]=triangular solves that ran as the chain variant (trsv_variant 4) */
 int bis_context_info(bis_context *ctx, int64_t info[8]);
 /* Device timing on the context's stream (cudaEvent pair). */
 int bis_timer_start(bis_context *ctx);

@@ -658,6 +658,55 @@ def test_scale_symmetric_matches_numpy_restatement(ctx):
     A.free()
 
 
+@pytest.mark.parametrize("case", ["hpcg_64_64_8", "anderson_100_20_10", "hpcg_ilu0"])
+def test_chain_variant_of_the_triangular_solve(ctx, case):
+    """trsv_variant = 4 (bis_sptrsv_chain.cuh: a lane per chain of consecutively dependent rows, 32 chains per
+    warp skewed by their levels): same bits as the sequential oracle, forward, backward, in place, and as
+    SGS / ILU(0) preconditioner.  The grids are large enough for the chain format to be accepted."""
+    if case == "anderson_100_20_10":
+        rp, col, val = matgen.anderson(100, 20, 10, 5.0, 1.0, 3, False)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        val = val.copy()
+        val[rows == col] += 8.0
+    else:
+        rp, col, val = matgen.hpcg(64, 64, 8)
+    rp = rp.astype(np.int32)
+    n = len(rp) - 1
+    pre = "ilu0" if case == "hpcg_ilu0" else "sgs"
+    f = port.factor(rp, col, val, pre)
+    DL, DU = (f.L_D, f.U_D) if pre == "ilu0" else (f.A_D, f.A_D)
+    b = np.cos(np.arange(n) * 0.01) + 0.3
+    ctx.set_option("trsv_variant", 4)
+    try:
+        before = ctx.info()["chain_solves"]
+        L = ctx.upload_triangular(f.l_rp, f.l_col, f.l_val, upper=False)
+        U = ctx.upload_triangular(f.u_rp, f.u_col, f.u_val, upper=True)
+        dDL, dDU, db, dx = ctx.upload(DL), ctx.upload(DU), ctx.upload(b), ctx.alloc(n)
+        for _ in range(2):      # the second solve reuses the format and the working vector
+            ctx.call("bis_sptrsv", L.h, dx, dDL, db)
+            assert np.array_equal(ctx.download(dx, n).view(np.int64),
+                                  port.sptrsv(f.l_rp, f.l_col, f.l_val, DL, b).view(np.int64))
+            ctx.call("bis_bsptrsv", U.h, dx, dDU, db)
+            assert np.array_equal(ctx.download(dx, n).view(np.int64),
+                                  port.sptrsv(f.u_rp, f.u_col, f.u_val, DU, b, backward=True).view(np.int64))
+        # in place (x aliases b): gmres.hpp:288-291, bicgstab.hpp:157-160
+        dxb = ctx.upload(b)
+        ctx.call("bis_sptrsv", L.h, dxb, dDL, dxb)
+        assert np.array_equal(ctx.download(dxb, n).view(np.int64), port.sptrsv(f.l_rp, f.l_col, f.l_val, DL, b).view(np.int64))
+        # as a preconditioner
+        want = port.apply_preconditioner(pre, f, b)
+        dAD, dLD, dUD = ctx.upload(f.A_D), ctx.upload(f.L_D), ctx.upload(f.U_D)
+        dout, dtmp = ctx.alloc(n), ctx.alloc(n)
+        ctx.call("bis_apply_preconditioner", capi.PRECOND[pre], n, L.h, U.h, dAD, None, dLD, dUD, dout, db, dtmp, None)
+        assert np.array_equal(ctx.download(dout, n).view(np.int64), want.view(np.int64))
+        assert ctx.info()["chain_solves"] - before == 7, "the chain format was not accepted for this matrix"
+        for v in (dDL, dDU, db, dx, dxb, dAD, dLD, dUD, dout, dtmp):
+            ctx.free(v)
+        L.free(), U.free()
+    finally:
+        ctx.set_option("trsv_variant", 0)
+
+
 def test_zero_diagonal_is_fatal(ctx):
     # SanityChecker::zero_diag (common.hpp:388-391, LU_factors.hpp:842-845)
     B = ctx.upload_crs(i32(0, 2, 4), i32(0, 1, 0, 1), f64(1e-17, 1, 1, 2))
