@@ -25,8 +25,7 @@ enum Slot : int {
     S_RR_BI = 8,     // adjacent to S_RHO_NEW
     S_RHO_OLD = 9,
     S_BETA2 = 10,
-    S_HN = 11,
-    S_H = 16         // S_H + j, j = 0..m  (GMRES Hessenberg column)
+    S_H = 16         // S_H + j, j = 0..k: GMRES Hessenberg column h_jk; S_H + k + 1: ||w||^2
 };
 
 class Solver {
