@@ -237,10 +237,17 @@ __global__ void __launch_bounds__(WARPS * 32) chain_kernel(Args a, double *w) {
             av[k] = rv[k * 32 + lane];
         }
         // operands made by this warp: from the ring, into the operand's own register
+        // (unconditional loads from a clamped index plus a select: as `if` bodies ptxas turned them into
+        // fourteen branch / reconvergence regions)
+        double rg[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const unsigned int e = (unsigned int)(CODE_RING0 - code[k]);   // 0..255 for a ring operand
+            rg[k] = ring[e < 256u ? e : 0u];
+        }
 #pragma unroll
         for (int k = 0; k < KT; ++k)
-            if (code[k] <= CODE_RING0 && code[k] != CODE_NONE)
-                cur.x[k] = (unsigned long long)__double_as_longlong(ring[CODE_RING0 - code[k]]);
+            if ((unsigned int)(CODE_RING0 - code[k]) < 256u) cur.x[k] = (unsigned long long)__double_as_longlong(rg[k]);
         // operands of other warps that were not there yet (warp-uniform loop; rare once the producing
         // warp runs a hop ahead).  The sentinel's high word cannot occur in a result.
         bool missing = false;
