@@ -167,3 +167,19 @@ def test_harness_run_ahead_order_and_stop_decisions():
     assert t == "IbXIeR|" + "bXIeR|" * 5 + "bXeR|"
     t, r = host.harness_trace(False, 7, 1e-30, 0.9)
     assert r["iterates"] == 7 and t == "IsXR|" * 7
+
+
+def test_integration_stub_compiles_against_the_header(tmp_path):
+    """The reference-side binding shown in INTEGRATION.md section 2 is real code: it must compile against
+    include/bis_b200.h (g++ -fsyntax-only; no CUDA, no device)."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"```cpp\n(.*?)```", text, re.S)
+    assert m, "INTEGRATION.md lost its C++ stub"
+    src = tmp_path / "bis_b200_binding.cpp"
+    src.write_text(m.group(1) + "\nint main() { return 0; }\n")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
