@@ -74,22 +74,28 @@ levels_dataflow_kernel(int64_t n, const RP *rp, const int *col, int upper, int *
     const RP e = rp[r + 1];
     int lv = 0;
     unsigned int spins = 0;
+    unsigned long long t_wd = 0;
     bool finished = false;
     while (!finished) {
+        const RP k_before = k;
         while (k < e) {
             const int l = ld_relaxed_s32(level + col[k]);
             if (l < 0) break;
             lv = max(lv, l + 1);
             ++k;
         }
+        if (k != k_before) t_wd = 0;
         if (k == e) {
             __stcg(level + r, lv);   // publish inside the loop (see the file header)
             finished = true;
-        } else if ((++spins & 0xfffffu) == 0 && *reinterpret_cast<volatile int *>(errflag)) {
-            finished = true;
-        } else if (spins > 0x40000000u) {
-            atomicExch(errflag, 3);
-            finished = true;
+        } else if ((++spins & 0x3fffu) == 0) {   // watchdog: another kernel's error, or 60 s without progress
+            if (t_wd == 0) t_wd = bis_globaltimer();
+            if (*reinterpret_cast<volatile int *>(errflag)) {
+                finished = true;
+            } else if (bis_globaltimer() - t_wd > 60000000000ull) {
+                atomicExch(errflag, 3);
+                finished = true;
+            }
         }
     }
 }
@@ -366,6 +372,7 @@ ilu0_dataflow_kernel(int64_t n, const int *lrp, const int *lcol, double *lval, c
     int kk = lrp[i];
     const int ke = lrp[i + 1], ub = urp[i], ue = urp[i + 1];
     unsigned int spins = 0;
+    unsigned long long t_wd = 0;
     bool finished = false;
     while (!finished) {
         if (kk < ke) {
@@ -395,11 +402,15 @@ ilu0_dataflow_kernel(int64_t n, const int *lrp, const int *lcol, double *lval, c
                 }
                 ++kk;
                 spins = 0;
-            } else if ((++spins & 0xfffffu) == 0 && *reinterpret_cast<volatile int *>(errflag)) {
-                finished = true;
-            } else if (spins > 0x40000000u) {
-                atomicExch(errflag, 4);
-                finished = true;
+                t_wd = 0;
+            } else if ((++spins & 0x3fffu) == 0) {   // watchdog: another kernel's error, or 60 s without progress
+                if (t_wd == 0) t_wd = bis_globaltimer();
+                if (*reinterpret_cast<volatile int *>(errflag)) {
+                    finished = true;
+                } else if (bis_globaltimer() - t_wd > 60000000000ull) {
+                    atomicExch(errflag, 4);
+                    finished = true;
+                }
             }
         } else {
             double u = __ldcg(ud + i);
