@@ -46,6 +46,7 @@ _SIGS = {
     "bis_profile_enable": ([c_ctx, cint], cint),
     "bis_profile_read": ([c_ctx, C.c_char_p, C.POINTER(dbl), C.POINTER(i64)], cint),
     "bis_context_set_option": ([c_ctx, C.c_char_p, cint], cint),
+    "bis_partition_row_block": ([i64, i64, cint, cint, C.POINTER(i64), C.POINTER(i64)], cint),
     "bis_vector_alloc": ([c_ctx, i64, C.POINTER(c_dev)], cint),
     "bis_vector_free": ([c_ctx, c_dev], cint),
     "bis_vector_upload": ([c_ctx, c_dev, C.c_void_p, i64], cint),
@@ -144,6 +145,15 @@ def load() -> C.CDLL:
         fn.restype = res
     _lib = lib
     return lib
+
+
+def partition_row_block(n_global: int, plane: int, rank: int, nranks: int):
+    """Row block of `rank` (bis_partition_row_block: pure function of the C-ABI, no device needed)."""
+    lib = load()
+    b, e = i64(0), i64(0)
+    if lib.bis_partition_row_block(int(n_global), int(plane), int(rank), int(nranks), C.byref(b), C.byref(e)) != 0:
+        raise BisError(lib.bis_last_error().decode(errors="replace"))
+    return int(b.value), int(e.value)
 
 
 def check(rc: int) -> None:

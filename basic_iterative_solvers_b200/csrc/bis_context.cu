@@ -240,6 +240,15 @@ extern "C" int bis_timer_stop(bis_context *c, double *elapsed_ms) {
     return 0;
 }
 
+int bis_ensure_dynamic_smem(bis_context *c, const void *func, size_t bytes) {
+    auto it = c->smem_configured.find(func);
+    if (it != c->smem_configured.end() && it->second >= bytes) return 0;
+    BIS_CUDA(cudaSetDevice(c->device));
+    BIS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    c->smem_configured[func] = bytes;
+    return 0;
+}
+
 // ---- per-family kernel timing ---------------------------------------------------
 static int prof_flush(bis_context *c, ProfTag &t) {
     if (t.used == 0) return 0;
@@ -336,10 +345,13 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_rows") c->opt_spmv_rows = value;
     else if (k == "spmv_stages") c->opt_spmv_stages = value;
     else if (k == "spmv_smem_kb") c->opt_spmv_smem_kb = value;
+    else if (k == "spmv_l2_mb") c->opt_spmv_l2_mb = value;
     else if (k == "spmv_blocked") c->opt_spmv_blocked = value;
     else if (k == "spmv_mult") c->opt_spmv_mult = value;
     else if (k == "win_rows") c->opt_win_rows = value;
+#ifdef BIS_PERF_DEBUG
     else if (k == "spmv_debug") c->opt_spmv_debug = value;
+#endif
     else {
         bis_set_error("unknown option '%s'", key);
         return 2;
@@ -470,6 +482,109 @@ int bis_reduce_finish(bis_context *c, int slot_a, int slot_b) {
     return 0;
 }
 
+// ---- row partition: 8 virtual slabs ------------------------------------------------------------------
+static int64_t pow2_ceil(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+void bis_partition_rule(int64_t n_global, int64_t plane, int64_t vb[BIS_NSLAB + 1], int *chunk) {
+    // rows per block of a reducing streaming kernel: 8192..16384 blocks on a large problem
+    int64_t ch = pow2_ceil((n_global + 16383) / 16384);
+    if (ch < BIS_RED_CHUNK_MIN) ch = BIS_RED_CHUNK_MIN;
+    if (ch > (1 << 20)) ch = 1 << 20;
+    *chunk = (int)ch;
+    // equal row blocks, rounded up to whole chunks (then streaming kernels AND the windowed SpMV reduce
+    // partition-invariantly; an eighth of HPCG-128/256/512 is a whole number of chunks and of z-planes), on
+    // small problems only to whole SpMV tiles of 128 rows, on tiny ones not at all -- never leaving a slab empty
+    (void)plane;
+    int64_t per = (n_global + BIS_NSLAB - 1) / BIS_NSLAB;
+    for (int64_t unit : {ch, (int64_t)128}) {
+        const int64_t r = (per + unit - 1) / unit * unit;
+        if (r * (BIS_NSLAB - 1) < n_global) {
+            per = r;
+            break;
+        }
+    }
+    for (int v = 0; v <= BIS_NSLAB; ++v) vb[v] = per * v < n_global ? per * v : n_global;
+}
+
+void bis_partition_rows(int64_t n_global, int64_t plane, int rank, int nranks, int64_t *begin, int64_t *end) {
+    if (nranks >= 1 && BIS_NSLAB % nranks == 0) {
+        int64_t vb[BIS_NSLAB + 1];
+        int ch;
+        bis_partition_rule(n_global, plane, vb, &ch);
+        const int per = BIS_NSLAB / nranks;
+        *begin = vb[rank * per];
+        *end = vb[(rank + 1) * per];
+        return;
+    }
+    // rank counts that do not divide 8: contiguous row blocks, whole planes when there are enough
+    const int64_t planes = plane > 0 ? n_global / plane : 0;
+    if (plane > 0 && planes >= nranks) {
+        const int64_t q = planes / nranks, r = planes % nranks;
+        const int64_t b = rank * q + (rank < r ? rank : r);
+        *begin = b * plane;
+        *end = (b + q + (rank < r ? 1 : 0)) * plane;
+    } else {
+        const int64_t q = n_global / nranks, r = n_global % nranks;
+        *begin = rank * q + (rank < r ? rank : r);
+        *end = *begin + q + (rank < r ? 1 : 0);
+    }
+}
+
+static RowPartition make_partition(int nranks, int64_t n_global, int64_t plane, int64_t row_begin, int64_t n_local) {
+    RowPartition p;
+    p.n_global = n_global;
+    p.row_begin = row_begin;
+    p.n_local = n_local;
+    int64_t vb[BIS_NSLAB + 1];
+    bis_partition_rule(n_global, plane, vb, &p.chunk);
+    p.n_slab = 1;
+    p.slab_first = 0;
+    p.slab_row[0] = 0;
+    p.slab_row[1] = n_local;
+    p.invariant = false;
+    if (nranks >= 1 && BIS_NSLAB % nranks == 0) {
+        // the row block must be a union of consecutive virtual slabs
+        const int per = BIS_NSLAB / nranks;
+        for (int v = 0; v + per <= BIS_NSLAB; v += per)
+            if (vb[v] == row_begin && vb[v + per] == row_begin + n_local) {
+                p.n_slab = per;
+                p.slab_first = v;
+                for (int i = 0; i <= per; ++i) p.slab_row[i] = vb[v + i] - row_begin;
+                p.invariant = true;
+                break;
+            }
+    }
+    return p;
+}
+
+void bis_partition_set(bis_context *c, int64_t n_global, int64_t plane, int64_t row_begin, int64_t n_local) {
+    c->part = make_partition(c->nranks, n_global, plane, row_begin, n_local);
+}
+
+RowPartition bis_partition_for(const bis_context *c, int64_t n) {
+    if (c->part.n_local == n && c->part.n_global > 0) return c->part;
+    // a vector of another length: on one GPU the default rule for that length (still the fixed tree);
+    // in a distributed context its global layout is unknown: one record per rank
+    if (c->nranks == 1) return make_partition(1, n, 0, 0, n);
+    RowPartition p;
+    p.n_global = p.n_local = n;
+    p.chunk = BIS_RED_CHUNK_MIN;
+    p.slab_row[1] = n;
+    return p;
+}
+
+extern "C" int bis_partition_row_block(int64_t n_global, int64_t plane, int rank, int nranks, int64_t *begin,
+                                       int64_t *end) {
+    BIS_REQUIRE(begin && end && nranks >= 1 && rank >= 0 && rank < nranks && n_global >= 0, "bis_partition_row_block: bad argument");
+    bis_partition_rows(n_global, plane, rank, nranks, begin, end);
+    return 0;
+}
+
+// Reduction arguments without a slab layout (the launcher fills n_slab / slab_off / total_blocks).
 RedArgs bis_red_args(bis_context *c, int slot_a, int slot_b) {
     RedArgs ra;
     ra.partials = c->d_partials;
@@ -480,6 +595,10 @@ RedArgs bis_red_args(bis_context *c, int slot_a, int slot_b) {
     ra.block_offset = 0;
     ra.total_blocks = 0;
     ra.finalize = 1;
+    ra.n_slab = 1;
+    for (int i = 0; i <= BIS_NSLAB; ++i) ra.slab_off[i] = 0;
+    ra.n_rec = 1;
+    ra.rec_first = 0;
     ra.peer_n = 0;
     ra.peer_rank = c->rank;
     ra.peer_epoch = 0;
@@ -488,6 +607,38 @@ RedArgs bis_red_args(bis_context *c, int slot_a, int slot_b) {
     if (c->nranks > 1 && c->peer_on && c->opt_dist_p2p && (slot_a >= 0 || slot_b >= 0)) {
         ra.peer_n = c->nranks;
         ra.peer_epoch = ++c->red_epoch;
+        ra.n_rec = c->nranks;       // one record per rank unless bis_red_set_slabs finds the invariant layout
+        ra.rec_first = c->rank;
     }
     return ra;
+}
+
+// Slab layout of the partials: `off[i]` = first partial of local slab i (n_slab + 1 entries).  With an
+// invariant partition the 8 slab records are exchanged; otherwise the rank contributes one record.
+void bis_red_set_slabs(const bis_context *c, RedArgs &ra, const RowPartition &part, const int *off, int total) {
+    ra.total_blocks = total;
+    const bool inv = part.invariant && BIS_NSLAB % c->nranks == 0;
+    if (inv) {
+        ra.n_slab = part.n_slab;
+        for (int i = 0; i <= part.n_slab; ++i) ra.slab_off[i] = off[i];
+        for (int i = part.n_slab + 1; i <= BIS_NSLAB; ++i) ra.slab_off[i] = off[part.n_slab];
+        if (ra.peer_n > 1) {
+            ra.n_rec = BIS_NSLAB;
+            ra.rec_first = part.slab_first;
+        } else {
+            ra.n_rec = part.n_slab;   // one GPU: all 8; NCCL transport: the local slabs, then ncclAllReduce
+            ra.rec_first = 0;
+        }
+    } else {
+        ra.n_slab = 1;
+        ra.slab_off[0] = 0;
+        for (int i = 1; i <= BIS_NSLAB; ++i) ra.slab_off[i] = total;
+        if (ra.peer_n > 1) {
+            ra.n_rec = c->nranks;
+            ra.rec_first = c->rank;
+        } else {
+            ra.n_rec = 1;
+            ra.rec_first = 0;
+        }
+    }
 }

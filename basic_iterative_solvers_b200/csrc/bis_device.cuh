@@ -35,16 +35,27 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Block-wide sum of NRED accumulators, then the grid-wide deterministic
-// finish.  Must be called by ALL threads of the block (blockDim.x <= 1024,
-// multiple of 32).
+// Fixed combination of the records of a reduction: 8 records as a balanced tree, otherwise in order.
+__device__ __forceinline__ double combine_records(const double *r, int n) {
+    if (n == BIS_NSLAB) return ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += r[i];
+    return t;
+}
+
+// Block-wide sum of NRED accumulators (fixed shape: shuffle tree per warp, then a shuffle tree over the
+// warp sums), then the grid-wide deterministic finish described in bis_internal.cuh.  Must be called by
+// ALL threads of the block (blockDim.x <= 1024, multiple of 32).  `part_index`: where this block's
+// partial goes (block_offset + blockIdx.x for plain launches).
+template <int NRED> __device__ __forceinline__ void grid_reduce_finish(const RedArgs &ra);
+
 template <int NRED>
-__device__ __forceinline__ void block_reduce_finish(double (&acc)[NRED], const RedArgs &ra) {
+__device__ __forceinline__ void block_reduce_finish(double (&acc)[NRED], const RedArgs &ra, int part_index = -1) {
     __shared__ double s_part[NRED][32];
-    __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarp = (blockDim.x + 31) >> 5;
+    if (part_index < 0) part_index = ra.block_offset + (int)blockIdx.x;
 #pragma unroll
     for (int q = 0; q < NRED; ++q) {
         double v = warp_sum(acc[q]);
@@ -56,10 +67,21 @@ __device__ __forceinline__ void block_reduce_finish(double (&acc)[NRED], const R
         for (int q = 0; q < NRED; ++q) {
             double v = (lane < nwarp) ? s_part[q][lane] : 0.0;
             v = warp_sum(v);
-            if (lane == 0)
-                ra.partials[q * BIS_MAX_RED_BLOCKS + ra.block_offset + blockIdx.x] = v;
+            if (lane == 0) ra.partials[q * BIS_MAX_RED_BLOCKS + part_index] = v;
         }
     }
+    grid_reduce_finish<NRED>(ra);
+}
+
+// The grid-wide part: called by ALL threads of every block after thread 0 of the block has stored the
+// block's partial(s).
+template <int NRED>
+__device__ __forceinline__ void grid_reduce_finish(const RedArgs &ra) {
+    __shared__ double s_rec[NRED][BIS_NSLAB];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x + 31) >> 5;
     if (!ra.finalize) return;
     if (threadIdx.x == 0) {
         __threadfence();
@@ -69,40 +91,47 @@ __device__ __forceinline__ void block_reduce_finish(double (&acc)[NRED], const R
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last block: fixed-order sum of all partials
-    __shared__ double s_tot[NRED];
+    // last block: one warp per local slab adds that slab's partials in a fixed order that depends on
+    // nothing but the slab (lane l: l, l+32, ...; 8 independent loads in flight; then the shuffle tree)
+    for (int i = warp; i < ra.n_slab; i += nwarp) {
+        const int lo = ra.slab_off[i], hi = ra.slab_off[i + 1];
 #pragma unroll
-    for (int q = 0; q < NRED; ++q) {
-        double v = 0.0;
-        for (int i = threadIdx.x; i < ra.total_blocks; i += blockDim.x)
-            v += __ldcg(&ra.partials[q * BIS_MAX_RED_BLOCKS + i]);
-        v = warp_sum(v);
-        __syncthreads();
-        if (lane == 0) s_part[q][warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            double t = (lane < nwarp) ? s_part[q][lane] : 0.0;
-            t = warp_sum(t);
-            if (lane == 0) s_tot[q] = t;
+        for (int q = 0; q < NRED; ++q) {
+            const double *p = ra.partials + q * BIS_MAX_RED_BLOCKS;
+            double v = 0.0;
+            int j = lo + lane;
+            for (; j + 7 * 32 < hi; j += 8 * 32) {
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = __ldcg(p + j + u * 32);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v += t[u];
+            }
+            for (; j < hi; j += 32) v += __ldcg(p + j);
+            v = warp_sum(v);
+            if (lane == 0) s_rec[q][i] = v;
         }
     }
+    __syncthreads();
     if (warp != 0) return;
-    __syncwarp();
-    double t0 = s_tot[0], t1 = NRED > 1 ? s_tot[NRED > 1 ? 1 : 0] : 0.0;
+    double t0 = 0.0, t1 = 0.0;   // lane i: record i
     if (ra.peer_n > 1) {
-        // Sum over ranks through peer memory: lane p stores this rank's partial(s) into rank p's
-        // bank (NVLink store, then the epoch as the ready flag), then waits for rank p's record in
-        // the local bank.  Records alternate between two copies by epoch parity: a rank can only
-        // be one reduction ahead of the slowest one, because finishing a reduction needs everybody's
-        // record of it.  All ranks add the P partials in rank order => identical bits everywhere.
+        // Sum over ranks through peer memory.  The lanes of warp 0 carry (destination rank, local slab)
+        // pairs: this rank's slab sums go into every rank's bank (NVLink stores, then the epoch as the ready
+        // flag), then lane i waits for record i in the local bank.  Records alternate between two copies by
+        // epoch parity: a rank can only be one reduction ahead of the slowest one, because finishing a
+        // reduction needs everybody's records of it.  All ranks add the same records in the same order.
         const int par = (int)(ra.peer_epoch & 1ull);
-        if (lane < ra.peer_n) {
-            volatile double *rec = ra.peer_bank[lane] + (par * BIS_MAX_PEERS + ra.peer_rank) * 4;
-            rec[0] = t0;
-            rec[1] = t1;
+        if (lane < ra.peer_n * ra.n_slab) {
+            const int dst = lane / ra.n_slab, i = lane - dst * ra.n_slab;
+            volatile double *rec = ra.peer_bank[dst] + (par * BIS_NSLAB + ra.rec_first + i) * 4;
+            rec[0] = s_rec[0][i];
+            rec[1] = NRED > 1 ? s_rec[NRED > 1 ? 1 : 0][i] : 0.0;
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long *>(rec + 2) = ra.peer_epoch;
-            volatile double *in = ra.peer_bank[ra.peer_rank] + (par * BIS_MAX_PEERS + lane) * 4;
+        }
+        if (lane < ra.n_rec) {
+            volatile double *in = ra.peer_bank[ra.peer_rank] + (par * BIS_NSLAB + lane) * 4;
             const unsigned long long t_start = bis_globaltimer();
             while (*reinterpret_cast<volatile unsigned long long *>(in + 2) != ra.peer_epoch) {
                 if (bis_globaltimer() - t_start > BIS_PEER_TIMEOUT_NS) {
@@ -114,17 +143,19 @@ __device__ __forceinline__ void block_reduce_finish(double (&acc)[NRED], const R
             t0 = in[0];
             t1 = in[1];
         }
-        double a0 = 0.0, a1 = 0.0;
-        for (int p = 0; p < ra.peer_n; ++p) {
-            a0 += __shfl_sync(0xffffffffu, t0, p);
-            a1 += __shfl_sync(0xffffffffu, t1, p);
-        }
-        t0 = a0;
-        t1 = a1;
+    } else if (lane < ra.n_rec) {
+        t0 = s_rec[0][lane];
+        t1 = NRED > 1 ? s_rec[NRED > 1 ? 1 : 0][lane] : 0.0;
+    }
+    double r0[BIS_NSLAB], r1[BIS_NSLAB];
+#pragma unroll
+    for (int i = 0; i < BIS_NSLAB; ++i) {
+        r0[i] = __shfl_sync(0xffffffffu, t0, i);
+        r1[i] = __shfl_sync(0xffffffffu, t1, i);
     }
     if (lane == 0) {
-        if (ra.slot[0] >= 0) ra.scalars[ra.slot[0]] = t0;
-        if (NRED > 1 && ra.slot[NRED > 1 ? 1 : 0] >= 0) ra.scalars[ra.slot[NRED > 1 ? 1 : 0]] = t1;
+        if (ra.slot[0] >= 0) ra.scalars[ra.slot[0]] = combine_records(r0, ra.n_rec);
+        if (NRED > 1 && ra.slot[NRED > 1 ? 1 : 0] >= 0) ra.scalars[ra.slot[NRED > 1 ? 1 : 0]] = combine_records(r1, ra.n_rec);
         *ra.counter = 0u;
     }
 }

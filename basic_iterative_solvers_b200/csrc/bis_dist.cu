@@ -276,6 +276,24 @@ int bis_matrix_finalize_distributed(bis_context *c, bis_matrix *A, int *d_col_gl
                         "row blocks of ranks %d and %d are not contiguous", p - 1, p);
     }
     first[P] = meta[3 * (P - 1)] + meta[3 * (P - 1) + 1];
+    // the partition-invariant sum needs EVERY rank's row block to be a union of virtual slabs
+    if (c->part.n_global == A->n_rows_global) {
+        bool all = BIS_NSLAB % P == 0;
+        if (all) {
+            int64_t vb[BIS_NSLAB + 1];
+            int ch;
+            bis_partition_rule(A->n_rows_global, 0, vb, &ch);
+            for (int p = 0; p < P; ++p)
+                if (meta[3 * p] != vb[p * (BIS_NSLAB / P)] || meta[3 * p] + meta[3 * p + 1] != vb[(p + 1) * (BIS_NSLAB / P)]) all = false;
+        }
+        if (!all) {
+            c->part.invariant = false;
+            c->part.n_slab = 1;
+            c->part.slab_first = 0;
+            c->part.slab_row[0] = 0;
+            c->part.slab_row[1] = A->n_rows;
+        }
+    }
     BIS_REQUIRE(first[P] == A->n_rows_global, "row blocks cover %lld rows, matrix has %lld",
                 (long long)first[P], (long long)A->n_rows_global);
     A->nnz_global = nnz_g;
@@ -507,7 +525,6 @@ int bis_halo_fuse_args(bis_context *c, const bis_matrix *A, HaloFuse *hf) {
     a.ticket = c->d_pack_ticket;
     a.epoch = e;
     a.errflag = c->d_errflag;
-    a.ghost_from = 0; a.tile_split2 = 0; a.tile_lo3 = 0;   // set by the SpMV driver
     return 0;
 }
 

@@ -195,11 +195,34 @@ int build_levels(bis_context *c, bis_matrix *T) {
     BIS_CHECK(dalloc(&d_slot_of, (size_t)n));
     BIS_CUDA(cudaMemsetAsync(d_level, 0xFF, sizeof(int) * (size_t)n, st));
     BIS_CUDA(cudaMemsetAsync(lv.d_ticket, 0, sizeof(unsigned int), st));
+    // a flag left behind by an earlier kernel's watchdog would make waiting rows give up at once: it is
+    // reported (and cleared) here, before the analysis starts
+    int stale = 0;
+    BIS_CUDA(cudaMemcpyAsync(&stale, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BIS_CUDA(cudaStreamSynchronize(st));
+    if (stale) {
+        cudaMemsetAsync(c->d_errflag, 0, sizeof(int), st);
+        cudaFree(d_level);
+        cudaFree(d_slot_of);
+        bis_set_error("level analysis: an earlier kernel's device watchdog had fired (code %d)", stale);
+        return 3;
+    }
     levels_dataflow_kernel<RP><<<(unsigned)((n + FB - 1) / FB), FB, 0, st>>>(n, rp, T->d_col, upper, d_level, lv.d_ticket, c->d_errflag);
     BIS_LAUNCH_CHECK(c);
-    const int max_level = thrust::reduce(pol, thrust::device_pointer_cast(d_level), thrust::device_pointer_cast(d_level) + n,
-                                         -1, thrust::maximum<int>());
-    BIS_REQUIRE(max_level >= 0, "level analysis did not finish (device watchdog)");
+    // every row must have a level: a row that gave up keeps -1 and would index level_size[-1] below
+    auto lvl_b = thrust::device_pointer_cast(d_level);
+    const int max_level = thrust::reduce(pol, lvl_b, lvl_b + n, -1, thrust::maximum<int>());
+    const int min_level = thrust::reduce(pol, lvl_b, lvl_b + n, 0x7fffffff, thrust::minimum<int>());
+    int fired = 0;
+    BIS_CUDA(cudaMemcpyAsync(&fired, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BIS_CUDA(cudaStreamSynchronize(st));
+    if (min_level < 0 || max_level < 0 || fired) {
+        if (fired) cudaMemsetAsync(c->d_errflag, 0, sizeof(int), st);
+        cudaFree(d_level);
+        cudaFree(d_slot_of);
+        bis_set_error("level analysis did not finish for every row (device watchdog code %d)", fired);
+        return 3;
+    }
     lv.n_levels = max_level + 1;
     // (3) rows by (level, row): a stable sort of the row ids by level
     BIS_CUDA(cudaMemcpyAsync(lv.d_slot_level, d_level, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));

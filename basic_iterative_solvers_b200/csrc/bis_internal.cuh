@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdint>
@@ -65,20 +66,32 @@ void bis_set_error(const char *fmt, ...);
     } while (0)
 
 // ---- reductions -----------------------------------------------------------
-// Deterministic two-stage reduction: every block writes one partial per
-// reduced quantity; the last block to arrive (ticket counter) adds the
-// partials in a fixed order and writes the device scalar slot(s).
-constexpr int BIS_MAX_RED_BLOCKS = 8192;   // partials per quantity
+// Deterministic AND partition-invariant reductions (SURVEY.md 8(e) "cross-P reproducibility").
+//
+// The global rows are cut into BIS_NSLAB = 8 fixed "virtual slabs" (bis_partition_rule: the 8-GPU row
+// blocks); a rank of a P-GPU run (P | 8) owns 8/P consecutive slabs.  Every reducing kernel maps its
+// blocks onto rows by a rule that depends on the GLOBAL problem only (streaming kernels: block b <->
+// rows [b*chunk, (b+1)*chunk) of the global index space; windowed SpMV: CTA b of a fixed logical grid
+// <-> positions b, b+G, ... of the slab's tile order), so a block partial is the same number at
+// every rank count.  The last block to arrive adds the partials of each local slab in a fixed order
+// (lane l: partials l, l+32, ... then a shuffle tree), the 8 slab sums are exchanged through the peer
+// banks, and every rank adds ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7)): residual histories are bit-identical
+// at 1, 2, 4 and 8 GPUs.  Where the conditions do not hold (rank count not dividing 8, a caller's own
+// unaligned row blocks, the vector-CRS / TMA-gather SpMV variants) a rank contributes ONE record and
+// the records are added in rank order: deterministic for a given rank count, as in round 1.
+constexpr int BIS_MAX_RED_BLOCKS = 32768;  // partials per quantity
 constexpr int BIS_MAX_RED = 2;             // quantities per kernel
 constexpr int BIS_MAX_PEERS = 8;           // ranks a peer-memory link can span (one NVSwitch box)
+constexpr int BIS_NSLAB = 8;               // virtual slabs
+constexpr int BIS_RED_CHUNK_MIN = 1024;    // rows per block of a reducing streaming kernel (x 2^k)
 
 // Peer-memory link (bis_dist.cu): every rank owns a small "bank" that all other ranks of the
 // box map through CUDA IPC.  Dot products are summed over ranks by the last block of the
-// reducing kernel itself (it stores its partial into every peer's bank over NVLink and adds
-// the ranks' partials in rank order), and halo values are stored straight into the
+// reducing kernel itself (it stores its slab sums into every peer's bank over NVLink and adds
+// the 8 records in the fixed order), and halo values are stored straight into the
 // neighbour's ghost buffer by the pack kernel: no NCCL call on the iteration path.
-// Bank layout, in doubles: [0, 2*P*4) reduction records {v0, v1, epoch, -} indexed by
-// (epoch parity, source rank); BIS_BANK_HALO_FLAG + s: newest halo epoch whose values from
+// Bank layout, in doubles: [0, 2*8*4) reduction records {v0, v1, epoch, -} indexed by
+// (epoch parity, record index); BIS_BANK_HALO_FLAG + s: newest halo epoch whose values from
 // source s have landed; BIS_BANK_HALO_ACK + q: rank q has finished every SpMV before that epoch.
 constexpr int BIS_BANK_HALO_FLAG = 256;
 constexpr int BIS_BANK_HALO_ACK = 320;
@@ -92,12 +105,31 @@ struct RedArgs {
     int block_offset;        // first partial index written by this launch
     int total_blocks;        // partials to add when finalising
     int finalize;            // 0: only write partials (a later launch finalises)
+    // local slabs: slab i covers partials [slab_off[i], slab_off[i+1])
+    int n_slab;
+    int slab_off[BIS_NSLAB + 1];
+    // records: n_rec numbers are added in the fixed order; this rank produces [rec_first, rec_first + n_slab)
+    int n_rec;
+    int rec_first;
     // sum over ranks through peer memory (peer_n > 1), done by the finalising block
     int peer_n;
     int peer_rank;
     unsigned long long peer_epoch;
     double *peer_bank[BIS_MAX_PEERS];
     int *errflag;
+};
+
+// How the rows of the current problem are cut (set when a matrix is created; streaming kernels of
+// another length fall back to the default rule for that length).
+struct RowPartition {
+    int64_t n_global = 0;
+    int64_t row_begin = 0;
+    int64_t n_local = 0;
+    int chunk = BIS_RED_CHUNK_MIN;     // rows per block of a reducing streaming kernel
+    int n_slab = 1;                    // local virtual slabs (0 < n_slab <= 8)
+    int slab_first = 0;                // global index of the first local slab
+    int64_t slab_row[BIS_NSLAB + 1] = {};   // LOCAL row offsets of the local slab boundaries
+    bool invariant = false;            // the conditions of the partition-invariant sum hold
 };
 
 // Optional per-kernel-family device timing (bis_profile_enable): cudaEvent pairs
@@ -137,6 +169,7 @@ struct bis_context {
     unsigned long long halo_epoch = 0;              // halo exchanges so far (same on all ranks)
     unsigned int *d_pack_ticket = nullptr;
     std::vector<void *> ipc_opened;                 // mappings to close
+    RowPartition part;                              // bis_partition_set (bis_context.cu)
     int64_t launches = 0;
     int64_t chain_solves = 0;   // triangular solves that ran as variant 4 (bis_sptrsv_chain.cuh)
     // options
@@ -158,13 +191,16 @@ struct bis_context {
     int opt_trsv_debug = 0;     // dump per-row timestamps of each solve to $BIS_TRSV_DEBUG_FILE
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
-    int opt_spmv_debug = 0;     // perf experiments (results invalid when non-zero)
+    int opt_spmv_debug = 0;     // perf experiments (results invalid when non-zero); only in -DBIS_PERF_DEBUG builds
     int opt_win_rows = 0;       // variant 3: rows per tile (0 auto; fixed once a matrix's format is built)
     int opt_spmv_mult = 0;      // TMA variant: threads per tile row (1, 2, 4; 0 auto)
     int opt_spmv_blocked = 0;   // TMA variant: 1 = contiguous tile run per CTA instead of interleaved
     int opt_spmv_smem_kb = 0;   // TMA variant: shared-memory budget per CTA (0 auto)
+    int opt_spmv_l2_mb = 0;     // variant 3: matrix bytes streamed between two uses of an x plane above which the sweep is y-blocked (0: 40 MB)
     int profile = 0;
     ProfTag prof[BIS_PROF_NTAGS];
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remembered per context
+    std::unordered_map<const void *, size_t> smem_configured;
 };
 
 // Variant 4 of the triangular solve (bis_sptrsv_chain.cuh): sliced-ELL records of 32 chains per warp
@@ -229,8 +265,6 @@ struct HaloFuse {
     const int *send_idx;
     unsigned int *ticket;
     unsigned long long epoch;
-    int64_t ghost_from;                            // virtual tile index from which tiles read ghosts
-    int64_t tile_split2, tile_lo3;                 // third tile range: tile_lo3 + (v - tile_split2) for v >= tile_split2
     int *errflag;
 };
 
@@ -246,6 +280,13 @@ struct WinFormat {
     unsigned short *d_seg_off = nullptr;
     int *d_nseg = nullptr;
     unsigned short *d_lidx = nullptr;
+    // processing order of the tiles (bis_spmv.cu: win_build_order)
+    int *d_order = nullptr;        // [n_tiles]; bit 31: the tile reads ghosts
+    int n_slab = 1;                // local virtual slabs the order is cut into
+    int pos0[BIS_NSLAB + 1] = {};  // positions of slab i: [pos0[i], pos0[i+1])
+    bool invariant = false;        // per-(slab, CTA) partials are partition-invariant
+    int slab_first = 0;
+    int traversal_blocks = 1;      // y-blocks of the interior traversal (1: natural order)
 };
 
 struct bis_matrix {
@@ -260,6 +301,7 @@ struct bis_matrix {
     int *d_col = nullptr;      // local column ids (ghosts >= n_cols)
     double *d_val = nullptr;
     int triangular = 0;        // 0 general, 1 strictly lower, 2 strictly upper
+    int64_t grid_nx = 0, grid_ny = 0, grid_nz = 0;   // structured-grid hint of the generators (0: unknown)
     double mean_row = 0.0;
     int max_row = 0;
     mutable LevelSets lv;
@@ -271,6 +313,15 @@ struct bis_matrix {
 // ---- internal entry points shared between translation units ---------------
 int bis_reduce_finish(bis_context *ctx, int slot_a, int slot_b);
 RedArgs bis_red_args(bis_context *ctx, int slot_a, int slot_b);
+void bis_red_set_slabs(const bis_context *ctx, RedArgs &ra, const RowPartition &part, const int *off, int total);
+// 8 virtual slabs of a problem: vb[0..8] global row boundaries, *chunk rows per reducing block
+void bis_partition_rule(int64_t n_global, int64_t plane, int64_t vb[BIS_NSLAB + 1], int *chunk);
+// the row block of `rank` under that rule (unions of virtual slabs when nranks divides 8)
+void bis_partition_rows(int64_t n_global, int64_t plane, int rank, int nranks, int64_t *begin, int64_t *end);
+// records the partition of the matrix just created (plane = 0: no plane structure known)
+void bis_partition_set(bis_context *ctx, int64_t n_global, int64_t plane, int64_t row_begin, int64_t n_local);
+// partition to use for a streaming kernel over n local rows
+RowPartition bis_partition_for(const bis_context *ctx, int64_t n);
 int bis_halo_exchange_begin(bis_context *ctx, const bis_matrix *A, const double *x);
 int bis_halo_exchange_end(bis_context *ctx, const bis_matrix *A);
 // starts a halo exchange that the SpMV kernel itself performs: advances the epoch, selects the ghost copy
@@ -285,6 +336,8 @@ int bis_build_levels_device(bis_context *ctx, bis_matrix *T);
 int bis_matrix_stats(bis_context *ctx, bis_matrix *A);
 // builds the SpMV acceleration structure of a general matrix (bis_spmv.cu); lazy on first SpMV otherwise
 int bis_spmv_prepare(bis_context *ctx, const bis_matrix *A);
+// raises the dynamic shared memory limit of `func` on the context's device when it is below `bytes`
+int bis_ensure_dynamic_smem(bis_context *ctx, const void *func, size_t bytes);
 int bis_prof_begin(bis_context *ctx, int tag);
 int bis_prof_end(bis_context *ctx, int tag);
 
@@ -300,6 +353,15 @@ template <typename T> static inline cudaError_t bis_cuda_malloc(T **p, size_t by
     }
     return e;
 }
+
+// NVTX ranges named like the reference's LIKWID regions (kernels.hpp:25-40,56-75,90-106): "spmv",
+// "sptrsv", "backwards-sptrsv".  Without an attached tool a push/pop is a null-pointer check.
+struct BisNvtxRange {
+    explicit BisNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~BisNvtxRange() { nvtxRangePop(); }
+    BisNvtxRange(const BisNvtxRange &) = delete;
+    BisNvtxRange &operator=(const BisNvtxRange &) = delete;
+};
 
 static inline int bis_blocks_for(int64_t n, int per_block, int cap) {
     int64_t b = (n + per_block - 1) / per_block;

@@ -48,6 +48,7 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->win.d_seg_off);
     cudaFree(A->win.d_nseg);
     cudaFree(A->win.d_lidx);
+    cudaFree(A->win.d_order);
 }
 
 template <typename RP>
@@ -106,6 +107,7 @@ extern "C" int bis_matrix_upload_crs(bis_context *c, int64_t n_rows, int64_t n_c
     BIS_REQUIRE(!c || c->nranks == 1,
                 "bis_matrix_upload_crs: distributed context; use bis_matrix_upload_crs_distributed");
     BIS_CHECK(upload_common<int32_t>(c, n_rows, n_cols, nnz, rp, col, val, A));
+    bis_partition_set(c, n_rows, 0, 0, n_rows);
     return bis_spmv_prepare(c, *A);
 }
 
@@ -115,6 +117,7 @@ extern "C" int bis_matrix_upload_crs64(bis_context *c, int64_t n_rows, int64_t n
     BIS_REQUIRE(!c || c->nranks == 1,
                 "bis_matrix_upload_crs64: distributed context; use bis_matrix_upload_crs_distributed");
     BIS_CHECK(upload_common<int64_t>(c, n_rows, n_cols, nnz, rp, col, val, A));
+    bis_partition_set(c, n_rows, 0, 0, n_rows);
     return bis_spmv_prepare(c, *A);
 }
 
@@ -128,6 +131,7 @@ extern "C" int bis_matrix_upload_crs_distributed(bis_context *c, int64_t row_beg
     BIS_CHECK(upload_common<int64_t>(c, n_rows_local, n_rows_local, nnz_local, rp, col, val, &A));
     A->n_rows_global = n_rows_global;
     A->row_begin = row_begin;
+    bis_partition_set(c, n_rows_global, 0, row_begin, n_rows_local);
     if (bis_matrix_finalize_distributed(c, A, A->d_col) != 0) {
         free_matrix_storage(A);
         delete A;
@@ -288,23 +292,12 @@ __global__ void anderson_fill_kernel(AndersonP p, int64_t row_begin, int64_t n_l
 }
 
 void slab(int64_t n, int rank, int nranks, int64_t plane, int64_t *begin, int64_t *end) {
-    // contiguous row blocks; whole planes per rank when the plane count allows
-    // it (z-slabs), otherwise plain row blocks
-    int64_t planes = plane > 0 ? n / plane : 0;
-    if (plane > 0 && planes >= nranks) {
-        int64_t q = planes / nranks, r = planes % nranks;
-        int64_t b = rank * q + std::min<int64_t>(rank, r);
-        int64_t e = b + q + (rank < r ? 1 : 0);
-        *begin = b * plane;
-        *end = e * plane;
-    } else {
-        int64_t q = n / nranks, r = n % nranks;
-        *begin = rank * q + std::min<int64_t>(rank, r);
-        *end = *begin + q + (rank < r ? 1 : 0);
-    }
+    // unions of the 8 virtual slabs (bis_context.cu: bis_partition_rows)
+    bis_partition_rows(n, plane, rank, nranks, begin, end);
 }
 
 int finish_generated(bis_context *c, bis_matrix *A, bis_matrix **out) {
+    bis_partition_set(c, A->n_rows_global, 0, A->row_begin, A->n_rows);
     if (c->nranks > 1) {
         if (bis_matrix_finalize_distributed(c, A, A->d_col) != 0) {
             free_matrix_storage(A);
@@ -337,6 +330,7 @@ extern "C" int bis_matrix_generate_hpcg(bis_context *c, int nx, int ny, int nz, 
     A->nnz = nnz_local;
     A->nnz_global = hpcg_prefix(n, nx, ny, nz);
     A->max_row = (int)(std::min(nx, 3) * std::min(ny, 3) * std::min(nz, 3));
+    A->grid_nx = nx; A->grid_ny = ny; A->grid_nz = nz;
     A->mean_row = n_local ? (double)nnz_local / (double)n_local : 0.0;
     const bool wide = nnz_local >= (int64_t)INT32_MAX;
     A->rp_bytes = wide ? 8 : 4;
@@ -391,6 +385,7 @@ extern "C" int bis_matrix_generate_anderson(bis_context *c, int lx, int ly, int 
     A->nnz = nnz_local;
     A->nnz_global = nnz_local;   // fixed below for nranks > 1
     A->max_row = 7;
+    A->grid_nx = lx; A->grid_ny = ly; A->grid_nz = lz;
     A->mean_row = n_local ? (double)nnz_local / (double)n_local : 0.0;
     A->rp_bytes = 8;
     A->d_rp = d_rp64;

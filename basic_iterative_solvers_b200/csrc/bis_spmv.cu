@@ -27,6 +27,15 @@ namespace {
 
 constexpr int SPMV_THREADS = 256;
 
+// variants 1 and 2: one record per rank (deterministic for a given launch shape and rank count; the
+// partition-invariant sum is the windowed variant's and the streaming kernels', bis_internal.cuh)
+inline void red_set_plain(RedArgs &ra, int total) {
+    ra.total_blocks = total;
+    ra.n_slab = 1;
+    ra.slab_off[0] = 0;
+    for (int i = 1; i <= BIS_NSLAB; ++i) ra.slab_off[i] = total;
+}
+
 struct SpmvIn {
     const void *rp;
     const int *col;
@@ -148,7 +157,7 @@ int launch_one(bis_context *c, const SpmvIn &in, const Epi &epi, RedArgs &ra, in
     if (cap > BIS_MAX_RED_BLOCKS / 4) cap = BIS_MAX_RED_BLOCKS / 4;
     int blocks = bis_blocks_for(rows, rows_per_block, cap);
     *blocks_out = blocks;
-    if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + blocks;
+    if (Epi::NRED > 0 && ra.finalize) red_set_plain(ra, ra.block_offset + blocks);
     spmv_vec_kernel<RP, LPR, GHOST, Epi><<<blocks, SPMV_THREADS, 0, c->stream>>>(in, epi, ra);
     BIS_LAUNCH_CHECK(c);
     return 0;
@@ -222,11 +231,7 @@ bool tma_plan(const bis_context *c, const bis_matrix *A, tma::Plan *p) {
 template <typename RP, bool GHOST, class Epi>
 int launch_tma(bis_context *c, const tma::Plan &p, SpmvTmaIn in, const Epi &epi, RedArgs &ra, int *nb) {
     auto kern = spmv_tma_kernel<RP, GHOST, Epi>;
-    static size_t configured = 0;
-    if (configured < p.smem_bytes) {
-        BIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        configured = p.smem_bytes;
-    }
+    BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(kern), p.smem_bytes));
     int occ = 1;
     BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, p.threads, p.smem_bytes));
     if (occ < 1) occ = 1;
@@ -241,7 +246,7 @@ int launch_tma(bis_context *c, const tma::Plan &p, SpmvTmaIn in, const Epi &epi,
     in.interleave = c->opt_spmv_blocked ? 0 : 1;
     in.rows = p.rows;
     *nb = (int)grid;
-    if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + (int)grid;
+    if (Epi::NRED > 0 && ra.finalize) red_set_plain(ra, ra.block_offset + (int)grid);
     kern<<<(unsigned)grid, p.threads, p.smem_bytes, c->stream>>>(in, epi, ra);
     BIS_LAUNCH_CHECK(c);
     return 0;
@@ -250,7 +255,6 @@ int launch_tma(bis_context *c, const tma::Plan &p, SpmvTmaIn in, const Epi &epi,
 struct Segment {
     int64_t lo, cnt;
     bool ghost;
-    int64_t lo2 = 0, cnt2 = 0;   // variant 3 only: a second range handled by the same launch
 };
 
 // One contiguous row range with either variant.
@@ -285,7 +289,130 @@ namespace {
 int win_free(bis_matrix *A) {
     WinFormat &w = A->win;
     cudaFree(w.d_seg_start); cudaFree(w.d_seg_len); cudaFree(w.d_seg_off); cudaFree(w.d_nseg); cudaFree(w.d_lidx);
+    cudaFree(w.d_order);
     w.d_seg_start = nullptr; w.d_seg_len = nullptr; w.d_seg_off = nullptr; w.d_nseg = nullptr; w.d_lidx = nullptr;
+    w.d_order = nullptr;
+    return 0;
+}
+
+// ---- tile order (bis_spmv_win.cuh: WinOrderArgs) ---------------------------------------------------
+// flags of a tile relative to ITS virtual slab [lo, hi) (local rows): bit 0 some column below the slab,
+// bit 1 some column at or above its end, bit 2 some ghost column.  Ghost columns are ordered by global id:
+// the first n_low_ghost of them belong to lower ranks.  One warp per tile.
+template <typename RP>
+__global__ void __launch_bounds__(256) tile_flags_kernel(int64_t n_tiles, int R, int64_t n_rows, const RP *rp, const int *col,
+                                                         int n_owned, int n_low_ghost, int n_slab, const int64_t *slab_row,
+                                                         unsigned char *flags) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < n_tiles; t += (int64_t)gridDim.x * 8) {
+        const int64_t r0 = t * R;
+        int64_t r1 = r0 + R;
+        if (r1 > n_rows) r1 = n_rows;
+        int i = 0;
+        while (i + 1 < n_slab && r0 >= slab_row[i + 1]) ++i;
+        const int64_t lo = slab_row[i], hi = slab_row[i + 1];
+        unsigned int f = 0;
+        for (int64_t k = (int64_t)rp[r0] + lane; k < (int64_t)rp[r1]; k += 32) {
+            const int cc = col[k];
+            if (cc >= n_owned) f |= 4u | ((cc - n_owned) < n_low_ghost ? 1u : 2u);
+            else if (cc < lo) f |= 1u;
+            else if (cc >= hi) f |= 2u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, o);
+        if (lane == 0) flags[t] = (unsigned char)f;
+    }
+}
+
+// Builds the processing order of the tiles (see bis_spmv_win.cuh).  Host work is O(n_tiles).
+int win_build_order(bis_context *c, const bis_matrix *A) {
+    WinFormat &w = A->win;
+    const int64_t nt = w.n_tiles;
+    const int R = w.R;
+    // virtual slabs: the context's partition when it describes this matrix and its slabs start on tiles
+    RowPartition part = bis_partition_for(c, A->n_rows);
+    bool inv = part.invariant && part.n_global == A->n_rows_global && part.row_begin == A->row_begin && A->triangular == 0;
+    for (int i = 0; inv && i < part.n_slab; ++i)
+        if (part.slab_row[i] % R != 0) inv = false;
+    if (!inv) {
+        part.n_slab = 1;
+        part.slab_first = 0;
+        part.slab_row[0] = 0;
+        part.slab_row[1] = A->n_rows;
+    }
+    int64_t *d_slab = nullptr;
+    unsigned char *d_flags = nullptr;
+    BIS_CUDA(bis_cuda_malloc(&d_slab, sizeof(int64_t) * (BIS_NSLAB + 1)));
+    BIS_CUDA(bis_cuda_malloc(&d_flags, (size_t)nt));
+    BIS_CUDA(cudaMemcpyAsync(d_slab, part.slab_row, sizeof(int64_t) * (part.n_slab + 1), cudaMemcpyHostToDevice, c->stream));
+    const int n_low = A->distributed ? (int)A->halo.recv_off[c->rank] : 0;
+    const int blocks = bis_blocks_for(nt, 8, c->sm_count * 16);
+    if (A->rp_bytes == 8)
+        tile_flags_kernel<int64_t><<<blocks, 256, 0, c->stream>>>(nt, R, A->n_rows, static_cast<const int64_t *>(A->d_rp), A->d_col,
+                                                                  (int)A->n_cols, n_low, part.n_slab, d_slab, d_flags);
+    else
+        tile_flags_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(nt, R, A->n_rows, static_cast<const int32_t *>(A->d_rp), A->d_col,
+                                                                  (int)A->n_cols, n_low, part.n_slab, d_slab, d_flags);
+    BIS_LAUNCH_CHECK(c);
+    std::vector<unsigned char> flags((size_t)nt);
+    BIS_CUDA(cudaMemcpyAsync(flags.data(), d_flags, (size_t)nt, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_flags);
+    cudaFree(d_slab);
+    // y-blocked traversal of the interiors: between two uses of a plane of x (by the tiles of plane z-1, z
+    // and z+1) the grid streams two planes of matrix data; when that no longer fits the L2 the planes are
+    // cut into nb blocks of tiles and the slab is swept block by block through z (SpMV "x planes in L2").
+    int nb = 1;
+    int64_t Pt = 0, Bt = 0;
+    const int64_t plane = A->grid_nx * A->grid_ny;
+    if (plane > 0 && plane % R == 0 && A->row_begin % plane == 0) {
+        Pt = plane / R;
+        const double bytes_per_row = 10.0 * A->mean_row + 32.0;
+        const double budget = 1.0e6 * (c->opt_spmv_l2_mb > 0 ? c->opt_spmv_l2_mb : 40);   // bytes streamed between two uses of an x value
+        const double two_planes = 2.0 * (double)plane * bytes_per_row;
+        if (two_planes > budget) nb = (int)((two_planes + budget - 1) / budget);
+        if (nb > Pt) nb = (int)Pt;
+        Bt = (Pt + nb - 1) / nb;
+    }
+    w.traversal_blocks = nb;
+    std::vector<int> order;
+    order.reserve((size_t)nt);
+    std::vector<int> interior, lowv, highv;
+    const int64_t tile0 = A->row_begin / R;   // global index of local tile 0 (row_begin % R == 0 when invariant)
+    w.pos0[0] = 0;
+    for (int i = 0; i < part.n_slab; ++i) {
+        const int64_t t0 = part.slab_row[i] / R, t1 = (part.slab_row[i + 1] + R - 1) / R;
+        interior.clear(); lowv.clear(); highv.clear();
+        for (int64_t t = t0; t < t1; ++t) {
+            const unsigned char f = flags[(size_t)t];
+            const int e = (int)t | ((f & 4) ? WIN_ORDER_GHOST : 0);
+            if (f & 2) highv.push_back(e);
+            else if (f & 1) lowv.push_back(e);
+            else interior.push_back(e);
+        }
+        if (nb > 1) {
+            // key (block, plane), ascending tile inside: a stable counting pass per block keeps it O(n)
+            std::vector<int> tmp;
+            tmp.reserve(interior.size());
+            for (int b = 0; b < nb; ++b)
+                for (int e : interior) {
+                    const int64_t tg = tile0 + (e & ~WIN_ORDER_GHOST);
+                    if ((tg % Pt) / Bt == b) tmp.push_back(e);
+                }
+            interior.swap(tmp);
+        }
+        order.insert(order.end(), interior.begin(), interior.end());
+        order.insert(order.end(), lowv.begin(), lowv.end());
+        order.insert(order.end(), highv.begin(), highv.end());
+        w.pos0[i + 1] = (int)order.size();
+    }
+    for (int i = part.n_slab + 1; i <= BIS_NSLAB; ++i) w.pos0[i] = w.pos0[part.n_slab];
+    w.n_slab = part.n_slab;
+    w.slab_first = part.slab_first;
+    w.invariant = inv;
+    BIS_CUDA(bis_cuda_malloc(&w.d_order, sizeof(int) * (size_t)(nt > 0 ? nt : 1)));
+    BIS_CUDA(cudaMemcpyAsync(w.d_order, order.data(), sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -339,6 +466,10 @@ int win_build(bis_context *c, const bis_matrix *A) {
     w.xcap = (status[0] + 1) & ~1;
     if (w.xcap < 2) w.xcap = 2;
     w.n_tiles = n_tiles;
+    if (win_build_order(c, A) != 0) {
+        win_free(const_cast<bis_matrix *>(A));
+        return 1;
+    }
     w.state = 1;
     return 0;
 }
@@ -370,77 +501,62 @@ bool win_plan(const bis_context *c, const bis_matrix *A, WinPlan *p) {
     return true;
 }
 
-template <typename RP, class Epi>
-int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const double *x, int64_t tile_lo,
-               int64_t tile_cnt1, int64_t tile_lo2, int64_t tile_cnt2, const Epi &epi, RedArgs &ra, int *nb) {
-    const int64_t tile_cnt = tile_cnt1 + tile_cnt2;
-    auto kern = spmv_win_kernel<RP, Epi>;
-    static size_t configured = 0;
-    if (configured < p.smem_bytes) {
-        BIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        configured = p.smem_bytes;
-    }
+// One launch over all tiles in table order.  FUSED: the kernel also performs the halo exchange (pack +
+// publish before the sweep, the senders' flags checked at the first tile that reads ghosts).
+template <typename RP, class Epi, bool FUSED>
+int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const double *x, const Epi &epi, RedArgs &ra) {
+    auto kern = spmv_win_kernel<RP, Epi, FUSED>;
+    BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(kern), p.smem_bytes));
     const WinFormat &w = A->win;
     const int threads = w.R * p.nstage + 32;          // one consumer group per stage + the producer warp
     int occ = 1;
     BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, p.smem_bytes));
     if (occ < 1) occ = 1;
-    int64_t grid = (int64_t)c->sm_count * occ;
-    if (grid > tile_cnt) grid = tile_cnt;
+    // logical grid G: a property of the device and the tile shape, NOT of the tile count (partition invariance);
+    // fewer CTAs are launched when there are fewer tiles -- the missing ones would have had no work
+    const int G = c->sm_count * occ;
+    int64_t grid = G;
+    if (grid > w.n_tiles) grid = w.n_tiles;
     if (grid < 1) grid = 1;
     SpmvWinIn in;
     in.rp = A->d_rp; in.val = A->d_val; in.lidx = w.d_lidx;
     in.seg_start = w.d_seg_start; in.seg_len = w.d_seg_len; in.seg_off = w.d_seg_off; in.nseg = w.d_nseg;
-    in.x = x; in.ghost = A->halo.cur_ghost; in.n_rows = A->n_rows;
-    in.tile_lo = tile_lo; in.tile_cnt = tile_cnt; in.tile_split = tile_cnt1; in.tile_lo2 = tile_lo2;
+    in.x = x; in.n_rows = A->n_rows;
+    in.ord.order = w.d_order;
+    in.ord.n_slab = w.n_slab;
+    for (int i = 0; i <= BIS_NSLAB; ++i) in.ord.pos0[i] = w.pos0[i];
+    in.ord.G = G;
+    in.ord.part_stride = (int)grid;
     in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.stage_bytes = p.stage_bytes;
+#ifdef BIS_PERF_DEBUG
     in.debug = c->opt_spmv_debug;
-    *nb = (int)grid;
-    if (Epi::NRED > 0 && ra.finalize) ra.total_blocks = ra.block_offset + (int)grid;
-    kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra, NoHaloFuse{});
-    BIS_LAUNCH_CHECK(c);
-    return 0;
-}
-
-// The whole distributed SpMV in one launch: pack + publish, interior tiles, halo wait, boundary tiles,
-// fused reduction and its sum over ranks (bis_spmv_win.cuh, DIST = true).
-template <typename RP, class Epi>
-int launch_win_fused(bis_context *c, const bis_matrix *A, const WinPlan &p, const double *x, const Epi &epi,
-                     RedArgs &ra) {
-    auto kern = spmv_win_kernel<RP, Epi, true>;
-    static size_t configured = 0;
-    if (configured < p.smem_bytes) {
-        BIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        configured = p.smem_bytes;
-    }
-    const WinFormat &w = A->win;
-    const int threads = w.R * p.nstage + 32;
-    int occ = 1;
-    BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, p.smem_bytes));
-    if (occ < 1) occ = 1;
-    const int64_t n_tiles = w.n_tiles;
-    int64_t grid = (int64_t)c->sm_count * occ;   // all CTAs are resident: the pack phase counts them in
-    if (grid > n_tiles) grid = n_tiles;
-    if (grid < 1) grid = 1;
-    HaloFuse hf;
-    BIS_CHECK(bis_halo_fuse_args(c, A, &hf));
-    // tile order: interior [ib, ie), then the low strip [0, ib), then the high strip [ie, n_tiles)
-    int64_t ib = (A->halo.interior_begin + w.R - 1) / w.R, ie = A->halo.interior_end / w.R;
-    if (A->halo.n_ghost == 0) { ib = 0; ie = n_tiles; }
-    if (ie < ib) ie = ib;
-    SpmvWinIn in;
-    in.rp = A->d_rp; in.val = A->d_val; in.lidx = w.d_lidx;
-    in.seg_start = w.d_seg_start; in.seg_len = w.d_seg_len; in.seg_off = w.d_seg_off; in.nseg = w.d_nseg;
-    in.x = x; in.ghost = A->halo.cur_ghost; in.n_rows = A->n_rows;
-    in.tile_lo = ib; in.tile_cnt = n_tiles; in.tile_split = ie - ib; in.tile_lo2 = 0;
-    hf.tile_split2 = (ie - ib) + ib; hf.tile_lo3 = ie;
-    hf.ghost_from = ie - ib;
-    in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.stage_bytes = p.stage_bytes;
-    in.debug = c->opt_spmv_debug;
+#endif
     ra.finalize = 1;
     ra.block_offset = 0;
-    if (Epi::NRED > 0) ra.total_blocks = (int)grid;
-    kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra, hf);
+    if (Epi::NRED > 0) {
+        RowPartition part;
+        part.invariant = w.invariant;
+        part.n_slab = w.n_slab;
+        part.slab_first = w.slab_first;
+        int off[BIS_NSLAB + 1];
+        for (int i = 0; i <= w.n_slab; ++i) off[i] = i * (int)grid;
+        bis_red_set_slabs(c, ra, part, off, w.n_slab * (int)grid);
+        if (!w.invariant) {
+            // one record per rank, but the partials are still laid out per slab: add them all
+            ra.n_slab = 1;
+            ra.slab_off[0] = 0;
+            for (int i = 1; i <= BIS_NSLAB; ++i) ra.slab_off[i] = w.n_slab * (int)grid;
+        }
+    }
+    if constexpr (FUSED) {
+        HaloFuse hf;
+        BIS_CHECK(bis_halo_fuse_args(c, A, &hf));
+        in.ghost = A->halo.cur_ghost;
+        kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra, hf);
+    } else {
+        in.ghost = A->halo.cur_ghost;
+        kern<<<(unsigned)grid, threads, p.smem_bytes, c->stream>>>(in, epi, ra, NoHaloFuse{});
+    }
     BIS_LAUNCH_CHECK(c);
     return 0;
 }
@@ -457,6 +573,7 @@ template <class Epi>
 static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, const Epi &epi,
                        int slot_a, int slot_b) {
     BIS_REQUIRE(c && A && x, "spmv: null argument");
+    BisNvtxRange nvtx_range("spmv");
     BIS_CUDA(cudaSetDevice(c->device));
     RedArgs ra = bis_red_args(c, slot_a, slot_b);
     // variant: 3 (windowed x) when the matrix is representable and x is 16-byte aligned (the reference
@@ -470,9 +587,20 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     BIS_REQUIRE(use_win || c->opt_spmv_variant != 3,
                 "spmv_variant=3 forced, but the matrix has no window representation or x is not 16-byte aligned");
     BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPMV));
-    if (use_win && A->distributed && c->opt_spmv_fused && c->peer_on && c->opt_dist_p2p && A->halo.peer_ready) {
-        if (A->rp_bytes == 8) BIS_CHECK((launch_win_fused<int64_t, Epi>(c, A, wplan, x, epi, ra)));
-        else BIS_CHECK((launch_win_fused<int32_t, Epi>(c, A, wplan, x, epi, ra)));
+    if (use_win) {
+        const bool fused = A->distributed && c->opt_spmv_fused && c->peer_on && c->opt_dist_p2p && A->halo.peer_ready;
+        if (fused) {
+            if (A->rp_bytes == 8) BIS_CHECK((launch_win<int64_t, Epi, true>(c, A, wplan, x, epi, ra)));
+            else BIS_CHECK((launch_win<int32_t, Epi, true>(c, A, wplan, x, epi, ra)));
+        } else {
+            // separate exchange (NCCL transport, or spmv_fused = 0): the sweep starts when the ghosts are in
+            if (A->distributed) {
+                BIS_CHECK(bis_halo_exchange_begin(c, A, x));
+                BIS_CHECK(bis_halo_exchange_end(c, A));
+            }
+            if (A->rp_bytes == 8) BIS_CHECK((launch_win<int64_t, Epi, false>(c, A, wplan, x, epi, ra)));
+            else BIS_CHECK((launch_win<int32_t, Epi, false>(c, A, wplan, x, epi, ra)));
+        }
         BIS_CHECK(bis_prof_end(c, BIS_PROF_SPMV));
         if (Epi::NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));
         return 0;
@@ -483,8 +611,8 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     // every rank of a distributed matrix takes part in the exchange, also one that needs no ghosts
     const bool halo = A->distributed;
     const bool has_ghost = A->halo.n_ghost > 0;
-    const int64_t unit = use_win ? A->win.R : 1;
-    const int64_t n_units = use_win ? A->win.n_tiles : A->n_rows;
+    const int64_t unit = 1;
+    const int64_t n_units = A->n_rows;
     if (!halo) {
         seg[nseg++] = {0, n_units, false};
     } else {
@@ -496,34 +624,26 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
             seg[nseg++] = {0, n_units, false};
         } else if (ie > ib) {
             seg[nseg++] = {ib, ie - ib, false};
-            if (use_win && ib > 0 && n_units > ie) {
-                // both boundary strips in ONE launch (one ramp-up and one tail instead of two)
-                seg[nseg] = {0, ib, true};
-                seg[nseg].lo2 = ie;
-                seg[nseg].cnt2 = n_units - ie;
-                ++nseg;
-            } else {
-                if (ib > 0) seg[nseg++] = {0, ib, true};
-                if (n_units > ie) seg[nseg++] = {ie, n_units - ie, true};
-            }
+            if (ib > 0) seg[nseg++] = {0, ib, true};
+            if (n_units > ie) seg[nseg++] = {ie, n_units - ie, true};
         } else {
             seg[nseg++] = {0, n_units, true};
         }
     }
+    bool halo_ended = false;
     for (int i = 0; i < nseg; ++i) {
-        if (halo && seg[i].ghost && (i == 0 || !seg[i - 1].ghost)) BIS_CHECK(bis_halo_exchange_end(c, A));
+        if (halo && seg[i].ghost && (i == 0 || !seg[i - 1].ghost)) {
+            BIS_CHECK(bis_halo_exchange_end(c, A));
+            halo_ended = true;
+        }
         int nb = 0;
         ra.finalize = (i == nseg - 1) ? 1 : 0;
-        if (use_win) {
-            if (A->rp_bytes == 8)
-                BIS_CHECK((launch_win<int64_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, seg[i].lo2, seg[i].cnt2, epi, ra, &nb)));
-            else
-                BIS_CHECK((launch_win<int32_t, Epi>(c, A, wplan, x, seg[i].lo, seg[i].cnt, seg[i].lo2, seg[i].cnt2, epi, ra, &nb)));
-        } else {
-            BIS_CHECK(launch_segment(c, A, x, seg[i], epi, ra, &nb));
-        }
+        BIS_CHECK(launch_segment(c, A, x, seg[i], epi, ra, &nb));
         ra.block_offset += nb;
     }
+    // a rank without ghosts may still SEND (non-symmetric neighbour sets): the main stream must not
+    // overwrite x before the NCCL transport's pack on the comm stream has read it
+    if (halo && !halo_ended) BIS_CHECK(bis_halo_exchange_end(c, A));
     BIS_CHECK(bis_prof_end(c, BIS_PROF_SPMV));
     if (Epi::NRED > 0) BIS_CHECK(bis_reduce_finish(c, slot_a, slot_b));
     return 0;

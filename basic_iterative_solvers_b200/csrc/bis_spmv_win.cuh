@@ -168,13 +168,31 @@ __global__ void __launch_bounds__(WIN_BUILD_THREADS) win_build_kernel(WinBuildAr
     }
 }
 
+// ---- tile order ----------------------------------------------------------------------------------
+// The tiles of a launch are processed in the order of a table built once per matrix (bis_spmv.cu:
+// win_build_order): per local virtual slab first the tiles that only read columns of their own slab
+// (y-blocked through z when the grid is known and a plane of x no longer survives in L2 between its
+// uses), then the slab's low and high boundary strips.  The order depends on the GLOBAL problem only,
+// and CTA b of the logical grid G takes positions b, b + G, ... of every slab, so the per-(slab, CTA)
+// partial sums of a fused dot product are the same numbers at every rank count (bis_internal.cuh).
+// Bit 31 of an entry: the tile reads ghost values (the halo exchange must have landed).
+constexpr int WIN_ORDER_GHOST = (int)0x80000000u;
+
+struct WinOrderArgs {
+    const int *order;            // [n_tiles]
+    int n_slab;
+    int pos0[BIS_NSLAB + 1];     // positions [pos0[i], pos0[i+1]) belong to local slab i
+    int G;                       // logical grid (interleave stride)
+    int part_stride;             // partial of (slab i, CTA b) sits at i * part_stride + b
+};
+
 // ---- SpMV ----------------------------------------------------------------------------------------
 // Distributed SpMV as ONE kernel (peer-memory transport, bis_dist.cu): every CTA first packs its share
 // of the boundary values of x and stores them straight into the neighbours' ghost buffers (the CTA
-// that finishes last publishes the exchange's epoch in their banks), then the grid sweeps the interior
-// tiles, and a CTA's producer warp looks at the senders' flags only when it reaches its first tile that
-// reads ghosts -- by then the values have long arrived.  The fused dot product and its sum over ranks
-// (block_reduce_finish) close the same kernel.
+// that finishes last publishes the exchange's epoch in their banks), then the grid sweeps the tiles in
+// table order (interiors first), and a CTA's producer warp looks at the senders' flags only when it
+// reaches its first tile that reads ghosts -- by then the values have long arrived.  The fused dot
+// product and its sum over ranks (block_reduce_finish) close the same kernel.
 struct NoHaloFuse {};
 
 struct SpmvWinIn {
@@ -188,18 +206,52 @@ struct SpmvWinIn {
     const double *x;
     const double *ghost;
     int64_t n_rows;
-    int64_t tile_lo, tile_cnt;    // tiles handled by this launch: tile_lo + v for v < tile_split,
-    int64_t tile_split, tile_lo2; // tile_lo2 + (v - tile_split) above (both boundary strips of a row block in one launch)
+    WinOrderArgs ord;
     int R;                        // rows per tile == consumer threads
     int cap;                      // nonzeros per stage (multiple of 8)
     int xcap;                     // window doubles per stage (even)
     int nstage;
     int stage_bytes;
+#ifdef BIS_PERF_DEBUG
     int debug;                    // perf experiments only (results invalid): 1 = consumers skip the row walk, 2 = no x-window copies
+#endif
 };
+#ifdef BIS_PERF_DEBUG
+#define BIS_WIN_DEBUG(in, bit) ((in).debug & (bit))
+#else
+#define BIS_WIN_DEBUG(in, bit) 0
+#endif
 
 // stage layout: [val cap*8][xwin xcap*8][rp (R+4)*8][lidx cap*2], every part 16-byte aligned
 constexpr int WIN_MAX_THREADS = 320;   // consumer groups (R x nstage) + the producer warp
+
+// This CTA's sequence of tiles: the s-th one is position pos0[i] + b + (s - cum[i]) * G of slab i.
+struct WinSeq {
+    int cum[BIS_NSLAB + 1];
+    __device__ __forceinline__ void init(const WinOrderArgs &o, int b) {
+        cum[0] = 0;
+#pragma unroll
+        for (int i = 0; i < BIS_NSLAB; ++i) {
+            int c = 0;
+            if (i < o.n_slab) {
+                const int len = o.pos0[i + 1] - o.pos0[i];
+                c = len > b ? (len - b + o.G - 1) / o.G : 0;
+            }
+            cum[i + 1] = cum[i] + c;
+        }
+    }
+    __device__ __forceinline__ int total() const { return cum[BIS_NSLAB]; }
+    __device__ __forceinline__ int slab_of(int s) const {
+        int i = 0;
+#pragma unroll
+        for (int k = 1; k < BIS_NSLAB; ++k) i += (s >= cum[k]) ? 1 : 0;
+        return i;
+    }
+    __device__ __forceinline__ int pos(const WinOrderArgs &o, int b, int s) const {
+        const int i = slab_of(s);
+        return o.pos0[i] + b + (s - cum[i]) * o.G;
+    }
+};
 
 template <typename RP, class Epi, bool DIST = false>
 __global__ void __launch_bounds__(WIN_MAX_THREADS, 2)
@@ -217,9 +269,9 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
     const bool producer = warp == n_cons_warps * in.nstage;       // the last warp
     const int group = warp / n_cons_warps;
     const int tid_g = (int)threadIdx.x - group * R;   // thread index inside its group
-    // static tile -> CTA map: CTA b takes tiles b, b + grid, ... (all CTAs sweep the matrix together,
-    // so the x windows they fetch are shared in L2)
-    const int64_t my_tiles = in.tile_cnt > blockIdx.x ? (in.tile_cnt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    WinSeq seq;
+    seq.init(in.ord, (int)blockIdx.x);
+    const int my_tiles = seq.total();
 
     double acc[Epi::NRED > 0 ? Epi::NRED : 1];
 #pragma unroll
@@ -276,55 +328,57 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
         uint64_t pol_keep;
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
         // What this lane copies for one tile: lane 0 val, lane 1 lidx, lane 2 the row_ptr slice,
-        // lanes 3.. one x window each.  The descriptors come from global memory (row_ptr and the
-        // window table), so they are requested PDEPTH tiles ahead: the producer never sits on a
-        // global-load latency between two tiles.
-        // Raw descriptor words are only LOADED ahead of time; nothing is computed from them until
-        // the tile is issued (a dependent instruction right after the load would stall the warp for
-        // a full memory latency per tile and serialise the whole pipeline).
+        // lanes 3.. one x window each.  Everything the copies are described by comes from global
+        // memory -- the tile id from the order table, then row_ptr and the window table -- so the
+        // tile ids are requested 2*PDEPTH and the descriptors PDEPTH tiles ahead: the producer never
+        // sits on a global-load latency between two tiles.
+        // Raw words are only LOADED ahead of time; nothing is computed from them until the next
+        // pipeline step (a dependent instruction right after a load would stall the warp for a full
+        // memory latency per tile and serialise the whole pipeline).
         struct Desc {
             RP a, b;                 // rp[r0], rp[r1]            (lanes 0, 1)
             int start;               // window start              (lanes 3..)
             unsigned short len, off; // window length / offset    (lanes 3..)
+            int tile;                // raw order entry
         };
         const uint32_t off_xw = (uint32_t)in.cap * 8u;
         const uint32_t off_rp = off_xw + (uint32_t)in.xcap * 8u;
         const uint32_t off_li = off_rp + (uint32_t)(R + 4) * 8u;
-        auto tile_rows = [&](int64_t j, int64_t &tile, int64_t &r0, int64_t &r1) {
-            const int64_t v = blockIdx.x + j * gridDim.x;
-            tile = v < in.tile_split ? in.tile_lo + v : in.tile_lo2 + (v - in.tile_split);
-            if constexpr (DIST) {
-                if (v >= hf.tile_split2) tile = hf.tile_lo3 + (v - hf.tile_split2);
-            }
-            r0 = tile * R;
+        auto tile_rows = [&](int tile, int64_t &r0, int64_t &r1) {
+            r0 = (int64_t)tile * R;
             r1 = r0 + R;
             if (r1 > in.n_rows) r1 = in.n_rows;
         };
+        auto load_order = [&](int s) -> int {
+            return s < my_tiles ? in.ord.order[seq.pos(in.ord, (int)blockIdx.x, s)] : 0;
+        };
         // loads only -- no conversion, no arithmetic on the loaded words (see above)
-        auto load_desc = [&](int64_t j, Desc &d) {
+        auto load_desc = [&](int s, int raw, Desc &d) {
             d.a = 0;
             d.b = 0;
             d.start = 0;
             d.len = 0;
             d.off = 0;
-            if (j >= my_tiles) return;
-            int64_t tile, r0, r1;
-            tile_rows(j, tile, r0, r1);
+            d.tile = raw;
+            if (s >= my_tiles) return;
+            const int tile = raw & ~WIN_ORDER_GHOST;
+            int64_t r0, r1;
+            tile_rows(tile, r0, r1);
             if (lane < 2) {
                 d.a = rp[r0];
                 d.b = rp[r1];
             } else if (lane >= 3 && lane - 3 < WIN_MAXSEG) {
-                const int64_t q = tile * WIN_MAXSEG + (lane - 3);
+                const int64_t q = (int64_t)tile * WIN_MAXSEG + (lane - 3);
                 d.start = in.seg_start[q];
                 d.len = in.seg_len[q];
                 d.off = in.seg_off[q];
             }
         };
         [[maybe_unused]] bool halo_seen = false;
-        auto issue = [&](int64_t j, const Desc &d) {
+        auto issue = [&](int s, const Desc &d) {
             if constexpr (DIST) {
                 // first tile of this CTA that reads ghosts: the senders' values must have landed
-                if (!halo_seen && (int64_t)blockIdx.x + j * gridDim.x >= hf.ghost_from) {
+                if (!halo_seen && (d.tile & WIN_ORDER_GHOST)) {
                     for (int q = 0; q < hf.n_src; ++q) {
                         const volatile unsigned long long *f = hf.flag_in + hf.src_rank[q];
                         const unsigned long long t0 = bis_globaltimer();
@@ -341,9 +395,9 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
                     halo_seen = true;
                 }
             }
-            const int st = (int)(j % in.nstage);
-            int64_t tile, r0, r1;
-            tile_rows(j, tile, r0, r1);
+            const int st = s % in.nstage;
+            int64_t r0, r1;
+            tile_rows(d.tile & ~WIN_ORDER_GHOST, r0, r1);
             const void *src = nullptr;
             uint32_t bytes = 0, dst = 0;
             if (lane < 2) {
@@ -361,7 +415,7 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
                 src = rp + r0;
                 bytes = (uint32_t)(((r1 - r0 + 1) + 3) & ~(int64_t)3) * (uint32_t)sizeof(RP);
                 dst = off_rp;
-            } else if (d.len && !(in.debug & 2)) {
+            } else if (d.len && !BIS_WIN_DEBUG(in, 2)) {
                 src = d.start >= 0 ? in.x + d.start : in.ghost + (~d.start);
                 bytes = (uint32_t)d.len * 8u;
                 dst = off_xw + (uint32_t)d.off * 8u;
@@ -370,37 +424,74 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             // the stage must have been released by every consumer warp
-            if (j >= in.nstage) tma::mbar_wait(&empty[st], (uint32_t)(((j / in.nstage) - 1) & 1));
+            if (s >= in.nstage) tma::mbar_wait(&empty[st], (uint32_t)(((s / in.nstage) - 1) & 1));
             unsigned char *sb = stages + (size_t)st * in.stage_bytes;
             if (lane == 0) tma::mbar_expect_tx(&full[st], total);
             __syncwarp();
             if (bytes) tma::bulk_g2s(sb + dst, src, bytes, &full[st], lane < 3 ? pol_stream : pol_keep);
         };
         constexpr int PDEPTH = 4;
-        Desc d0, d1, d2, d3;
-        load_desc(0, d0);
-        load_desc(1, d1);
-        load_desc(2, d2);
-        load_desc(3, d3);
-        for (int64_t j = 0; j < my_tiles; j += PDEPTH) {
-            issue(j, d0);
-            load_desc(j + PDEPTH, d0);
-            if (j + 1 < my_tiles) issue(j + 1, d1);
-            load_desc(j + PDEPTH + 1, d1);
-            if (j + 2 < my_tiles) issue(j + 2, d2);
-            load_desc(j + PDEPTH + 2, d2);
-            if (j + 3 < my_tiles) issue(j + 3, d3);
-            load_desc(j + PDEPTH + 3, d3);
+        int tq[2 * PDEPTH];     // order entries of tiles s .. s + 7
+        Desc dq[PDEPTH];        // descriptors of tiles s .. s + 3
+#pragma unroll
+        for (int u = 0; u < 2 * PDEPTH; ++u) tq[u] = load_order(u);
+#pragma unroll
+        for (int u = 0; u < PDEPTH; ++u) load_desc(u, tq[u], dq[u]);
+        for (int s0 = 0; s0 < my_tiles; s0 += 2 * PDEPTH) {
+#pragma unroll
+            for (int u = 0; u < 2 * PDEPTH; ++u) {
+                const int s = s0 + u;
+                if (s < my_tiles) issue(s, dq[u % PDEPTH]);
+                // slot u of tq held tile s: refill it with tile s + 8; the descriptor slot takes tile s + 4,
+                // whose id was requested at least four tiles ago
+                load_desc(s + PDEPTH, tq[(u + PDEPTH) % (2 * PDEPTH)], dq[u % PDEPTH]);
+                tq[u] = load_order(s + 2 * PDEPTH);
+            }
         }
     } else {
-        for (int64_t j = group; j < my_tiles; j += in.nstage) {
-            const int st = group;
-            const int64_t v = blockIdx.x + j * gridDim.x;
-            int64_t tile = v < in.tile_split ? in.tile_lo + v : in.tile_lo2 + (v - in.tile_split);
-            if constexpr (DIST) {
-                if (v >= hf.tile_split2) tile = hf.tile_lo3 + (v - hf.tile_split2);
+        [[maybe_unused]] int cur_slab = 0;
+        // the slab-end partial of a fused reduction is formed by the consumer warps alone (the producer
+        // is still copying): consumer-only named barrier, warp sums parked by LOGICAL warp (the group that
+        // took the slab's first tile counts as group 0, so the sum is independent of where in this CTA's
+        // sequence the slab starts), two parities so that one barrier per slab suffices
+        __shared__ double s_wsum[2][Epi::NRED > 0 ? Epi::NRED : 1][32];
+        const int n_cons_threads = R * in.nstage;
+        auto close_slab = [&](int slab) {
+            if constexpr (Epi::NRED > 0) {
+                const int par = slab & 1;
+                const int g0 = seq.cum[slab] % in.nstage;                    // group that got the slab's first tile
+                const int lgroup = (group - g0 + in.nstage) % in.nstage;
+                const int lwarp = lgroup * n_cons_warps + (warp - group * n_cons_warps);
+#pragma unroll
+                for (int q = 0; q < Epi::NRED; ++q) {
+                    const double v = warp_sum(acc[q]);
+                    if (lane == 0) s_wsum[par][q][lwarp] = v;
+                    acc[q] = 0.0;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(n_cons_threads) : "memory");
+                if (warp == 0) {
+                    const int nw = n_cons_warps * in.nstage;
+#pragma unroll
+                    for (int q = 0; q < Epi::NRED; ++q) {
+                        double v = lane < nw ? s_wsum[par][q][lane] : 0.0;
+                        v = warp_sum(v);
+                        if (lane == 0)
+                            ra.partials[q * BIS_MAX_RED_BLOCKS + ra.block_offset + slab * in.ord.part_stride + (int)blockIdx.x] = v;
+                    }
+                }
             }
-            const int64_t row = tile * R + tid_g;
+        };
+        int raw_next = group < my_tiles ? in.ord.order[seq.pos(in.ord, (int)blockIdx.x, group)] : 0;
+        for (int s = group; s < my_tiles; s += in.nstage) {
+            const int st = group;
+            const int tile = raw_next & ~WIN_ORDER_GHOST;
+            if constexpr (Epi::NRED > 0) {
+                const int slab = seq.slab_of(s);
+                while (cur_slab < slab) close_slab(cur_slab++);
+            }
+            // the next tile's id is requested a whole tile ahead
+            if (s + in.nstage < my_tiles) raw_next = in.ord.order[seq.pos(in.ord, (int)blockIdx.x, s + in.nstage)];
+            const int64_t row = (int64_t)tile * R + tid_g;
             const unsigned char *sb = stages + (size_t)st * in.stage_bytes;
             const double *__restrict__ sval = reinterpret_cast<const double *>(sb);
             const double *__restrict__ sxw = sval + in.cap;
@@ -409,8 +500,8 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
                 reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(srp) + (size_t)(R + 4) * 8);
             EpiPre pre{0.0, 0.0, 0.0};
             if (row < in.n_rows) pre = epi.load(row);   // in flight during the wait and the row walk
-            tma::mbar_wait(&full[st], (uint32_t)((j / in.nstage) & 1));
-            if (row < in.n_rows && !(in.debug & 1)) {
+            tma::mbar_wait(&full[st], (uint32_t)((s / in.nstage) & 1));
+            if (row < in.n_rows && !BIS_WIN_DEBUG(in, 1)) {
                 const int64_t base = (int64_t)srp[0] & ~(int64_t)7;
                 const int ks = (int)((int64_t)srp[tid_g] - base);
                 const int ke = (int)((int64_t)srp[tid_g + 1] - base);
@@ -432,6 +523,9 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
             __syncwarp();
             if (lane == 0) tma::mbar_arrive(&empty[st]);
         }
+        if constexpr (Epi::NRED > 0) {
+            while (cur_slab < in.ord.n_slab) close_slab(cur_slab++);
+        }
     }
-    if constexpr (Epi::NRED > 0) block_reduce_finish<Epi::NRED>(acc, ra);
+    if constexpr (Epi::NRED > 0) grid_reduce_finish<Epi::NRED>(ra);
 }

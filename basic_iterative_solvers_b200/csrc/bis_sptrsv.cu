@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a, 
                 while (ld_volatile_u32(a.level_done + (lv - 1)) < need) {
                     if ((++spins & 1023u) == 0) {
                         if (*reinterpret_cast<volatile int *>(a.errflag)) break;
-                        if (clock64() - t0 > 6000000000LL) {   // ~3 s: something is broken
+                        if (clock64() - t0 > 120000000000LL) {   // ~60 s: something is broken
                             atomicExch(a.errflag, 1);
                             break;
                         }
@@ -149,6 +149,9 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a, 
 // and rows far ahead of the wavefront wait on their "gates" (bis_matrix.cu) with long sleeps instead of
 // polling every operand.
 constexpr unsigned long long TRSV_SENTINEL = 0xFFF87E5E7E5E7E5EULL;
+// watchdog: 60 s WITHOUT PROGRESS (the timer restarts whenever an operand arrives), the rule of the
+// factor kernels -- a healthy solve under compute-sanitizer, ncu replay or time-slicing must not trip it
+constexpr unsigned long long TRSV_WATCHDOG_NS = 60000000000ull;
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
     unsigned long long v;
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(THREADS) sptrsv_flag_kernel(TrsvArgs a, double
                 if ((++spins & 1023u) == 0) {
                     if (t_gate == 0) t_gate = bis_globaltimer();
                     if (*reinterpret_cast<volatile int *>(a.errflag)) break;
-                    if (bis_globaltimer() - t_gate > 3000000000ull) {
+                    if (bis_globaltimer() - t_gate > TRSV_WATCHDOG_NS) {
                         atomicExch(a.errflag, 2);
                         break;
                     }
@@ -241,12 +244,14 @@ __global__ void __launch_bounds__(THREADS) sptrsv_flag_kernel(TrsvArgs a, double
         // warp-uniform wait: the warp moves on when every row of this level has its operands
         for (;;) {
             if (mine && miss) {
+                const unsigned int before = miss;
 #pragma unroll
                 for (int j = 0; j < TRSV_PF; ++j)
                     if (miss & (1u << j)) xv[j] = ld_relaxed_u64(w + cv[j]);
 #pragma unroll
                 for (int j = 0; j < TRSV_PF; ++j)
                     if (xv[j] != TRSV_SENTINEL) miss &= ~(1u << j);
+                if (miss != before) t_wd = 0;   // progress
             }
             if (__all_sync(0xffffffffu, !mine || miss == 0u)) break;
             if (a.dbg && spins == 0) ts_first = bis_globaltimer();
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(THREADS) sptrsv_flag_kernel(TrsvArgs a, double
             bool give_up = false;
             if ((++spins & 4095u) == 0) {
                 if (t_wd == 0) t_wd = bis_globaltimer();
-                give_up = *reinterpret_cast<volatile int *>(a.errflag) != 0 || bis_globaltimer() - t_wd > 3000000000ull;
+                give_up = *reinterpret_cast<volatile int *>(a.errflag) != 0 || bis_globaltimer() - t_wd > TRSV_WATCHDOG_NS;
             }
             if (__any_sync(0xffffffffu, give_up)) {
                 atomicExch(a.errflag, 1);
@@ -262,25 +267,36 @@ __global__ void __launch_bounds__(THREADS) sptrsv_flag_kernel(TrsvArgs a, double
                 break;
             }
         }
-        if (mine) {
+        // a warp that gave up publishes nothing: its rows stay "not ready" and their readers give up too
+        if (mine && ok) {
             if (a.dbg) ts1 = bis_globaltimer();
             double sum = 0.0;
 #pragma unroll
             for (int j = 0; j < TRSV_PF; ++j)
                 if (cv[j] >= 0) sum = add_rn(sum, mul_rn(av[j], __longlong_as_double((long long)xv[j])));
-            for (int64_t k = s + TRSV_PF; ok && k < e; ++k) {   // rows longer than the register window
-                unsigned long long t;
+            bool tail_ok = true;
+            for (int64_t k = s + TRSV_PF; tail_ok && k < e; ++k) {   // rows longer than the register window
+                unsigned long long t, t_tail = 0;
                 unsigned int sp2 = 0;
                 while ((t = ld_relaxed_u64(w + a.col[k])) == TRSV_SENTINEL) {
-                    if ((++sp2 & 0xfffffu) == 0 && *reinterpret_cast<volatile int *>(a.errflag)) break;
+                    if ((++sp2 & 0xffffu) == 0) {
+                        if (t_tail == 0) t_tail = bis_globaltimer();
+                        if (*reinterpret_cast<volatile int *>(a.errflag) || bis_globaltimer() - t_tail > TRSV_WATCHDOG_NS) {
+                            atomicExch(a.errflag, 1);
+                            tail_ok = false;
+                            break;
+                        }
+                    }
                 }
                 sum = add_rn(sum, mul_rn(a.val[k], __longlong_as_double((long long)t)));
             }
             const double r = div_rn(sub_rn(bb, sum), dd);
             // publish: the value doubles as the flag.  A result that IS the sentinel pattern cannot occur
             // (hardware NaNs are canonical), so readers can never mistake a result for "not ready".
-            __stcg(w + slot, r);
-            a.x[row] = r;
+            if (tail_ok) {
+                __stcg(w + slot, r);
+                a.x[row] = r;
+            }
             if (a.dbg) {
                 ts2 = bis_globaltimer();
                 a.dbg[4 * (int64_t)row] = ts0;       // the row's level came up in its warp
@@ -417,6 +433,7 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
                 "sptrsv: matrix is not the %s strictly-triangular factor this call needs",
                 want_kind == 1 ? "lower" : "upper");
     BIS_REQUIRE(!T->distributed, "sptrsv: triangular sweeps do not shard (single-GPU only)");
+    BisNvtxRange nvtx_range(want_kind == 1 ? "sptrsv" : "backwards-sptrsv");
     BIS_CUDA(cudaSetDevice(c->device));
     LevelSets &lv = T->lv;
     if (T->n_rows == 0) return 0;

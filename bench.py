@@ -130,15 +130,10 @@ class ClockSampler:
 
 
 def slab_rows(n: int, nz_planes: int, plane: int, rank: int, nranks: int):
-    """Row block of `rank`: whole z-planes (csrc/bis_matrix.cu: slab())."""
-    if nz_planes >= nranks:
-        q, r = divmod(nz_planes, nranks)
-        b = rank * q + min(rank, r)
-        e = b + q + (1 if rank < r else 0)
-        return b * plane, e * plane
-    q, r = divmod(n, nranks)
-    b = rank * q + min(rank, r)
-    return b, b + q + (1 if rank < r else 0)
+    """Row block of `rank`: the library's own rule (bis_partition_row_block: unions of 8 fixed virtual
+    slabs when nranks divides 8, which makes the reductions partition-invariant)."""
+    from basic_iterative_solvers_b200 import capi
+    return capi.partition_row_block(n, plane, rank, nranks)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -96,6 +96,13 @@ int bis_flush_l2(bis_context *ctx);
 /* Tuning knobs (all have defaults): key = "spmv_variant" (0 auto, 1 vector
  * CRS, 2 TMA-staged), "spmv_lanes" (0 auto, 2..32), "graph" (0/1). */
 int bis_context_set_option(bis_context *ctx, const char *key, int value);
+/* Row block [begin, end) of `rank` in an n_global-row problem split over `nranks` GPUs: the rule the
+ * generators use (unions of 8 fixed virtual slabs when nranks divides 8, so that reductions add the
+ * same partial sums in the same order at 1, 2, 4 and 8 GPUs; `plane` = rows per grid plane or 0, only
+ * used for rank counts that do not divide 8).  Pure function, no device needed.  New in the build:
+ * the reference is single-process. */
+int bis_partition_row_block(int64_t n_global, int64_t plane, int rank, int nranks,
+                            int64_t *begin /* [host] */, int64_t *end /* [host] */);
 
 /* ---- vectors ------------------------------------------------------------ */
 /* Replaces `new double[N]` / `delete[]` in Solver::allocate_structs and the

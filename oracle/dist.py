@@ -16,8 +16,34 @@ import torch.distributed as dist
 from . import port
 
 
+NSLAB = 8            # virtual slabs (csrc/bis_internal.cuh: BIS_NSLAB)
+RED_CHUNK_MIN = 1024
+
+
+def partition_rule(n: int):
+    """csrc/bis_context.cu bis_partition_rule(): the 8 virtual slabs of an n-row problem and the rows per
+    block of a reducing streaming kernel.  Equal row blocks rounded up to whole chunks (whole z-planes
+    whenever an eighth of the rows is a whole number of chunks, as for HPCG-128/256/512)."""
+    ch = 1
+    while ch < (n + 16383) // 16384:
+        ch <<= 1
+    ch = min(max(ch, RED_CHUNK_MIN), 1 << 20)
+    per = (n + NSLAB - 1) // NSLAB
+    for unit in (ch, 128):          # whole chunks, else whole SpMV tiles, else exact: never an empty slab
+        r = (per + unit - 1) // unit * unit
+        if r * (NSLAB - 1) < n:
+            per = r
+            break
+    return [min(n, per * v) for v in range(NSLAB + 1)], ch
+
+
 def slab(n: int, planes: int, plane: int, rank: int, nranks: int):
-    """csrc/bis_matrix.cu slab(): whole planes per rank when there are enough of them."""
+    """csrc/bis_context.cu bis_partition_rows(): unions of the virtual slabs when nranks divides 8,
+    otherwise contiguous blocks (whole planes per rank when there are enough of them)."""
+    if nranks >= 1 and NSLAB % nranks == 0:
+        vb, _ = partition_rule(n)
+        per = NSLAB // nranks
+        return vb[rank * per], vb[(rank + 1) * per]
     if plane > 0 and planes >= nranks:
         q, r = divmod(planes, nranks)
         b = rank * q + min(rank, r)

@@ -53,7 +53,8 @@ def _worker(rank, world, port_no, dims, q):
         ghost_rows = np.unique(rows[plan.col >= plan.n])
         assert not ((ghost_rows >= ib) & (ghost_rows < ie)).any()
         # z-slab halo: one plane per neighbour
-        expect = (nx * ny) * ((1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)) if nz >= world else None
+        plane_aligned = nz >= world and lo % (nx * ny) == 0 and hi % (nx * ny) == 0
+        expect = (nx * ny) * ((1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)) if plane_aligned else None
         if expect is not None:
             assert plan.ghost_global.size == expect
         diag = np.full(hi - lo, 26.0)
