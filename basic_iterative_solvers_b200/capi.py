@@ -46,6 +46,13 @@ _SIGS = {
     "bis_profile_enable": ([c_ctx, cint], cint),
     "bis_profile_read": ([c_ctx, C.c_char_p, C.POINTER(dbl), C.POINTER(i64)], cint),
     "bis_context_set_option": ([c_ctx, C.c_char_p, cint], cint),
+    "bis_context_get_option": ([c_ctx, C.c_char_p, C.POINTER(cint)], cint),
+    "bis_graph_begin": ([c_ctx], cint),
+    "bis_graph_end": ([c_ctx, C.POINTER(C.c_void_p)], cint),
+    "bis_graph_abort": ([c_ctx], cint),
+    "bis_graph_launch": ([c_ctx, C.c_void_p], cint),
+    "bis_graph_free": ([c_ctx, C.c_void_p], cint),
+    "bis_dist_wait_read": ([c_ctx, C.POINTER(dbl), cint], cint),
     "bis_partition_row_block": ([i64, i64, cint, cint, C.POINTER(i64), C.POINTER(i64)], cint),
     "bis_vector_alloc": ([c_ctx, i64, C.POINTER(c_dev)], cint),
     "bis_vector_free": ([c_ctx, c_dev], cint),
@@ -337,6 +344,12 @@ class Context:
         return r.value
 
     # timing ------------------------------------------------------------------
+    def dist_wait_read(self, reset: bool = False):
+        """In-kernel wait accounting of a distributed context (bis_dist_wait_read), ns."""
+        out = (dbl * 4)()
+        check(load().bis_dist_wait_read(self.h, out, int(reset)))
+        return [float(v) for v in out]
+
     def profile_enable(self, on: bool = True):
         self.call("bis_profile_enable", int(on))
 

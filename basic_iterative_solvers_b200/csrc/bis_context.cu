@@ -82,6 +82,7 @@ static int context_init(bis_context *c, int device) {
     // experiment switches (must be set alike on every rank)
     if (const char *e = getenv("BIS_SPMV_FUSED")) c->opt_spmv_fused = atoi(e);
     if (const char *e = getenv("BIS_TRSV_VARIANT")) c->opt_trsv_variant = atoi(e);
+    if (const char *e = getenv("BIS_GRAPH")) c->opt_graph = atoi(e);
     return 0;
 }
 
@@ -308,6 +309,114 @@ extern "C" int bis_profile_read(bis_context *c, const char *family, double *tota
     return 0;
 }
 
+// ---- CUDA graphs ----------------------------------------------------------------------------------
+// An iteration body is a fixed sequence of launches whose arguments (device addresses, scalar slots)
+// repeat with the period of the method's pointer exchange; alpha, beta, ... are formed on the device,
+// so nothing in it depends on the host.  begin/end record that sequence once from the ordinary C-ABI
+// calls (nothing executes while recording), launch replays it: one submission instead of 3..30.
+struct bis_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int64_t kernel_nodes = 0;
+};
+
+extern "C" int bis_graph_begin(bis_context *c) {
+    BIS_REQUIRE(c, "null context");
+    BIS_REQUIRE(!c->capturing, "bis_graph_begin: already recording");
+    BIS_REQUIRE(c->nranks == 1, "bis_graph_begin: the halo / reduction epochs of a distributed context are launch arguments");
+    BIS_REQUIRE(!c->profile, "bis_graph_begin: per-launch profiling is on");
+    BIS_CUDA(cudaSetDevice(c->device));
+    BIS_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = 1;
+    return 0;
+}
+
+extern "C" int bis_graph_end(bis_context *c, bis_graph **out) {
+    BIS_REQUIRE(c && out, "null argument");
+    BIS_REQUIRE(c->capturing, "bis_graph_end: not recording");
+    c->capturing = 0;
+    c->graph_epoch++;
+    *out = nullptr;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        bis_set_error("bis_graph_end: the recorded sequence cannot be a graph: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    bis_graph *bg = new bis_graph;
+    bg->graph = g;
+    e = cudaGraphInstantiate(&bg->exec, g, 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphDestroy(g);
+        delete bg;
+        bis_set_error("bis_graph_end: cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    size_t n_nodes = 0;
+    if (cudaGraphGetNodes(g, nullptr, &n_nodes) == cudaSuccess && n_nodes) {
+        std::vector<cudaGraphNode_t> nodes(n_nodes);
+        if (cudaGraphGetNodes(g, nodes.data(), &n_nodes) == cudaSuccess)
+            for (size_t i = 0; i < n_nodes; ++i) {
+                cudaGraphNodeType t;
+                if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) bg->kernel_nodes++;
+            }
+    }
+    *out = bg;
+    return 0;
+}
+
+// Abandons a recording (the caller then issues the same calls again, eagerly).
+extern "C" int bis_graph_abort(bis_context *c) {
+    BIS_REQUIRE(c, "null context");
+    if (!c->capturing) return 0;
+    c->capturing = 0;
+    c->graph_epoch++;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(c->stream, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return 0;
+}
+
+extern "C" int bis_graph_launch(bis_context *c, bis_graph *g) {
+    BIS_REQUIRE(c && g && g->exec, "bis_graph_launch: null argument");
+    BIS_REQUIRE(!c->capturing, "bis_graph_launch: recording");
+    BIS_CUDA(cudaSetDevice(c->device));
+    BIS_CUDA(cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->kernel_nodes;   // the kernels a replay runs count like the launches they replace
+    c->graph_epoch++;
+    return 0;
+}
+
+extern "C" int bis_graph_free(bis_context *c, bis_graph *g) {
+    if (!g) return 0;
+    if (c) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return 0;
+}
+
+extern "C" int bis_context_get_option(bis_context *c, const char *key, int *value) {
+    BIS_REQUIRE(c && key && value, "null argument");
+    std::string k(key);
+    if (k == "graph") *value = (c->opt_graph && c->nranks == 1) ? 1 : 0;
+    else if (k == "spmv_variant") *value = c->opt_spmv_variant;
+    else if (k == "trsv_variant") *value = c->opt_trsv_variant;
+    else if (k == "spmv_fused") *value = c->opt_spmv_fused;
+    else if (k == "dist_p2p") *value = c->opt_dist_p2p;
+    else {
+        bis_set_error("bis_context_get_option: unknown option '%s'", key);
+        return 2;
+    }
+    return 0;
+}
+
 extern "C" int bis_flush_l2(bis_context *c) {
     BIS_REQUIRE(c, "null context");
     if (!c->d_flush) {
@@ -329,6 +438,7 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
         c->opt_dist_p2p = value;
     }
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
+    else if (k == "graph") c->opt_graph = value;
     else if (k == "trsv_variant") c->opt_trsv_variant = value;
     else if (k == "trsv_debug") c->opt_trsv_debug = value;
     else if (k == "vector_cache") {
@@ -604,6 +714,7 @@ RedArgs bis_red_args(bis_context *c, int slot_a, int slot_b) {
     ra.peer_epoch = 0;
     for (int p = 0; p < BIS_MAX_PEERS; ++p) ra.peer_bank[p] = c->peer_bank[p];
     ra.errflag = c->d_errflag;
+    ra.waitstat = c->d_waitstat;
     if (c->nranks > 1 && c->peer_on && c->opt_dist_p2p && (slot_a >= 0 || slot_b >= 0)) {
         ra.peer_n = c->nranks;
         ra.peer_epoch = ++c->red_epoch;

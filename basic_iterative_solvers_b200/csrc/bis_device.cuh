@@ -122,6 +122,7 @@ __device__ __forceinline__ void grid_reduce_finish(const RedArgs &ra) {
         // epoch parity: a rank can only be one reduction ahead of the slowest one, because finishing a
         // reduction needs everybody's records of it.  All ranks add the same records in the same order.
         const int par = (int)(ra.peer_epoch & 1ull);
+        unsigned long long waited = 0ull;
         if (lane < ra.peer_n * ra.n_slab) {
             const int dst = lane / ra.n_slab, i = lane - dst * ra.n_slab;
             volatile double *rec = ra.peer_bank[dst] + (par * BIS_NSLAB + ra.rec_first + i) * 4;
@@ -139,9 +140,20 @@ __device__ __forceinline__ void grid_reduce_finish(const RedArgs &ra) {
                     break;
                 }
             }
+            waited = bis_globaltimer() - t_start;
             __threadfence_system();
             t0 = in[0];
             t1 = in[1];
+        }
+        // how long this rank sat waiting for the slowest one: the number that names the scaling limiter
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, waited, o);
+            waited = other > waited ? other : waited;
+        }
+        if (lane == 0 && ra.waitstat) {
+            ra.waitstat[0] += waited;
+            ra.waitstat[1] += 1ull;
         }
     } else if (lane < ra.n_rec) {
         t0 = s_rec[0][lane];

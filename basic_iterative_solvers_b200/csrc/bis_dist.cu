@@ -226,6 +226,8 @@ int bis_peer_link_setup(bis_context *c) {
     BIS_CUDA(cudaMemset(c->d_bank, 0, BIS_BANK_BYTES));
     BIS_CUDA(bis_cuda_malloc(&c->d_pack_ticket, sizeof(unsigned int)));
     BIS_CUDA(cudaMemset(c->d_pack_ticket, 0, sizeof(unsigned int)));
+    BIS_CUDA(bis_cuda_malloc(&c->d_waitstat, 4 * sizeof(unsigned long long)));
+    BIS_CUDA(cudaMemset(c->d_waitstat, 0, 4 * sizeof(unsigned long long)));
     BIS_CUDA(cudaDeviceSynchronize());   // banks are zero before the allgather below lets anyone write
     void *banks[BIS_MAX_PEERS] = {};
     int ok = 0;
@@ -241,6 +243,8 @@ void bis_peer_link_teardown(bis_context *c) {
     c->ipc_opened.clear();
     cudaFree(c->d_bank);
     cudaFree(c->d_pack_ticket);
+    cudaFree(c->d_waitstat);
+    c->d_waitstat = nullptr;
     c->d_bank = nullptr;
     c->d_pack_ticket = nullptr;
     c->peer_on = 0;
@@ -525,6 +529,22 @@ int bis_halo_fuse_args(bis_context *c, const bis_matrix *A, HaloFuse *hf) {
     a.ticket = c->d_pack_ticket;
     a.epoch = e;
     a.errflag = c->d_errflag;
+    a.waitstat = c->d_waitstat;
+    return 0;
+}
+
+// In-kernel wait accounting (ns): out[0] total time the finalising blocks of reductions waited for the
+// other ranks' records, out[1] reductions, out[2] time CTA 0's producer warp of the fused SpMV waited
+// for the senders' halo flags, out[3] exchanges.
+extern "C" int bis_dist_wait_read(bis_context *c, double out[4], int reset) {
+    BIS_REQUIRE(c && out, "null argument");
+    for (int i = 0; i < 4; ++i) out[i] = 0.0;
+    if (!c->d_waitstat) return 0;
+    unsigned long long h[4];
+    BIS_CUDA(cudaMemcpyAsync(h, c->d_waitstat, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 4; ++i) out[i] = (double)h[i];
+    if (reset) BIS_CUDA(cudaMemsetAsync(c->d_waitstat, 0, sizeof h, c->stream));
     return 0;
 }
 

@@ -19,6 +19,7 @@
 
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
+#include <thrust/fill.h>
 #include <thrust/reduce.h>
 #include <thrust/scan.h>
 #include <thrust/sequence.h>
@@ -163,6 +164,14 @@ int build_levels(bis_context *c, bis_matrix *T) {
     lv.n_levels = 0;
     BIS_CHECK(dalloc(&lv.d_ticket, 1));
     BIS_CHECK(dalloc(&lv.d_w, (size_t)n));
+    BIS_CHECK(dalloc(&lv.d_w2, (size_t)n));
+    // 0xFFF87E5E7E5E7E5E ("not ready", bis_sptrsv.cu) in both working vectors; every solve re-arms the other one
+    if (n > 0) {
+        thrust::fill(pol, thrust::device_pointer_cast(reinterpret_cast<unsigned long long *>(lv.d_w)),
+                     thrust::device_pointer_cast(reinterpret_cast<unsigned long long *>(lv.d_w)) + n, 0xFFF87E5E7E5E7E5EULL);
+        thrust::fill(pol, thrust::device_pointer_cast(reinterpret_cast<unsigned long long *>(lv.d_w2)),
+                     thrust::device_pointer_cast(reinterpret_cast<unsigned long long *>(lv.d_w2)) + n, 0xFFF87E5E7E5E7E5EULL);
+    }
     BIS_CHECK(dalloc(&lv.d_slot_row, (size_t)n));
     BIS_CHECK(dalloc(&lv.d_slot_level, (size_t)n));
     BIS_CHECK(dalloc(&lv.d_slot_gate, (size_t)n * 4 + 4));

@@ -56,7 +56,7 @@ void bis_set_error(const char *fmt, ...);
 
 #define BIS_LAUNCH_CHECK(ctx)                                                  \
     do {                                                                       \
-        (ctx)->launches++;                                                     \
+        if (!(ctx)->capturing) (ctx)->launches++; /* recorded launches count when replayed */ \
         cudaError_t _e = cudaGetLastError();                                   \
         if (_e != cudaSuccess) {                                               \
             bis_set_error("%s:%d: kernel launch failed: %s", __FILE__,         \
@@ -117,6 +117,7 @@ struct RedArgs {
     unsigned long long peer_epoch;
     double *peer_bank[BIS_MAX_PEERS];
     int *errflag;
+    unsigned long long *waitstat;   // [0] ns spent waiting for the other ranks' records, [1] reductions counted
 };
 
 // How the rows of the current problem are cut (set when a matrix is created; streaming kernels of
@@ -168,8 +169,14 @@ struct bis_context {
     unsigned long long red_epoch = 0;               // finalised reductions so far (same on all ranks)
     unsigned long long halo_epoch = 0;              // halo exchanges so far (same on all ranks)
     unsigned int *d_pack_ticket = nullptr;
+    unsigned long long *d_waitstat = nullptr;       // in-kernel wait accounting (bis_dist_wait_read)
     std::vector<void *> ipc_opened;                 // mappings to close
     RowPartition part;                              // bis_partition_set (bis_context.cu)
+    // CUDA graphs (bis_graph_*): `capturing` while the stream records; graph_epoch counts captures and
+    // replays -- host-side knowledge about device buffers that a replay may have changed (the working
+    // vectors of the triangular solves) is only trusted within one epoch
+    int capturing = 0;
+    uint64_t graph_epoch = 0;
     int64_t launches = 0;
     int64_t chain_solves = 0;   // triangular solves that ran as variant 4 (bis_sptrsv_chain.cuh)
     // options
@@ -181,6 +188,7 @@ struct bis_context {
     int opt_vector_cache = 1;
     int opt_spmv_fused = 1;     // distributed SpMV over peer memory as ONE kernel (0: pack / interior / wait / strips launches)
     int opt_dist_p2p = 1;       // 0: NCCL transport even when the peer-memory link is up
+    int opt_graph = 1;          // the host stack records iteration bodies as CUDA graphs (bis_context_get_option)
     int opt_spmv_variant = 0;
     int opt_spmv_lanes = 0;
     int opt_trsv_variant = 0;
@@ -227,6 +235,9 @@ struct LevelSets {
     unsigned int *d_level_done = nullptr;   // [n_levels] completion counters
     unsigned int *d_ticket = nullptr; // chunk ticket
     double *d_w = nullptr;            // [n_slots] working vector of the solve IN SLOT ORDER: sentinel until the slot's value is final
+    double *d_w2 = nullptr;           // its twin: solves alternate between the two, each resets the other one while it runs
+    int w_clean[2] = {1, 1};          // host's knowledge: that working vector holds "not ready" everywhere
+    uint64_t w_epoch = 0;             // ... valid while the context's graph_epoch has this value
     // level-ordered copy of the strict factor (rows stored in slot order, operands named by slot)
     int64_t *d_rp = nullptr;          // [n_slots+1]
     int *d_col = nullptr;
@@ -266,6 +277,7 @@ struct HaloFuse {
     unsigned int *ticket;
     unsigned long long epoch;
     int *errflag;
+    unsigned long long *waitstat;   // [2] ns CTA 0's producer waited for the senders' flags, [3] exchanges counted
 };
 
 // Acceleration structure of SpMV variant 3 (bis_spmv_win.cuh), derived lazily from the CRS arrays.

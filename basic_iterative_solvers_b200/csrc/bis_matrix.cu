@@ -36,6 +36,7 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->lv.d_level_done);
     cudaFree(A->lv.d_ticket);
     cudaFree(A->lv.d_w);
+    cudaFree(A->lv.d_w2);
     cudaFree(A->lv.d_rp);
     cudaFree(A->lv.d_col);
     cudaFree(A->lv.d_val);

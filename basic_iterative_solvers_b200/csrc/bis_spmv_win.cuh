@@ -379,6 +379,7 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
             if constexpr (DIST) {
                 // first tile of this CTA that reads ghosts: the senders' values must have landed
                 if (!halo_seen && (d.tile & WIN_ORDER_GHOST)) {
+                    const unsigned long long t_wait0 = bis_globaltimer();
                     for (int q = 0; q < hf.n_src; ++q) {
                         const volatile unsigned long long *f = hf.flag_in + hf.src_rank[q];
                         const unsigned long long t0 = bis_globaltimer();
@@ -393,6 +394,10 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
                     // the bulk copies below read the ghosts through the async proxy
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                     halo_seen = true;
+                    if (blockIdx.x == 0 && lane == 0 && hf.waitstat) {
+                        hf.waitstat[2] += bis_globaltimer() - t_wait0;
+                        hf.waitstat[3] += 1ull;
+                    }
                 }
             }
             const int st = s % in.nstage;

@@ -48,6 +48,8 @@ struct TrsvArgs {
     double *x;
     const double *D;
     const double *b;
+    int post_mul_d;                // store x[row] = D[row] * result (the "tmp <- D tmp" of the SGS preconditioner, kernels.hpp:366-370)
+    double *w_clean;               // the working vector of the PREVIOUS solve with this factor: reset to "not ready" here
 };
 
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) sptrsv_level_kernel(TrsvArgs a, 
                 sum = add_rn(sum, mul_rn(a.val[k], __ldcg(w + a.col[k])));
             const double r = div_rn(sub_rn(bb, sum), dd);
             __stcg(w + slot, r);
-            a.x[row] = r;
+            a.x[row] = a.post_mul_d ? mul_rn(r, dd) : r;
             __threadfence();   // release: the value is visible before the counter moves
         }
         const unsigned int m = __ballot_sync(0xffffffffu, mine);
@@ -182,6 +184,9 @@ __global__ void __launch_bounds__(THREADS) sptrsv_flag_kernel(TrsvArgs a, double
         e = a.rp[slot + 1];
         bb = a.b[row];
         dd = a.D[row];
+        // two working vectors alternate: this solve marks the other one "not ready" for the next solve
+        // (nobody reads it any more), so no separate fill launch precedes a solve
+        reinterpret_cast<unsigned long long *>(a.w_clean)[slot] = TRSV_SENTINEL;
     }
     // the head of the row is in registers before anything is waited for
     double av[TRSV_PF];
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(THREADS) sptrsv_flag_kernel(TrsvArgs a, double
             // (hardware NaNs are canonical), so readers can never mistake a result for "not ready".
             if (tail_ok) {
                 __stcg(w + slot, r);
-                a.x[row] = r;
+                a.x[row] = a.post_mul_d ? mul_rn(r, dd) : r;
             }
             if (a.dbg) {
                 ts2 = bis_globaltimer();
@@ -319,9 +324,10 @@ sptrsv_one_level_kernel(TrsvArgs a, double *w, int64_t slot_begin, int64_t slot_
     const int64_t s = a.rp[slot], e = a.rp[slot + 1];
     double sum = 0.0;
     for (int64_t k = s; k < e; ++k) sum = add_rn(sum, mul_rn(a.val[k], __ldcg(w + a.col[k])));
-    const double r = div_rn(sub_rn(a.b[row], sum), a.D[row]);
+    const double dd = a.D[row];
+    const double r = div_rn(sub_rn(a.b[row], sum), dd);
     w[slot] = r;
-    a.x[row] = r;
+    a.x[row] = a.post_mul_d ? mul_rn(r, dd) : r;
 }
 
 } // namespace
@@ -427,7 +433,7 @@ static int chain_solve(bis_context *c, const bis_matrix *T, double *x, const dou
 }
 
 static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const double *D,
-                      const double *b, int want_kind) {
+                      const double *b, int want_kind, int post_mul_d = 0) {
     BIS_REQUIRE(c && T && x && D && b, "sptrsv: null argument");
     BIS_REQUIRE(T->triangular == want_kind,
                 "sptrsv: matrix is not the %s strictly-triangular factor this call needs",
@@ -460,6 +466,8 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.x = x;
     a.D = D;
     a.b = b;
+    a.post_mul_d = post_mul_d;
+    a.w_clean = nullptr;
     if (c->opt_trsv_variant == 4 && T->lv.chain.state == 0) {
         if (T->rp_bytes == 8) BIS_CHECK(chain_build_t<int64_t>(c, T));
         else BIS_CHECK(chain_build_t<int32_t>(c, T));
@@ -468,8 +476,10 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     if (c->opt_trsv_variant == 4 && T->lv.chain.state == 1) {
         BIS_CHECK(chain_solve(c, T, x, D, b));
         c->chain_solves++;
+        if (post_mul_d) BIS_CHECK(bis_elemwise_mult_vectors(c, x, x, D, T->n_rows, 1.0));
         return bis_prof_end(c, BIS_PROF_SPTRSV);
     }
+    if (c->opt_trsv_variant == 1 || c->opt_trsv_variant == 2) lv.w_clean[0] = 0;   // they leave results in d_w
     if (c->opt_trsv_variant == 1) {
         const std::vector<int64_t> &ls = lv.level_start;
         for (int l = 0; l < lv.n_levels; ++l) {
@@ -483,17 +493,30 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     const int64_t blocks = (lv.n_slots + TRSV_THREADS - 1) / TRSV_THREADS;
     BIS_CUDA(cudaMemsetAsync(lv.d_ticket, 0, sizeof(unsigned int), c->stream));
     if (c->opt_trsv_variant != 2) {
-        trsv_fill_sentinel_kernel<<<bis_blocks_for(lv.n_slots, 1024, c->sm_count * 8), 256, 0, c->stream>>>(lv.n_slots, lv.d_w);
-        BIS_LAUNCH_CHECK(c);
+        // the working vector of this solve is clean (filled at build time, or by the previous solve)
+        if (lv.w_epoch != c->graph_epoch || c->capturing) {   // a graph replay may have used either vector since
+            lv.w_clean[0] = lv.w_clean[1] = 0;
+            lv.w_epoch = c->graph_epoch;
+        }
+        int p = lv.w_clean[0] ? 0 : (lv.w_clean[1] ? 1 : -1);
+        if (p < 0) {   // neither is known to be clean: inside a graph (fixed pointers), after one, or after another variant
+            trsv_fill_sentinel_kernel<<<bis_blocks_for(lv.n_slots, 1024, c->sm_count * 8), 256, 0, c->stream>>>(lv.n_slots, lv.d_w);
+            BIS_LAUNCH_CHECK(c);
+            p = 0;
+        }
+        double *w_use = p ? lv.d_w2 : lv.d_w;
+        a.w_clean = p ? lv.d_w : lv.d_w2;
+        lv.w_clean[p] = 0;
+        lv.w_clean[1 - p] = c->capturing ? 0 : 1;
         // rows per block (opt "trsv_block"): a block retires when its last row is done, so smaller blocks
         // hand their registers to rows further down the list sooner
         const int tb = c->opt_trsv_block;
         if (tb == 64)
-            sptrsv_flag_kernel<64><<<(unsigned int)((lv.n_slots + 63) / 64), 64, 0, c->stream>>>(a, lv.d_w);
+            sptrsv_flag_kernel<64><<<(unsigned int)((lv.n_slots + 63) / 64), 64, 0, c->stream>>>(a, w_use);
         else if (tb == 128)
-            sptrsv_flag_kernel<128><<<(unsigned int)((lv.n_slots + 127) / 128), 128, 0, c->stream>>>(a, lv.d_w);
+            sptrsv_flag_kernel<128><<<(unsigned int)((lv.n_slots + 127) / 128), 128, 0, c->stream>>>(a, w_use);
         else
-            sptrsv_flag_kernel<256><<<(unsigned int)blocks, 256, 0, c->stream>>>(a, lv.d_w);
+            sptrsv_flag_kernel<256><<<(unsigned int)blocks, 256, 0, c->stream>>>(a, w_use);
         BIS_LAUNCH_CHECK(c);
         if (a.dbg) {   // debug aid (tools/trsv_trace.py): per-row timestamps of the last solve
             std::vector<unsigned long long> h(4 * (size_t)lv.n_slots);
@@ -540,8 +563,9 @@ extern "C" int bis_apply_preconditioner(bis_context *c, int precond, int64_t n,
         return bis_bsptrsv(c, U, out, A_D, in);
     case BIS_PRECOND_SGS:
         BIS_REQUIRE(tmp, "bis_apply_preconditioner: sgs needs tmp");
-        BIS_CHECK(bis_sptrsv(c, L, tmp, A_D, in));                  // tmp <- (L+D)^-1 in
-        BIS_CHECK(bis_elemwise_mult_vectors(c, tmp, tmp, A_D, n, 1.0));   // tmp <- D tmp
+        // tmp <- D (L+D)^-1 in: the multiply rides in the forward solve's store (same rounding: the
+        // reference's elemwise_mult_vectors with scale 1.0 is one rounded product)
+        BIS_CHECK(trsv_solve(c, L, tmp, A_D, in, 1, /*post_mul_d=*/1));
         return bis_bsptrsv(c, U, out, A_D, tmp);                    // out <- (D+U)^-1 tmp
     case BIS_PRECOND_2ST:
         BIS_REQUIRE(work && A_D_inv, "bis_apply_preconditioner: 2st needs work and A_D_inv");

@@ -52,6 +52,9 @@ def load() -> C.CDLL:
     lib.bis_host_bench_close.restype = None
     lib.bis_host_bench_e2e.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.bis_host_bench_prepare.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.bis_host_bench_setup_ms.argtypes = [C.c_void_p]
+    lib.bis_host_bench_setup_ms.restype = C.c_double
+    lib.bis_host_bench_history.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.bis_host_bench_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     _lib = lib
     return lib
@@ -229,6 +232,16 @@ class BenchSession:
                 "breakdown_ms": {"allocate_init_upload": out[6], "r0_and_factor": out[7],
                                  "iterations": info[6] / 1e3, "x_star_download": info[7] / 1e3},
                 **self._info(info)}
+
+    def setup_ms(self) -> float:
+        """Wall time of the last matrix set-up (generation, SpMV tile format, order table)."""
+        return float(self.lib.bis_host_bench_setup_ms(self.h))
+
+    def history(self, cap: int = 64) -> np.ndarray:
+        """First residual norms of the session's current solver."""
+        buf = np.zeros(cap)
+        n = self.lib.bis_host_bench_history(self.h, _p(buf), cap)
+        return buf[:min(n, cap)].copy()
 
     def prepare(self, warmup: int):
         info = (C.c_int64 * 8)()

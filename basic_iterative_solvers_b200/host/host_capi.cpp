@@ -246,6 +246,7 @@ struct BenchSession {
     Timers timers;
     std::unique_ptr<Solver> solver;
     bis_context *dev = nullptr;
+    double setup_ms = 0.0;   // wall time of the last obtain_matrix (generation + SpMV tile format + order table)
 };
 
 static void bench_make(BenchSession *s) {
@@ -284,15 +285,20 @@ int bis_host_bench_e2e(void *h, int steps, const double *b_host, const double *x
                        double *x_star_host, double *out, int64_t *info) {
     auto *s = static_cast<BenchSession *>(h);
     try {
-        if (steps < 1 || steps > MAX_ITERS) bis_fatal("bench: steps outside [1, MAX_ITERS]");
+        if (steps > MAX_ITERS) bis_fatal("bench: steps outside [1, MAX_ITERS]");
         bench_make(s);
         Solver *solver = s->solver.get();
-        solver->max_iters = steps;
-        solver->tolerance = 0.0;   // never stop early: exactly `steps` iterations
+        if (steps >= 1) {
+            solver->max_iters = steps;
+            solver->tolerance = 0.0;   // never stop early: exactly `steps` iterations
+        }                              // steps <= 0: a real solve (TOL, MAX_ITERS)
         std::unique_ptr<MatrixCRS> A;
         std::unique_ptr<DeviceCRS> dA;
+        Stopwatch ws;
+        ws.start();
         obtain_matrix(&s->args, s->dev, A, dA);
         BIS_OK(bis_context_synchronize(s->dev));
+        s->setup_ms = ws.check() * 1e3;
         int64_t i0[8], i1[8];
         BIS_OK(bis_context_info(s->dev, i0));
         Stopwatch w;
@@ -317,13 +323,23 @@ int bis_host_bench_e2e(void *h, int steps, const double *b_host, const double *x
         out[4] = solver->collected_residual_norms[0];
         out[5] = solver->residual_norm;
         bench_fill_info(solver, info);
-        s->solver.reset();
-        return 0;
+        return 0;   // the solver stays alive until the next call (bis_host_bench_history)
     } catch (const std::exception &e) {
         g_host_err = e.what();
         s->solver.reset();
         return 1;
     }
+}
+
+double bis_host_bench_setup_ms(void *h) { return static_cast<BenchSession *>(h)->setup_ms; }
+
+// History of the session's solver: the first `cap` collected residual norms; returns how many exist.
+int bis_host_bench_history(void *h, double *out, int cap) {
+    auto *s = static_cast<BenchSession *>(h);
+    if (!s->solver) return 0;
+    const int n = s->solver->collected_residual_norms_count;
+    for (int i = 0; i < n && i < cap; ++i) out[i] = s->solver->collected_residual_norms[i];
+    return n;
 }
 
 // Untimed: build the solver, obtain the matrix, preprocessing, `warmup` iterations.

@@ -48,6 +48,12 @@ class BiCGSTABSolver : public Solver {
         if (fused_precond()) precondition(y, p_old);   // y of the first iteration (:24-27)
     }
     void iterate(Timers *) override {
+        // residual / residual_new / residual_old rotate with period 3 (the swap below and the one in
+        // exchange(), bicgstab.hpp:177,183), everything else with period 2: the arguments repeat every 6
+        graphed(exchange_count % 6, [&] { enqueue_iterate(); });
+        std::swap(residual, residual_new);   // bicgstab.hpp:177
+    }
+    void enqueue_iterate() {
         const int pc = static_cast<int>(preconditioner);
         if (!fused_precond()) precondition(y, p_old);
         BIS_OK(bis_spmv_dot(dev, dA->handle, y, v, residual_0, S_R0V, -1));
@@ -58,9 +64,9 @@ class BiCGSTABSolver : public Solver {
                                s_rho_old, S_R0V, S_ZS, S_ZZ, s_rho_new, S_RR_BI));
         BIS_OK(bis_bicgstab_p(dev, pc, N, nullptr, p_new, p_old, v, residual_new,
                               fused_precond() ? y : nullptr, A_D, s_rho_new, s_rho_old, S_R0V, S_ZS, S_ZZ));
-        std::swap(residual, residual_new);   // bicgstab.hpp:177
     }
     void exchange() override {
+        ++exchange_count;
         std::swap(p_old, p_new);
         std::swap(residual_old, residual);   // bicgstab.hpp:183
         std::swap(x_old, x_new);

@@ -64,11 +64,15 @@ class ConjugateGradientSolver : public Solver {
         Solver::init_residual();
     }
     void iterate(Timers *) override {
-        cg_separate_iteration(dev, preconditioner, N, dA.get(), dL_strict.get(), dU_strict.get(), A_D,
-                              A_D_inv, L_D, U_D, x_new, x_old, tmp, work, p_new, p_old, residual_new,
-                              residual_old, z_new, z_old, s_rz, s_rz_new);
+        // the vector pointers and the two (r,z) slots swap in exchange(): the arguments have period 2
+        graphed(exchange_count & 1, [&] {
+            cg_separate_iteration(dev, preconditioner, N, dA.get(), dL_strict.get(), dU_strict.get(), A_D,
+                                  A_D_inv, L_D, U_D, x_new, x_old, tmp, work, p_new, p_old, residual_new,
+                                  residual_old, z_new, z_old, s_rz, s_rz_new);
+        });
     }
     void exchange() override {
+        ++exchange_count;
         std::swap(p_old, p_new);
         std::swap(z_old, z_new);
         std::swap(residual_old, residual_new);

@@ -38,7 +38,7 @@ class GaussSeidelSolver : public Solver {
         Solver::init_residual();
     }
     void iterate(Timers *) override {
-        gs_separate_iteration(dev, dU_strict.get(), dL_strict.get(), tmp, A_D, b, x);
+        graphed(0, [&] { gs_separate_iteration(dev, dU_strict.get(), dL_strict.get(), tmp, A_D, b, x); });
     }
     void exchange() override {}
     void save_x_star() override {
@@ -58,7 +58,9 @@ class SymmetricGaussSeidelSolver : public GaussSeidelSolver {
     SymmetricGaussSeidelSolver(const Args *cli_args, Interface *device)
         : GaussSeidelSolver(cli_args, device) {}
     void iterate(Timers *) override {
-        gs_separate_iteration(dev, dU_strict.get(), dL_strict.get(), tmp, A_D, b, x);
-        bgs_separate_iteration(dev, dU_strict.get(), dL_strict.get(), tmp, A_D, b, x);
+        graphed(0, [&] {
+            gs_separate_iteration(dev, dU_strict.get(), dL_strict.get(), tmp, A_D, b, x);
+            bgs_separate_iteration(dev, dU_strict.get(), dL_strict.get(), tmp, A_D, b, x);
+        });
     }
 };

@@ -122,6 +122,10 @@ class GMRESSolver : public Solver {
     // needs (V[k]) is produced on the device, so it can be enqueued before the host has looked at
     // iteration k-1.  h_0k..h_kk land in slots S_H..S_H+k, ||w||^2 in S_H+k+1.
     void enqueue_iteration(const int k) {
+        // V, w and the slots are fixed: the launches of basis index k are the same in every restart cycle
+        graphed(k, [&] { enqueue_iteration_calls(k); });
+    }
+    void enqueue_iteration_calls(const int k) {
         spmv(dev, dA.get(), V + (int64_t)k * N, w);
         precondition(w, w);
         // orthogonalize_V: h_jk = (w, v_j) ; w -= h_jk v_j, j = 0..k ; h_{k+1,k} = ||w||

@@ -34,9 +34,12 @@ class JacobiSolver : public Solver {
         Solver::init_residual();
     }
     void iterate(Timers *) override {
-        jacobi_separate_iteration(dev, dA.get(), A_D, b, x_new, x_old);
+        graphed(exchange_count & 1, [&] { jacobi_separate_iteration(dev, dA.get(), A_D, b, x_new, x_old); });
     }
-    void exchange() override { std::swap(x_old, x_new); }
+    void exchange() override {
+        ++exchange_count;
+        std::swap(x_old, x_new);
+    }
     void save_x_star() override {
         std::swap(x_old, x_star);
         Solver::save_x_star();

@@ -68,7 +68,55 @@ class Solver {
           gmres_restart_len(cli_args->restart_length), num_scale(cli_args->num_scale) {
         collected_residual_norms = new double[max_iters * 2]();
         time_per_iteration = new double[max_iters * 2]();
+        int v = 0;
+        if (dev && bis_context_get_option(dev, "graph", &v) == 0) graphs_on = v != 0;
     }
+
+    // ---- CUDA graphs (new in the build) ------------------------------------------------------------
+    // The device part of an iteration is a fixed sequence of launches: its arguments repeat with the
+    // period of the method's pointer exchange, its scalars (alpha, beta, omega, h_jk) live on the device.
+    // graphed(key, enqueue): the first time a key comes up the calls are issued as usual (that also
+    // builds whatever a kernel builds lazily), the second time they are recorded into a CUDA graph and the
+    // graph is launched, from then on it is replayed -- one submission per iteration instead of 3..30.
+    // `enqueue` must only enqueue (no host-side state change, no readback).  Values are bit-identical.
+    struct GraphSlot {
+        bis_graph *graph = nullptr;
+        int seen = 0;
+        bool failed = false;
+    };
+    std::vector<GraphSlot> graph_slots;
+    bool graphs_on = false;
+
+    template <class F> void graphed(const int key, F &&enqueue) {
+        if (!graphs_on || !dev || key < 0) {
+            enqueue();
+            return;
+        }
+        if ((int)graph_slots.size() <= key) graph_slots.resize((size_t)key + 1);
+        GraphSlot &slot = graph_slots[(size_t)key];
+        if (slot.graph) {
+            BIS_OK(bis_graph_launch(dev, slot.graph));
+            return;
+        }
+        if (slot.failed || slot.seen++ < 1 || bis_graph_begin(dev) != 0) {
+            enqueue();
+            return;
+        }
+        enqueue();
+        if (bis_graph_end(dev, &slot.graph) != 0 || !slot.graph) {
+            slot.failed = true;     // e.g. a call that is not a pure enqueue: issue the sequence as usual
+            slot.graph = nullptr;
+            enqueue();
+            return;
+        }
+        BIS_OK(bis_graph_launch(dev, slot.graph));
+    }
+    void drop_graphs() {
+        for (GraphSlot &slot : graph_slots)
+            if (slot.graph) bis_graph_free(dev, slot.graph);
+        graph_slots.clear();
+    }
+    int exchange_count = 0;   // pointer exchanges so far: the key of the iteration's graph
 
     virtual void iterate(Timers *) = 0;
     virtual void exchange() = 0;
@@ -120,6 +168,7 @@ class Solver {
     virtual void get_explicit_x() {}
 
     virtual ~Solver() {
+        drop_graphs();
         for (double **p : {&x_star, &x_0, &b, &tmp, &work, &residual, &residual_0, &A_D, &A_D_inv, &L_D, &U_D, &A_D_scale})
             dev_delete(dev, *p);
         delete[] collected_residual_norms;

@@ -140,10 +140,11 @@ def slab_rows(n: int, nz_planes: int, plane: int, rank: int, nranks: int):
 def reference_leg(n_sample: int, iters: int, threads: int | None, n_target: int):
     """The UNMODIFIED reference (oracle/_ref/libbis_ref.so: /root/reference compiled behind an
     extern-C shim) running `-cg -p j` on HPCG-<n_sample> with all host threads, `iters`
-    iterations.  Returns ms/iter scaled to HPCG-<n_target> by the row ratio (every kernel on the
-    path is linear in the rows), plus the description."""
-    from oracle import refshim
-    from basic_iterative_solvers_b200 import host
+    iterations.  The CRS comes from oracle/matgen.py (numpy): nothing of the product is imported or
+    loaded on this path.  Returns the measured ms/iter, and that number scaled to HPCG-<n_target> by
+    the row ratio (every kernel on the path is linear in the rows; the reference cannot hold HPCG-512:
+    32-bit nnz)."""
+    from oracle import matgen, refshim
     if not refshim.available():
         raise RuntimeError("oracle/_ref/libbis_ref.so is missing (built by __graft_entry__.build() where "
                            "/root/reference exists)")
@@ -155,7 +156,9 @@ def reference_leg(n_sample: int, iters: int, threads: int | None, n_target: int)
         pass
     os.environ.setdefault("OMP_PROC_BIND", "close")
     lib.ref_omp_set_threads(int(cores))
-    rp, col, val = host.matrix(f"HPCG-{n_sample}")      # host generator: identical CRS to the device one
+    t0 = time.time()
+    rp, col, val = matgen.hpcg(n_sample)
+    t_gen = time.time() - t0
     lib.ref_set_max_iters(int(iters))
     t0 = time.time()
     r = refshim.solve(rp, col, val, "cg", "j")
@@ -172,8 +175,10 @@ def reference_leg(n_sample: int, iters: int, threads: int | None, n_target: int)
         "value": ms_iter * scale, "unit": UNIT, "cores": int(cores), "kind": "reference",
         "sample": (f"HPCG-{n_sample} -cg -p j, {its} iterations of the reference's solve() at {cores} OpenMP "
                    f"threads: {ms_iter:.2f} ms/iter measured (SpMV {spmv_ms:.2f} ms = "
-                   f"{spmv_bytes / spmv_ms / 1e6:.1f} GB/s), x{scale:.0f} row ratio to HPCG-{n_target}; "
-                   f"{wall:.1f} s of CPU work incl. its preprocessing"),
+                   f"{spmv_bytes / spmv_ms / 1e6:.1f} GB/s)"
+                   + (f", x{scale:.0f} row ratio to HPCG-{n_target}" if scale != 1 else "")
+                   + f"; {wall:.1f} s of CPU work incl. its preprocessing, {t_gen:.0f} s numpy matrix generation"),
+        "extrapolated": scale != 1, "sample_config": f"HPCG-{n_sample} -cg -p j", "scale": scale,
         "measured_ms_per_iter": ms_iter, "spmv_ms": spmv_ms, "spmv_gbs": spmv_bytes / spmv_ms / 1e6,
     }
 
@@ -187,6 +192,51 @@ def pick_cpu_sample(n_target: int) -> int:
     return min(n, n_target)
 
 
+PARITY_GOLDEN = os.path.join(ROOT, "tests", "golden", "bench_parity.json")
+PARITY_LEN = 25
+
+
+def parity_block(histories: dict, n: int, world: int, write_to: str | None):
+    """First residual norms of the bench workload (CG + Jacobi and BiCGSTAB + Jacobi) against the committed
+    one-GPU golden of the same workload (tests/golden/bench_parity.json, written by `--write-parity-golden` on one
+    GPU).  Reductions are partition-invariant, so the expected max_rel at 2, 4 and 8 GPUs is exactly 0."""
+    key = f"hpcg{n}"
+    out = {"n_residuals": PARITY_LEN, "golden": "tests/golden/bench_parity.json", "workload": f"HPCG-{n} -cg/-bi -p j"}
+    if write_to and world == 1:
+        rec = {}
+        try:
+            with open(PARITY_GOLDEN) as f:
+                rec = json.load(f)
+        except (OSError, ValueError):
+            pass
+        rec[key] = {m: [float(v).hex() for v in h] for m, h in histories.items()}
+        os.makedirs(os.path.dirname(os.path.abspath(write_to)), exist_ok=True)
+        with open(write_to, "w") as f:
+            json.dump(rec, f, indent=1)
+        out["written"] = write_to
+    try:
+        with open(PARITY_GOLDEN) as f:
+            gold = json.load(f).get(key)
+    except (OSError, ValueError):
+        gold = None
+    if not gold:
+        out["status"] = "no golden for this grid"
+        return out
+    worst, bit = 0.0, True
+    for m, h in histories.items():
+        g = [float.fromhex(v) for v in gold[m]]
+        k = min(len(g), len(h))
+        r0 = g[0]
+        d = max(abs(a - b) for a, b in zip(h[:k], g[:k])) / r0
+        out[f"{m}_max_rel"] = d
+        out[f"{m}_bit_identical"] = all(float(a).hex() == float(b).hex() for a, b in zip(h[:k], g[:k]))
+        worst = max(worst, d)
+        bit = bit and out[f"{m}_bit_identical"]
+    out["max_rel"] = worst
+    out["bit_identical"] = bit
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -198,7 +248,11 @@ def main():
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling: every GPU keeps an HPCG-<grid> sized slab (global grid n x n x n*N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-solve", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="HPCG edge of the CPU sample (0: auto)")
+    ap.add_argument("--write-parity-golden", default=None, metavar="PATH",
+                    help="one GPU: write the parity golden (merged with the committed one) to PATH")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=INT", help="bis_context_set_option")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,7 +266,7 @@ def main():
     gname = f"HPCG-{n}-{n}-{nz}" if args.weak else f"HPCG-{n}"
     workload = f"{gname} -cg -p j (27-point, {n_rows_g} rows, {nnz_g} nnz, fp64 CRS, b=1, x0=0.1)"
     config = {"workload": workload, "rows": n_rows_g, "nnz": nnz_g,
-              "partition": f"{world} z-slab(s)" if world > 1 else "single GPU",
+              "partition": f"{world} row block(s) = unions of 8 fixed z-slabs" if world > 1 else "single GPU",
               "l2": "inputs larger than L2 (no flush): CRS alone is %.1f GB per GPU" %
                     (12 * nnz_g / world / 1e9)}
 
@@ -220,16 +274,17 @@ def main():
         if rank != 0:
             return
         n_s = args.cpu_sample or pick_cpu_sample(n)
-        vals = []
-        leg = None
-        for _ in range(1):   # one bounded solve: warm-up iterations are inside it (steps + warmup iterations)
-            leg = reference_leg(n_s, args.steps + args.warmup, None, n)
-            vals.append(leg["value"])
+        leg = reference_leg(n_s, args.steps + args.warmup, None, n)   # warm-up iterations are inside the one bounded solve
+        if leg["extrapolated"]:
+            config["workload"] = (f"{workload} -- REFERENCE ARM: measured on {leg['sample_config']} "
+                                  f"({leg['measured_ms_per_iter']:.2f} ms/iter) and scaled x{leg['scale']:.0f} by the row "
+                                  f"ratio, because the reference cannot hold HPCG-{n} (32-bit nnz)")
         out = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["value"],
                "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config,
-               "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+               "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated",
+                                                    "sample_config", "scale", "measured_ms_per_iter")},
                "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "spmv_gbs": leg["spmv_gbs"]}
         print(json.dumps(out), flush=True)
@@ -267,9 +322,12 @@ def main():
         return float(t.item())
 
     ctx = capi.Context(local_rank, rank, world, nccl_id)
+    for kv in args.option:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     if world > 1:
-        config["partition"] += (", halo planes and dot-product sums over peer memory (NVLink stores from inside the "
-                                "pack / reducing kernels, CUDA IPC)" if ctx.info()["peer_memory"]
+        config["partition"] += (", halo planes and the 8 slab sums of every dot product over peer memory (NVLink stores "
+                                "from inside the SpMV / reducing kernels, CUDA IPC)" if ctx.info()["peer_memory"]
                                 else ", NCCL halo send/recv + allreduce")
     K, W = args.steps, args.warmup
     name = gname
@@ -286,27 +344,47 @@ def main():
     e = sess.e2e(K, b_h.data_ptr(), x0_h.data_ptr(), xs_h.data_ptr())
     barrier()
     e2e_ms = max_over_ranks(e["wall_ms"]) / K
+    setup_ms = max_over_ranks(sess.setup_ms())
     assert e["iters"] == K and e["n_rows"] == n_local
     e2e_check = float(xs_h[:4].sum())
+    # parity: the first residual norms of the bench workload against the committed one-GPU golden
+    histories = {}
+    ep = sess.e2e(PARITY_LEN - 1, b_h.data_ptr(), x0_h.data_ptr(), None)
+    histories["cg_j"] = [float(v) for v in sess.history(PARITY_LEN)]
+    # a REAL solve through the same path: TOL = 1e-14, MAX_ITERS = 1000, set-up included
+    full = None
+    if not args.no_full_solve:
+        barrier()
+        f = sess.e2e(0, b_h.data_ptr(), x0_h.data_ptr(), xs_h.data_ptr())
+        barrier()
+        full = {"iters": f["iters"], "wall_ms": max_over_ranks(f["wall_ms"]), "setup_ms": max_over_ranks(sess.setup_ms()),
+                "final_true_residual_rel": f["res_true"] / f["res0"], "launches": f["launches"],
+                "note": "solve() to TOL = 1e-14 or MAX_ITERS = 1000 from host b / x0 to host x_star; setup_ms (matrix "
+                        "generation + SpMV tile format) is reported beside it, not inside wall_ms"}
+        full["ms_per_iter"] = full["wall_ms"] / max(full["iters"], 1)
     sess.close()
+    sessb = host.BenchSession(ctx, name, "bi", "j")
+    sessb.e2e(PARITY_LEN - 1, b_h.data_ptr(), x0_h.data_ptr(), None)
+    histories["bi_j"] = [float(v) for v in sessb.history(PARITY_LEN)]
+    sessb.close()
+    parity = parity_block(histories, n, world, args.write_parity_golden) if (rank == 0 and not args.weak) else None
 
-    # ---- resident: K timed iterations between CUDA events ------------------------------------------
+    # ---- resident: K timed iterations between CUDA events, per-launch profiling OFF ------------------
     sess = host.BenchSession(ctx, name, "cg", "j")
     info = sess.prepare(W)
-    ctx.profile_enable(True)
+    if world > 1:
+        ctx.dist_wait_read(reset=True)
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
     t_clk = time.time()
     r = sess.run(K)
     barrier()
-    spmv_ms_total, spmv_cnt = ctx.profile_read("spmv")
-    vec_ms_total, vec_cnt = ctx.profile_read("vector")
-    ctx.profile_enable(False)
+    waits = ctx.dist_wait_read(reset=True) if world > 1 else None
     # a short timed region (tens of ms at 8 GPUs) gives the sampler nothing to see: keep the same
     # iteration loop running, untimed and unreported, until the sampler has watched ~0.6 s of it
     extra = 0
-    while time.time() - t_clk < 0.6 and extra < 400 and W + 2 * K + extra + 2 < 1000:   # MAX_ITERS bounds a session
+    while time.time() - t_clk < 0.6 and extra < 400 and W + 3 * K + extra + 2 < 1000:   # MAX_ITERS bounds a session
         sess.run(K)
         extra += K
     barrier()
@@ -314,11 +392,28 @@ def main():
     clk["window"] = f"the {K} timed iterations + {extra} further iterations of the same loop (untimed)"
     dev_ms = max_over_ranks(r["device_ms"])
     launches = r["launches"]
-    sess.close()
     ms_iter = dev_ms / K
+    # ---- second pass of the same loop for the roofline: per-launch event pairs on, graph replay off ---
+    sess.close()
+    ctx.set_option("graph", 0)
+    sess = host.BenchSession(ctx, name, "cg", "j")
+    sess.prepare(W)
+    ctx.profile_enable(True)
+    barrier()
+    rp_ = sess.run(K)
+    barrier()
+    spmv_ms_total, spmv_cnt = ctx.profile_read("spmv")
+    vec_ms_total, vec_cnt = ctx.profile_read("vector")
+    ctx.profile_enable(False)
+    ctx.set_option("graph", 1)
+    prof_dev_ms = rp_["device_ms"]
+    sess.close()
     spmv_ms = spmv_ms_total / max(spmv_cnt, 1)
-    spmv_bytes = 12 * info["nnz"] + info["rp_bytes"] * (info["n_rows"] + 1) + 16 * info["n_rows"]
-    achieved = spmv_bytes / spmv_ms / 1e6            # GB/s, this rank's SpMV (per GPU)
+    # bytes the kernel itself has to move per launch: 8 B value + 2 B local column id per nonzero, row_ptr,
+    # x once, y once, and the dot operand (p) once; the CRS-equivalent figure (12 B / nnz) beside it
+    own_bytes = 10 * info["nnz"] + info["rp_bytes"] * (info["n_rows"] + 1) + 24 * info["n_rows"]
+    crs_bytes = 12 * info["nnz"] + info["rp_bytes"] * (info["n_rows"] + 1) + 16 * info["n_rows"]
+    achieved = own_bytes / spmv_ms / 1e6            # GB/s, this rank's SpMV (per GPU)
     peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -326,12 +421,13 @@ def main():
             peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     except (OSError, KeyError, ValueError):
         pass
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
             t = json.load(f)
             if t.get("workload_n") == n and world == 1:
                 traffic = t["dram_bytes_per_launch"]
+                traffic_src = "static: " + t.get("source", "ncu --set full capture under profiles/")
     except (OSError, KeyError, ValueError):
         pass
 
@@ -344,6 +440,24 @@ def main():
     bi_ms = max_over_ranks(rb["device_ms"]) / K
     sess.close()
 
+    # ---- the same metric on the configuration the CPU reference can actually hold (one GPU) --------
+    same = None
+    if world == 1 and rank == 0 and not args.weak and n > 256:
+        s2 = host.BenchSession(ctx, "HPCG-256", "cg", "j")
+        n2 = 256 ** 3
+        b2 = torch.full((n2,), 1.0, dtype=torch.float64).pin_memory()
+        x2 = torch.full((n2,), 0.1, dtype=torch.float64).pin_memory()
+        o2 = torch.empty(n2, dtype=torch.float64).pin_memory()
+        s2.e2e(W, b2.data_ptr(), x2.data_ptr(), o2.data_ptr())
+        e2 = s2.e2e(K, b2.data_ptr(), x2.data_ptr(), o2.data_ptr())
+        s2.close()
+        s2 = host.BenchSession(ctx, "HPCG-256", "cg", "j")
+        s2.prepare(W)
+        r2 = s2.run(K)
+        s2.close()
+        same = {"workload": "HPCG-256 -cg -p j", "gpu_ms_per_iter": r2["device_ms"] / K,
+                "gpu_e2e_ms_per_iter": e2["wall_ms"] / K}
+
     out = {
         "metric": METRIC, "value": ms_iter, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_iter, "higher_is_better": False, "scaling": scaling, "vs_baseline": None,
@@ -351,26 +465,49 @@ def main():
         "e2e": {"value": e2e_ms, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * n_local / K, "d2h_bytes_per_step": 8 * n_local / K + 8,
                 "note": "preprocessing (allocate, upload b/x0 from pinned host memory, r0) + K harness "
-                        "iterations with the residual norm read back each + x_star download, / K",
-                "x_star_check": e2e_check, "breakdown_ms_rank0": e["breakdown_ms"]},
+                        "iterations with the residual norm read back each + x_star download, / K; the matrix set-up "
+                        "(setup_ms: generation + SpMV tile format + order table, once per matrix) is outside",
+                "setup_ms": setup_ms, "x_star_check": e2e_check, "breakdown_ms_rank0": e["breakdown_ms"],
+                "full_solve": full},
         "gpu_launches": launches,
+        "timing": "value: CUDA events around the K iterations, per-launch profiling OFF, iteration bodies replayed as "
+                  "CUDA graphs on one GPU; roofline: a second pass of the same loop with per-launch event pairs",
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "spmv_win_kernel<long, EpiDot> (y = A p fused with (y,p); val, 16-bit local column ids, row_ptr slice and x windows by TMA)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms,
-                     "launches_timed": spmv_cnt, "share_of_step": spmv_ms_total / dev_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": own_bytes,
+                     "bytes_note": "the kernel's own compulsory bytes: 10 B per nonzero (value + 16-bit local column id), "
+                                   "row_ptr, x once, y once, the dot operand once",
+                     "crs_equivalent_bytes_per_launch": crs_bytes, "crs_equivalent_gbs": crs_bytes / spmv_ms / 1e6,
+                     "ms_per_launch": spmv_ms, "launches_timed": spmv_cnt,
+                     "share_of_step": spmv_ms_total / prof_dev_ms,
                      "frac_of_nominal_8tbs": achieved / 8000.0},
         "spmv_gbs": achieved,
         "vector_kernels_ms_per_iter": vec_ms_total / K,
         "residual_after_timed_steps": r["res_last"] / r["res0"],
+        "parity": parity,
         "also": {"bicgstab_jacobi_ms_per_iter": bi_ms, "bicgstab_launches": rb["launches"]},
     }
+    if waits is not None:
+        out["dist_wait"] = {"rank": rank,
+                            "reduction_wait_ms_per_iter": max_over_ranks(waits[0] / 1e6 / K),
+                            "reductions": int(waits[1]),
+                            "halo_wait_ms_per_iter": max_over_ranks(waits[2] / 1e6 / K),
+                            "note": "globaltimer inside the kernels: how long the finalising block of a reduction waited for "
+                                    "the other ranks' slab sums, and CTA 0's producer for the halo flags (max over ranks)"}
+    if same is not None:
+        out["same_config"] = same
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
             n_s = args.cpu_sample or pick_cpu_sample(n)
             leg = reference_leg(n_s, 30, None, n)
-            out["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            out["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated",
+                                                       "sample_config", "scale", "measured_ms_per_iter")}
+            if same is not None and n_s == 256:
+                same["cpu_ms_per_iter"] = leg["measured_ms_per_iter"]
+                same["ratio"] = leg["measured_ms_per_iter"] / same["gpu_ms_per_iter"]
+                same["e2e_ratio"] = leg["measured_ms_per_iter"] / same["gpu_e2e_ms_per_iter"]
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                    "sample": f"unavailable: {ex}"}

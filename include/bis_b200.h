@@ -20,8 +20,12 @@
  *  - a context is not thread-safe (the reference harness is single-threaded,
  *    solver_harness.hpp:7-61).
  *  - in a distributed context (bis_context_create_distributed) matrices are
- *    row-partitioned, vectors hold the local rows, reductions are summed
- *    over ranks with NCCL and SpMV exchanges halo values with NCCL.
+ *    row-partitioned, vectors hold the local rows; halo values and the
+ *    partial sums of reductions move over peer memory (CUDA IPC mappings,
+ *    NVLink stores issued from inside the SpMV / reducing kernels).  NCCL
+ *    sets the link up and is the fallback transport (option "dist_p2p" = 0).
+ *    Reductions add 8 fixed slab sums in a fixed order: bit-identical
+ *    results at 1, 2, 4 and 8 GPUs (bis_partition_row_block).
  */
 #ifndef BIS_B200_H
 #define BIS_B200_H
@@ -94,13 +98,37 @@ int bis_profile_read(bis_context *ctx, const char *family,
 /* Write `bytes` of scratch to evict L2 between timed launches. */
 int bis_flush_l2(bis_context *ctx);
 /* Tuning knobs (all have defaults): key = "spmv_variant" (0 auto, 1 vector
- * CRS, 2 TMA-staged), "spmv_lanes" (0 auto, 2..32), "graph" (0/1). */
+ * CRS, 2 TMA-staged tiles + gathers, 3 windowed x), "spmv_lanes" (0 auto,
+ * 2..32), "trsv_variant" (0 auto, 1 launch per level, 2 level counters,
+ * 3 dataflow, 4 chains, 5 stencil wavefront), "graph" (0/1: the host stack
+ * replays the iteration body as a CUDA graph; default 1 on one GPU),
+ * "spmv_fused", "dist_p2p", "vector_cache", ... (bis_context.cu). */
 int bis_context_set_option(bis_context *ctx, const char *key, int value);
+int bis_context_get_option(bis_context *ctx, const char *key, int *value /* [host] */);
+
+/* ---- CUDA graphs --------------------------------------------------------
+ * New in the build.  The body of an iteration
+ * (methods/cg.hpp:6-54, bicgstab.hpp:8-83, gmres.hpp:150-183, ...) is a fixed
+ * sequence of launches whose scalars live on the device: between begin and
+ * end the ordinary calls of this header are RECORDED instead of executed
+ * (only enqueue-type calls are allowed: no upload/download, no scalar read,
+ * no matrix creation), launch replays the recording.  Results are bit-
+ * identical to issuing the calls.  Single-GPU contexts only. */
+typedef struct bis_graph bis_graph;
+int bis_graph_begin(bis_context *ctx);
+int bis_graph_end(bis_context *ctx, bis_graph **graph /* out */);
+int bis_graph_abort(bis_context *ctx);
+int bis_graph_launch(bis_context *ctx, bis_graph *graph);
+int bis_graph_free(bis_context *ctx, bis_graph *graph);
 /* Row block [begin, end) of `rank` in an n_global-row problem split over `nranks` GPUs: the rule the
  * generators use (unions of 8 fixed virtual slabs when nranks divides 8, so that reductions add the
  * same partial sums in the same order at 1, 2, 4 and 8 GPUs; `plane` = rows per grid plane or 0, only
  * used for rank counts that do not divide 8).  Pure function, no device needed.  New in the build:
  * the reference is single-process. */
+/* In-kernel wait accounting of a distributed context, in ns: out[0] time the finalising blocks of
+ * reductions waited for the other ranks' records, out[1] reductions counted, out[2] time the fused
+ * SpMV's first producer warp waited for the senders' halo flags, out[3] exchanges counted. */
+int bis_dist_wait_read(bis_context *ctx, double out[4] /* [host] */, int reset);
 int bis_partition_row_block(int64_t n_global, int64_t plane, int rank, int nranks,
                             int64_t *begin /* [host] */, int64_t *end /* [host] */);
 

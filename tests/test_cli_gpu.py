@@ -1,0 +1,49 @@
+"""The CLI (`lib/bis <matrix> -cg -p sgs ...`, host/main.cpp) on the GPU against the stdout of the UNMODIFIED
+reference executable on the same .mtx file (fixtures: tests/golden/make_cli_fixture.py): the residual read-out of
+postprocessing.hpp:8-30 -- `||A*x_k - b||_2 = <%.16e>` per sampled iteration -- must have the same number of lines
+and the same values to 1e-10 * ||r0||, the summary line the same solver / preconditioner / iteration count, and the
+res3 / res6 milestones of solver_harness.hpp:27-37 the same iteration numbers."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, HIST_TOL
+
+from basic_iterative_solvers_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+RES = re.compile(r"^\|\|A\*x_(\d+) - b\|\|_2 = (\S+)")
+CASES = [("cg_sgs", ["-cg", "-p", "sgs"]), ("gm_j", ["-gm", "-p", "j"]), ("sgs", ["-sgs"])]
+
+
+def parse(text):
+    ks, vals, other = [], [], []
+    for ln in text.splitlines():
+        m = RES.match(ln)
+        if m:
+            ks.append(int(m.group(1)))
+            vals.append(float(m.group(2)))
+        elif ln.startswith(("Solver:", "res3", "res6", "With the stopping", "The residual")):
+            other.append(ln.strip())
+    return ks, np.array(vals), other
+
+
+@pytest.mark.parametrize("key,flags", CASES)
+def test_cli_readout_matches_reference_binary(built, key, flags):
+    assert os.path.exists(host.CLI_PATH), "lib/bis is missing: __graft_entry__.build()"
+    mtx = os.path.join(GOLDEN, "cli_fdm2d12.mtx")
+    with open(os.path.join(GOLDEN, f"cli_fdm2d12_{key}.txt")) as f:
+        want_k, want_v, want_other = parse(f.read())
+    out = subprocess.run([host.CLI_PATH, mtx] + flags, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got_k, got_v, got_other = parse(out.stdout)
+    assert got_k == want_k, (len(got_k), len(want_k))
+    assert np.max(np.abs(got_v - want_v)) <= HIST_TOL * want_v[0]
+    # summary lines: solver name, preconditioner, "converged in: N iterations." / milestones
+    solver_got = [s for s in got_other if s.startswith(("Solver:", "res3", "res6"))]
+    solver_want = [s for s in want_other if s.startswith(("Solver:", "res3", "res6"))]
+    assert solver_got == solver_want

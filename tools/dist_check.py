@@ -1,8 +1,10 @@
 """Multi-GPU check (run under torchrun on a box with >= 2 GPUs):
    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
 Every rank solves the row-partitioned problem; rank 0 also solves the whole problem on its own GPU
-(single-GPU context) and compares: SpMV / Jacobi sweep bit-identical (row-local kernels do not depend on
-the partition), Krylov histories within 1e-10 * ||r0|| (only the reduction order changes)."""
+(single-GPU context) and compares.  With the peer-memory transport and a rank count that divides 8 the
+reductions are partition-invariant (8 fixed slab sums added in a fixed order, csrc/bis_internal.cuh): EVERY
+history -- CG, BiCGSTAB, GMRES, Jacobi -- must be bit-identical to the single-GPU one, iteration counts
+included.  The NCCL fallback transport adds per-rank sums instead: compared to 1e-10 * ||r0||."""
 import os
 import sys
 
@@ -68,7 +70,7 @@ if peer:
         if rank == 0:
             print(f"{name} -{method} -p {pre}: fused SpMV kernel vs separate launches: its {r.iter_count} vs {q.iter_count}, "
                   f"max |dr|/r0 = {err:.2e}", flush=True)
-        ok &= err <= 1e-10
+        ok &= np.array_equal(q.history, r.history)   # same kernels, same sums: bit-identical
     ctx.set_option("spmv_fused", 1)
     dist.barrier()
 
@@ -124,12 +126,17 @@ if rank == 0:
     with capi.Context(local) as solo:
         for (method, pre), r in results.items():
             s = host.solve(solo, method, pre, matrix_name=name, want_x=False, max_iters=300)
-            k = cmp_len(method, s.history.size, r.history.size)
+            k = min(s.history.size, r.history.size)
             err = float(np.max(np.abs(s.history[:k] - r.history[:k])) / s.history[0])
-            same = (method == "j" and np.array_equal(s.history[:50], r.history[:50]))
+            same = s.iter_count == r.iter_count and np.array_equal(s.history, r.history)
             print(f"{name} -{method} -p {pre}: its {r.iter_count} vs single-GPU {s.iter_count}, "
-                  f"max |dr|/r0 = {err:.2e}" + (" (first 50 residuals bit-identical)" if same else ""), flush=True)
-            ok &= err <= 1e-10 and abs(r.iter_count - s.iter_count) <= max(2, (0.15 if method == "bi" else 0.05) * s.iter_count)
+                  f"max |dr|/r0 = {err:.2e}: " + ("WHOLE HISTORY BIT-IDENTICAL" if same else "histories differ"), flush=True)
+            if peer and 8 % world == 0:
+                ok &= same
+            else:
+                kk = cmp_len(method, s.history.size, r.history.size)
+                e2 = float(np.max(np.abs(s.history[:kk] - r.history[:kk])) / s.history[0])
+                ok &= e2 <= 1e-10 and abs(r.iter_count - s.iter_count) <= max(2, (0.15 if method == "bi" else 0.05) * s.iter_count)
     print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
 ctx.close()
 dist.barrier()
