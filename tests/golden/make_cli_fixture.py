@@ -16,7 +16,9 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(ROOT, "oracle", "_ref", "bis_ref")
 N = 12
 
-CASES = [("cg_sgs", ["-cg", "-p", "sgs"]), ("gm_j", ["-gm", "-p", "j"]), ("sgs", ["-sgs"]), ("bi_ilu0_unavailable", None)]
+# no GMRES case: the reference executable reads y[restart_len] one past the end in get_explicit_x (gmres.hpp:358,
+# SURVEY F6); as a stand-alone binary that word is heap garbage and `-gm -p j` never converges on this matrix
+CASES = [("cg_sgs", ["-cg", "-p", "sgs"]), ("bi_j", ["-bi", "-p", "j"]), ("sgs", ["-sgs"]), ("j", ["-j"])]
 
 
 def write_mtx(path):

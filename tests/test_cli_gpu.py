@@ -17,7 +17,7 @@ from basic_iterative_solvers_b200 import host
 pytestmark = pytest.mark.gpu
 
 RES = re.compile(r"^\|\|A\*x_(\d+) - b\|\|_2 = (\S+)")
-CASES = [("cg_sgs", ["-cg", "-p", "sgs"]), ("gm_j", ["-gm", "-p", "j"]), ("sgs", ["-sgs"])]
+CASES = [("cg_sgs", ["-cg", "-p", "sgs"]), ("bi_j", ["-bi", "-p", "j"]), ("sgs", ["-sgs"]), ("j", ["-j"])]
 
 
 def parse(text):
