@@ -244,7 +244,7 @@ class Context:
         self.call("bis_context_info", arr)
         return {"sm_count": int(arr[0]), "free": int(arr[1]), "total": int(arr[2]),
                 "launches": int(arr[3]), "l2_bytes": int(arr[4]),
-                "peer_memory": bool(arr[5]), "chain_solves": int(arr[6])}
+                "peer_memory": bool(arr[5]), "chain_solves": int(arr[6]), "wave_solves": int(arr[7])}
 
     def set_option(self, key: str, value: int):
         self.call("bis_context_set_option", key.encode(), int(value))

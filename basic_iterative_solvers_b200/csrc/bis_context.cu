@@ -221,6 +221,7 @@ extern "C" int bis_context_info(bis_context *c, int64_t info[8]) {
     info[3] = c->launches;
     info[4] = (int64_t)c->l2_bytes;
     info[6] = c->chain_solves;
+    info[7] = c->wave_solves;
     info[5] = (c->peer_on && c->opt_dist_p2p) ? 1 : 0;   // 1: collectives run over peer memory, 0: NCCL
     return 0;
 }
@@ -460,6 +461,7 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_mult") c->opt_spmv_mult = value;
     else if (k == "win_rows") c->opt_win_rows = value;
 #ifdef BIS_PERF_DEBUG
+    else if (k == "wave_debug") c->opt_wave_debug = value;
     else if (k == "spmv_debug") c->opt_spmv_debug = value;
 #endif
     else {

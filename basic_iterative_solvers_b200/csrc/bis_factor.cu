@@ -365,6 +365,9 @@ int split_device(bis_context *c, const bis_matrix *A, int sorted, double *diag, 
     }
     L->max_row = ml; L->mean_row = n ? (double)tl / (double)n : 0.0;
     U->max_row = mu; U->mean_row = n ? (double)tu / (double)n : 0.0;
+    L->grid_nx = U->grid_nx = A->grid_nx;   // the factors of a grid matrix live on the same grid
+    L->grid_ny = U->grid_ny = A->grid_ny;
+    L->grid_nz = U->grid_nz = A->grid_nz;
     int *lrp = static_cast<int *>(L->d_rp), *urp = static_cast<int *>(U->d_rp);
     thrust::exclusive_scan(pol, pl, pl + n + 1, thrust::device_pointer_cast(lrp));
     thrust::exclusive_scan(pol, pu, pu + n + 1, thrust::device_pointer_cast(urp));
@@ -458,10 +461,32 @@ ilu0_dataflow_kernel(int64_t n, const int *lrp, const int *lcol, double *lval, c
 
 } // namespace
 
-int bis_build_levels_device(bis_context *c, bis_matrix *T) {
+static int build_levels_now(bis_context *c, bis_matrix *T) {
     BIS_CUDA(cudaSetDevice(c->device));
-    if (T->rp_bytes == 8) return build_levels<int64_t>(c, T);
-    return build_levels<int32_t>(c, T);
+    int rc = T->rp_bytes == 8 ? build_levels<int64_t>(c, T) : build_levels<int32_t>(c, T);
+    if (rc == 0) T->lv.built = true;
+    return rc;
+}
+
+// What a triangular solve needs beyond the CRS arrays.  A factor of a structured-grid matrix gets the
+// records of the stencil wavefront (bis_sptrsv_wave.cuh) and NO level analysis / level-ordered copy (it
+// would double the factor's footprint: HPCG-512 -p sgs fits one GPU only without it); everything else,
+// and any factor a caller forces another variant on, gets the level sets of the dataflow solve.
+int bis_build_levels_device(bis_context *c, bis_matrix *T) {
+    T->lv.n_slots = T->n_rows;
+    if (c->opt_trsv_variant == 0 || c->opt_trsv_variant == 5) {
+        BIS_CHECK(bis_wave_build(c, T));
+        if (T->lv.wave.state == 1) {
+            // validation is the wavefront's own (strictly triangular, ascending columns, stencil slots)
+            return 0;
+        }
+    }
+    return build_levels_now(c, T);
+}
+
+int bis_ensure_levels(bis_context *c, const bis_matrix *T) {
+    if (T->lv.built) return 0;
+    return build_levels_now(c, const_cast<bis_matrix *>(T));
 }
 
 // split_LU_new (LU_factors.hpp:122-309), strict parts, on the device.

@@ -178,6 +178,7 @@ struct bis_context {
     int capturing = 0;
     uint64_t graph_epoch = 0;
     int64_t launches = 0;
+    int64_t wave_solves = 0;    // triangular solves that ran as variant 5 (bis_sptrsv_wave.cuh)
     int64_t chain_solves = 0;   // triangular solves that ran as variant 4 (bis_sptrsv_chain.cuh)
     // options
     // freed vectors are kept for the next allocation of the same size (a solver allocates ~20 vectors of
@@ -199,6 +200,7 @@ struct bis_context {
     int opt_trsv_debug = 0;     // dump per-row timestamps of each solve to $BIS_TRSV_DEBUG_FILE
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
+    int opt_wave_debug = 0;     // stencil-wavefront perf experiments (results invalid); only in -DBIS_PERF_DEBUG builds
     int opt_spmv_debug = 0;     // perf experiments (results invalid when non-zero); only in -DBIS_PERF_DEBUG builds
     int opt_win_rows = 0;       // variant 3: rows per tile (0 auto; fixed once a matrix's format is built)
     int opt_spmv_mult = 0;      // TMA variant: threads per tile row (1, 2, 4; 0 auto)
@@ -222,7 +224,21 @@ struct ChainFormat {
     double *d_w = nullptr;              // [32 * n_recs] working vector, record-major
 };
 
+// Variant 5 of the triangular solve (bis_sptrsv_wave.cuh): records of a structured-grid factor
+struct WaveFormat {
+    int state = 0;                 // 0 not tried, 1 usable, -1 not a (<= 27-point) stencil in natural ordering
+    int nx = 0, ny = 0, nz = 0, W = 0, S = 0;
+    long long n_groups = 0;
+    double *d_rec = nullptr;       // [n_groups][S][13][32]
+    double *d_w[2] = {nullptr, nullptr};   // working vectors [n_groups][S][32]; solves alternate, each re-arms the other
+    int w_clean[2] = {0, 0};
+    uint64_t w_epoch = 0;
+    unsigned int *d_ticket = nullptr;
+};
+
 struct LevelSets {
+    bool built = false;            // level analysis done (skipped while the stencil wavefront serves the factor)
+    mutable WaveFormat wave;
     int n_levels = 0;
     int64_t n_slots = 0;              // == n_rows: position in the level-ordered row list
     int *d_slot_row = nullptr;        // [n_slots] original row
@@ -345,6 +361,10 @@ int bis_peer_map(bis_context *ctx, void *mine, void **out);
 int bis_matrix_finalize_distributed(bis_context *ctx, bis_matrix *A,
                                     int *d_col_global_in_place);
 int bis_build_levels_device(bis_context *ctx, bis_matrix *T);
+// the level sets of a factor that has been served by the stencil wavefront so far (bis_factor.cu)
+int bis_ensure_levels(bis_context *ctx, const bis_matrix *T);
+// tries to build the stencil-wavefront records of a triangular factor (bis_sptrsv.cu); wave.state tells
+int bis_wave_build(bis_context *ctx, const bis_matrix *T);
 int bis_matrix_stats(bis_context *ctx, bis_matrix *A);
 // builds the SpMV acceleration structure of a general matrix (bis_spmv.cu); lazy on first SpMV otherwise
 int bis_spmv_prepare(bis_context *ctx, const bis_matrix *A);

@@ -37,6 +37,10 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->lv.d_ticket);
     cudaFree(A->lv.d_w);
     cudaFree(A->lv.d_w2);
+    cudaFree(A->lv.wave.d_rec);
+    cudaFree(A->lv.wave.d_w[0]);
+    cudaFree(A->lv.wave.d_w[1]);
+    cudaFree(A->lv.wave.d_ticket);
     cudaFree(A->lv.d_rp);
     cudaFree(A->lv.d_col);
     cudaFree(A->lv.d_val);

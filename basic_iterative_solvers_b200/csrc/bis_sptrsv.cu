@@ -22,6 +22,9 @@
 // (HPCG-n has 7n-6 levels).
 #include "bis_device.cuh"
 #include "bis_sptrsv_chain.cuh"
+#include "bis_sptrsv_wave.cuh"
+
+#include <algorithm>
 
 #include <cstdlib>
 
@@ -432,6 +435,186 @@ static int chain_solve(bis_context *c, const bis_matrix *T, double *x, const dou
     return 0;
 }
 
+// ---- variant 5: stencil wavefront (bis_sptrsv_wave.cuh) ------------------------------------------------
+namespace {
+
+template <typename RP>
+int wave_try_grid(bis_context *c, const bis_matrix *T, int nx, int ny, int nz, bool *ok) {
+    *ok = false;
+    const int64_t n = T->n_rows;
+    if (nx < 1 || ny < 1 || nz < 1 || (int64_t)nx * ny * nz != n) return 0;
+    if (nx < 4 && n > 64) return 0;               // the lane skew assumes lines, not dots
+    wave::Grid g;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.W = (ny + 31) / 32;
+    g.S = nx + 62;
+    g.n = n;
+    g.upper = T->triangular == 2 ? 1 : 0;
+    int *d_status = nullptr;
+    BIS_CUDA(bis_cuda_malloc(&d_status, sizeof(int)));
+    BIS_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), c->stream));
+    const int grid = bis_blocks_for(n, 256, c->sm_count * 16);
+    wave::validate_kernel<RP><<<grid, 256, 0, c->stream>>>(g, static_cast<const RP *>(T->d_rp), T->d_col, d_status);
+    BIS_LAUNCH_CHECK(c);
+    int status = 0;
+    BIS_CUDA(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_status);
+    if (status != 0) return 0;
+    WaveFormat &wf = T->lv.wave;
+    wf.nx = nx; wf.ny = ny; wf.nz = nz; wf.W = g.W; wf.S = g.S;
+    wf.n_groups = wave::n_groups(g);
+    *ok = true;
+    return 0;
+}
+
+// distinct |row - col| of the factor, ascending (empty when there are more than a stencil has)
+template <typename RP>
+int wave_offsets(bis_context *c, const bis_matrix *T, std::vector<int> *out) {
+    out->clear();
+    int *d_tab = nullptr;
+    const size_t bytes = sizeof(int) * (wave::OFFS_CAP + 2);
+    BIS_CUDA(bis_cuda_malloc(&d_tab, bytes));
+    BIS_CUDA(cudaMemsetAsync(d_tab, 0, bytes, c->stream));
+    wave::offsets_kernel<RP><<<bis_blocks_for(T->n_rows, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+        T->n_rows, static_cast<const RP *>(T->d_rp), T->d_col, d_tab);
+    BIS_LAUNCH_CHECK(c);
+    int tab[wave::OFFS_CAP + 2];
+    BIS_CUDA(cudaMemcpyAsync(tab, d_tab, bytes, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tab);
+    if (tab[wave::OFFS_CAP + 1] != 0 || tab[0] > 13) return 0;
+    for (int i = 0; i < tab[0]; ++i) out->push_back(tab[1 + i]);
+    std::sort(out->begin(), out->end());
+    return 0;
+}
+
+template <typename RP>
+int wave_build_t(bis_context *c, const bis_matrix *T) {
+    WaveFormat &wf = T->lv.wave;
+    wf.state = -1;
+    const int64_t n = T->n_rows;
+    if (n < 32 || T->nnz == 0 || T->max_row > wave::K || T->triangular == 0) return 0;
+    bool ok = false;
+    if (T->grid_nx > 0) {
+        BIS_CHECK(wave_try_grid<RP>(c, T, (int)T->grid_nx, (int)T->grid_ny, (int)T->grid_nz, &ok));
+    } else {
+        // no hint (an uploaded factor): the grid is read off the distinct offsets 1, nx-1..nx+1, P-nx-1..P+nx+1
+        std::vector<int> offs;
+        BIS_CHECK(wave_offsets<RP>(c, T, &offs));
+        std::vector<int> nx_c, p_c;
+        if (!offs.empty() && offs[0] == 1) {
+            size_t i = 1;
+            if (i < offs.size()) {
+                const int a = offs[i];
+                for (int cand : {a + 1, a}) nx_c.push_back(cand);
+            } else {
+                nx_c.push_back((int)n);          // a single chain
+            }
+        } else if (!offs.empty()) {
+            nx_c.push_back(offs[0]);             // no x-coupling at all
+            nx_c.push_back(offs[0] + 1);
+        }
+        for (int nx : nx_c) {
+            if (ok) break;
+            if (nx < 1 || n % nx != 0) continue;
+            p_c.clear();
+            for (int o : offs)
+                if (o > nx + 1) {
+                    for (int cand : {o, o + 1, o + nx - 1, o + nx, o + nx + 1}) p_c.push_back(cand);
+                    break;
+                }
+            p_c.push_back((int)n);               // a single plane
+            for (int P : p_c) {
+                if (P < nx || P % nx != 0 || n % P != 0) continue;
+                BIS_CHECK(wave_try_grid<RP>(c, T, nx, P / nx, (int)(n / P), &ok));
+                if (ok) break;
+            }
+        }
+    }
+    if (!ok) return 0;
+    // records (zeros where a neighbour does not exist) and the two working vectors, both "not ready"
+    const size_t rec_doubles = (size_t)wf.n_groups * wf.S * wave::REC_DOUBLES;
+    const size_t w_doubles = (size_t)wf.n_groups * wf.S * 32;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && (rec_doubles + 2 * w_doubles) * 8 + ((size_t)1 << 30) > fr) {
+        bis_vector_cache_release_all();
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && (rec_doubles + 2 * w_doubles) * 8 + ((size_t)1 << 30) > fr) return 0;   // no room: dataflow solve
+    }
+    BIS_CUDA(bis_cuda_malloc(&wf.d_rec, rec_doubles * 8));
+    BIS_CUDA(bis_cuda_malloc(&wf.d_w[0], w_doubles * 8));
+    BIS_CUDA(bis_cuda_malloc(&wf.d_w[1], w_doubles * 8));
+    BIS_CUDA(bis_cuda_malloc(&wf.d_ticket, sizeof(unsigned int)));
+    BIS_CUDA(cudaMemsetAsync(wf.d_rec, 0, rec_doubles * 8, c->stream));
+    wave::Grid g;
+    g.nx = wf.nx; g.ny = wf.ny; g.nz = wf.nz; g.W = wf.W; g.S = wf.S; g.n = n; g.upper = T->triangular == 2 ? 1 : 0;
+    const int grid = bis_blocks_for(n, 256, c->sm_count * 16);
+    wave::fill_kernel<RP><<<grid, 256, 0, c->stream>>>(g, static_cast<const RP *>(T->d_rp), T->d_col, T->d_val, wf.d_rec);
+    BIS_LAUNCH_CHECK(c);
+    for (int i = 0; i < 2; ++i) {
+        wave::fill_u64_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((long long)w_doubles, reinterpret_cast<unsigned long long *>(wf.d_w[i]), wave::SENT);
+        BIS_LAUNCH_CHECK(c);
+        wf.w_clean[i] = 1;
+    }
+    wf.w_epoch = c->graph_epoch;
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    wf.state = 1;
+    return 0;
+}
+
+int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, const double *b, int post_mul_d) {
+    WaveFormat &wf = T->lv.wave;
+    wave::Args a;
+    a.g.nx = wf.nx; a.g.ny = wf.ny; a.g.nz = wf.nz; a.g.W = wf.W; a.g.S = wf.S; a.g.n = T->n_rows;
+    a.g.upper = T->triangular == 2 ? 1 : 0;
+    a.rec = wf.d_rec;
+    a.ticket = wf.d_ticket;
+    a.errflag = c->d_errflag;
+    a.x = x; a.D = D; a.b = b;
+    a.post_mul_d = post_mul_d;
+#ifdef BIS_PERF_DEBUG
+    a.dbg = c->opt_wave_debug;
+#endif
+    if (wf.w_epoch != c->graph_epoch || c->capturing) {   // a graph replay may have used either vector since
+        wf.w_clean[0] = wf.w_clean[1] = 0;
+        wf.w_epoch = c->graph_epoch;
+    }
+    int p = wf.w_clean[0] ? 0 : (wf.w_clean[1] ? 1 : -1);
+    if (p < 0) {
+        wave::fill_u64_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((long long)wf.n_groups * wf.S * 32,
+                                                                      reinterpret_cast<unsigned long long *>(wf.d_w[0]), wave::SENT);
+        BIS_LAUNCH_CHECK(c);
+        p = 0;
+    }
+    a.w = wf.d_w[p];
+    a.w_clean = wf.d_w[1 - p];
+    wf.w_clean[p] = 0;
+    wf.w_clean[1 - p] = c->capturing ? 0 : 1;
+    BIS_CUDA(cudaMemsetAsync(wf.d_ticket, 0, sizeof(unsigned int), c->stream));
+    const size_t smem = wave::SMEM_PER_WARP * wave::WARPS;
+    const long long warps_needed = wf.n_groups;
+    int blocks = c->sm_count;
+    if ((long long)blocks * wave::WARPS > warps_needed) blocks = (int)((warps_needed + wave::WARPS - 1) / wave::WARPS);
+    if (a.g.upper) {
+        BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<true>), smem));
+        wave::wave_kernel<true><<<blocks, wave::WARPS * 32, smem, c->stream>>>(a);
+    } else {
+        BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<false>), smem));
+        wave::wave_kernel<false><<<blocks, wave::WARPS * 32, smem, c->stream>>>(a);
+    }
+    BIS_LAUNCH_CHECK(c);
+    return 0;
+}
+
+} // namespace
+
+int bis_wave_build(bis_context *c, const bis_matrix *T) {
+    if (T->lv.wave.state != 0) return 0;
+    BIS_CUDA(cudaSetDevice(c->device));
+    if (T->rp_bytes == 8) return wave_build_t<int64_t>(c, T);
+    return wave_build_t<int32_t>(c, T);
+}
+
 static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const double *D,
                       const double *b, int want_kind, int post_mul_d = 0) {
     BIS_REQUIRE(c && T && x && D && b, "sptrsv: null argument");
@@ -443,6 +626,14 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     BIS_CUDA(cudaSetDevice(c->device));
     LevelSets &lv = T->lv;
     if (T->n_rows == 0) return 0;
+    if ((c->opt_trsv_variant == 0 || c->opt_trsv_variant == 5) && lv.wave.state == 1) {
+        BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPTRSV));
+        BIS_CHECK(wave_solve(c, T, x, D, b, post_mul_d));
+        c->wave_solves++;
+        return bis_prof_end(c, BIS_PROF_SPTRSV);
+    }
+    BIS_REQUIRE(c->opt_trsv_variant != 5, "trsv_variant=5 forced, but the factor is not a (<= 27-point) stencil in natural ordering");
+    BIS_CHECK(bis_ensure_levels(c, T));
     TrsvArgs a;
     a.n_slots = lv.n_slots;
     a.slot_row = lv.d_slot_row;

@@ -1,0 +1,540 @@
+// bis_sptrsv_wave.cuh -- triangular solve, variant 5 ("stencil wavefront"): the default for factors of
+// matrices on a structured grid (<= 27-point stencils in natural ordering: HPCG, Anderson / 7-point, 2-D
+// 5- and 9-point), see DESIGN.md 3.2.  Same row semantics and the same bits as native_sptrsv /
+// native_bsptrsv (kernels.hpp:54-76, 88-107): products separately rounded and added in storage order.
+//
+// Why: the general dataflow solve (bis_sptrsv.cu) pays one L2 round trip per LEVEL, and HPCG-n has 7n-6
+// of them (1.28 us per level measured, 2.3 ms per sweep at n = 256).  In a stencil factor the rows of an
+// x-line form a chain (row r reads r-1), and everything else a row reads lies in the neighbouring lines
+// y-1 (same plane) and y-1, y, y+1 (previous plane).  So:
+//   * a LANE owns an x-line and walks it one row per step; a WARP owns 32 consecutive lines of a plane,
+//     lane j running 2j steps behind lane 0 (row (x,y) needs (x+1,y-1): the level function is x+2y+4z);
+//   * what a row needs from its own line is a register, what it needs from the lines of its own warp are
+//     the results of at most three steps ago: a shared-memory ring indexed by STEP, so that for every lane
+//     the operand of stencil slot (dx,dy) sits in ring row (step + dx + 2 dy) -- a compile-time offset once
+//     the step loop is unrolled by the ring depth: no index arithmetic, no shuffles, no selects;
+//   * the values of the previous plane (same lines: one coalesced 256-byte load per step) and of the two
+//     neighbouring warps (one value each per step) come from the working vector in L2, requested 4 steps
+//     before they enter the rings and checked against the "not ready" pattern there (the value is its own
+//     ready flag, as in the dataflow solve): a producer only has to run a few steps AHEAD, the L2 latency
+//     is off the critical path, and the dependency chain of a step is register/shared-memory only;
+//   * matrix values arrive as one bulk copy (cp.async.bulk, SASS UBLKCP) per warp step from a record
+//     layout built once per factor ([group][step][slot][lane], zeros where a neighbour does not exist),
+//     b and D by 8-byte cp.async eight steps ahead.
+// Warps take (plane, 32-line block) groups in order from a ticket: everything a group waits for belongs
+// to an earlier ticket, i.e. to a warp that already runs -- no co-residency assumption, no deadlock.
+//
+// Absent neighbours are stored as value +0.0; their products (+-0.0) do not change the running sum
+// (it starts at +0.0 and can never be -0.0), so the result is bit-identical to skipping them -- as long
+// as the solution is finite (0 * inf would spread a NaN differently from the reference; a diverged
+// solve is stopped by the harness on its NaN norm either way).
+#pragma once
+
+#include "bis_device.cuh"
+#include "bis_spmv_tma.cuh"
+
+namespace wave {
+
+constexpr int K = 13;          // slots of a lower (<= 27-point) stencil, lexicographic (dz, dy, dx)
+constexpr int RING = 8;        // ring rows (steps); the step loop is unrolled by it
+constexpr int RW = 64;         // ring width: column = lane + 1 + dy (0: line left of the warp, 33: right of it)
+#ifndef WAVE_NST
+#define WAVE_NST 8
+#endif
+#ifndef WAVE_WARPS
+#define WAVE_WARPS 5
+#endif
+#ifndef WAVE_PF
+#define WAVE_PF 24
+#endif
+constexpr int NST = WAVE_NST;  // matrix records in flight per warp (shared memory); divides RING
+constexpr int PF = WAVE_PF;    // steps a record is prefetched into L2 ahead of its bulk copy (0: off)
+constexpr int GA = 4;          // steps between the request of an L2 operand and its entry into a ring
+constexpr int BD = 8;          // steps b and D are requested ahead
+constexpr int WARPS = WAVE_WARPS;
+constexpr int REC_DOUBLES = K * 32;
+constexpr unsigned long long SENT = 0xFFF87E5E7E5E7E5EULL;
+constexpr unsigned long long WATCHDOG_NS = 60000000000ull;
+
+// per warp: records, the two rings, b and D rings, the record barriers
+constexpr size_t SMEM_PER_WARP = (size_t)NST * REC_DOUBLES * 8 + 2 * (size_t)RING * RW * 8 + 2 * (size_t)BD * 32 * 8 + 64;
+
+struct Grid {
+    int nx, ny, nz;            // lines of nx rows, planes of ny lines
+    int W;                     // warps (32-line blocks) per plane
+    int S;                     // steps per group: nx + 62
+    long long n;               // rows
+    int upper;                 // 1: backward solve; all coordinates are those of position p = n-1-row
+};
+
+__host__ __device__ inline long long n_groups(const Grid &g) { return (long long)g.nz * g.W; }
+
+// ---- build ------------------------------------------------------------------------------------------
+// slot of the entry (row, col) or -1 when it does not fit the stencil
+__device__ __forceinline__ int slot_of(const Grid &g, long long p, long long pc) {
+    const long long P = (long long)g.nx * g.ny;
+    const int x = (int)(p % g.nx), y = (int)((p / g.nx) % g.ny);
+    const long long z = p / P;
+    const int xc = (int)(pc % g.nx), yc = (int)((pc / g.nx) % g.ny);
+    const long long zc = pc / P;
+    const int dx = xc - x, dy = yc - y;
+    const long long dz = zc - z;
+    if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 0) return -1;
+    const int k = (((int)dz + 1) * 3 + (dy + 1)) * 3 + (dx + 1);
+    return k < K ? k : -1;     // k == 13 is the diagonal, above it the other triangle
+}
+
+// status[0] != 0: some entry does not fit; also requires ascending columns inside a row (then the slot
+// order is the storage order, i.e. the reference's summation order)
+template <typename RP>
+__global__ void validate_kernel(Grid g, const RP *rp, const int *col, int *status) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < g.n; r += (long long)gridDim.x * blockDim.x) {
+        const long long p = g.upper ? g.n - 1 - r : r;
+        int prev = -1;
+        bool bad = false;
+        for (RP q = rp[r]; q < rp[r + 1]; ++q) {
+            const int c = col[q];
+            if (c <= prev) bad = true;
+            prev = c;
+            const long long pc = g.upper ? g.n - 1 - c : c;
+            if (pc < 0 || pc >= p || slot_of(g, p, pc) < 0) bad = true;
+        }
+        if (bad) atomicExch(status, 1);
+    }
+}
+
+template <typename RP>
+__global__ void fill_kernel(Grid g, const RP *rp, const int *col, const double *val, double *rec) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < g.n; r += (long long)gridDim.x * blockDim.x) {
+        const long long p = g.upper ? g.n - 1 - r : r;
+        const long long P = (long long)g.nx * g.ny;
+        const int x = (int)(p % g.nx), y = (int)((p / g.nx) % g.ny);
+        const long long z = p / P;
+        const int lane = y & 31;
+        const long long grp = z * g.W + (y >> 5);
+        const int ls = x + 2 * lane;
+        double *base = rec + ((size_t)grp * g.S + ls) * REC_DOUBLES + lane;
+        for (RP q = rp[r]; q < rp[r + 1]; ++q) {
+            const int c = col[q];
+            const long long pc = g.upper ? g.n - 1 - c : c;
+            const int k = slot_of(g, p, pc);
+            // an upper factor's storage order (ascending column) is DESCENDING in position space: the kernel
+            // always adds planes 0..12, so its planes are stored mirrored
+            base[(size_t)(g.upper ? K - 1 - k : k) * 32] = val[q];
+        }
+    }
+}
+
+__global__ void fill_u64_kernel(long long n, unsigned long long *p, unsigned long long v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// distinct |row - col| of a triangular factor (a stencil has at most 13): tab[0] = count, tab[1..]
+constexpr int OFFS_CAP = 32;
+template <typename RP>
+__global__ void offsets_kernel(long long n, const RP *rp, const int *col, int *tab) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x)
+        for (RP q = rp[r]; q < rp[r + 1]; ++q) {
+            const long long d = r - col[q];
+            const int o = (int)(d < 0 ? -d : d);
+            bool found = false;
+            for (int guard = 0; guard < 4 * OFFS_CAP && !found; ++guard) {
+                const int cnt = *reinterpret_cast<volatile int *>(tab);
+                for (int i = 0; i < cnt && i < OFFS_CAP; ++i)
+                    if (*reinterpret_cast<volatile int *>(tab + 1 + i) == o) found = true;
+                if (found || cnt >= OFFS_CAP) break;
+                // append: claim slot cnt
+                if (atomicCAS(tab + 1 + cnt, 0, o) == 0) {
+                    atomicMax(tab, cnt + 1);
+                    found = true;
+                } else if (*reinterpret_cast<volatile int *>(tab + 1 + cnt) == o) {
+                    atomicMax(tab, cnt + 1);
+                    found = true;
+                } else {
+                    atomicMax(tab, cnt + 1);   // somebody else's offset sits there: look again
+                }
+            }
+            if (!found) atomicExch(tab + 1 + OFFS_CAP, 1);   // more distinct offsets than a stencil has
+        }
+}
+
+// ---- solve ------------------------------------------------------------------------------------------
+struct Args {
+    Grid g;
+    const double *rec;
+    double *w;                 // working vector of this solve, [group][step][lane]
+    double *w_clean;           // its twin: marked "not ready" here for the next solve
+    unsigned int *ticket;
+    int *errflag;
+    double *x;
+    const double *D;
+    const double *b;
+    int post_mul_d;
+#ifdef BIS_PERF_DEBUG
+    int dbg;                   // perf experiments (results invalid): 1 no record wait, 2 no b/D wait, 4 no x store,
+                               // 8 no L2 operand requests, 16 no w stores, 32 no record copies
+#endif
+};
+#ifdef BIS_PERF_DEBUG
+#define WAVE_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define WAVE_DBG(a, bit) 0
+#endif
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void *gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
+}
+
+// ---- exact division off the critical path ---------------------------------------------------------------------
+// x[r] = (b[r] - sum) / D[r] must be the IEEE quotient (bit parity with the reference's `/`), but D[r] is known a
+// step ahead: the reciprocal r = RN(1/D) is formed there with a full IEEE division, and the dependent chain only
+// carries   q0 = RN(a r) ; e0 = fma(-d, q0, a) ; q1 = fma(e0, r, q0) ; e1 = fma(-d, q1, a) ; q = fma(e1, r, q1)
+// (Markstein: a correctly rounded reciprocal and a faithful quotient make the last fma the correctly rounded
+// quotient).  Exponents far from 0, subnormal numerators and a divisor whose significand is all ones take the
+// IEEE division instead; tools/micro/divcheck.c checks the sequence against `/` on 3e10 operand pairs (random,
+// next to rounding ties, long runs of ones) under exactly this guard: no mismatch.
+__device__ __forceinline__ bool div_guard_d(double d) {
+    const unsigned int hi = (unsigned int)__double2hiint(d), lo = (unsigned int)__double2loint(d);
+    const unsigned int e = (hi >> 20) & 0x7ffu;
+    return (e - 623u > 800u) || ((hi & 0xfffffu) == 0xfffffu && lo == 0xffffffffu);
+}
+__device__ __forceinline__ bool div_guard_a(double a) {   // also zero: the sequence would lose the sign of -0
+    const unsigned int e = ((unsigned int)__double2hiint(a) >> 20) & 0x7ffu;
+    return e - 623u > 800u;
+}
+// RN(1/d) for a divisor that passed div_guard_d: the hardware's 2^-23 estimate, three Newton steps, and the
+// rounding step r = fma(x, fma(-d, x, 1), x) (checked against 1.0 / d on 3e9 divisors, tools/micro/divcheck.c).
+// Branch-free, unlike the IEEE division: it can sit in the same basic block as the step's dependent chain.
+__device__ __forceinline__ double rcp_exact(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ __forceinline__ double div_by_rcp(double a, double d, double r) {
+    const double q0 = mul_rn(a, r);
+    const double e0 = fma(-d, q0, a);
+    const double q1 = fma(e0, r, q0);
+    const double e1 = fma(-d, q1, a);
+    return fma(e1, r, q1);
+}
+
+// everything a warp keeps across the steps of a group.  Addresses are base pointers of the current block of
+// RING steps: step U of the block adds a compile-time multiple of the stride (an immediate offset in the load /
+// store), and the bases move once per block -- no pointer arithmetic inside a step.
+struct State {
+    // shared memory of this warp (lane's column already added where it is fixed)
+    double *recs;              // [NST][K][32] + lane
+    double *ringR;             // [RING][RW] results of this plane, + lane
+    double *ringG;             // [RING][RW] values of the previous plane, + lane
+    double *ringB, *ringD;     // [BD][32] + lane
+    double *ring_edge;         // lanes 0..2: the cell (row 0) their edge value goes to; other lanes: a scratch cell
+    uint64_t *full;            // [NST]
+    int lane;
+    int xp;                    // position of this lane in its line at step U = 0 of the block: s0 - 2 * lane
+    int nx_eff;                // nx, or 0 for a lane without a line (y >= ny): "0 <= xp < nx_eff" is "active"
+    double r_prev;             // own result of the previous step
+    // what the previous step prepared for this one (software pipeline, see step())
+    double pre;                // lower: sum of the products of slots 0..10, in order
+    double pp[K - 2];          // upper: the products of the slots that come AFTER the two late ones in the sum
+    double v_own, v_nb;        // matrix values of the two late slots: own predecessor (x-1) and (x+1, y-1)
+    double bb, dd, rcp;        // b, D and RN(1/D) of this step's row (0, 1, 1 for a lane without a row)
+    bool ieee;                 // this step's divisor needs the IEEE division
+    unsigned long long qm[GA], qe[GA];   // requested L2 operands (main ghost; lanes 0..2: edge values)
+    const double *pm;          // main request at step U = 0 of the block (+ U * 32)
+    int pm_lo, pm_hi;          // ... valid while pm_lo <= ls < pm_hi
+    const double *pe;          // edge request (lanes 0..2), same stride
+    int pe_lo, pe_hi;
+    double *w_out;             // w[grp][s0][lane] (+ U * 32)
+    unsigned long long *wc_out;
+    double *x_out;             // x[row of this lane at step s0] (+- U)
+    const double *b_req, *d_req;   // b / D of the row this lane has at step s0 + BD (+- U)
+    uint64_t pol;
+    const double *rec_next;    // record of step s0 + 1 + NST (+ U records)
+};
+
+// One step, software-pipelined.  Of the 13 products of a row only TWO depend on results of the previous step:
+// the own predecessor (x-1, in a register) and (x+1, y-1), which the lane to the left stored in the ring one
+// step ago.  Everything else -- the record of the NEXT step, its eleven other operands (rings), their products
+// and, for a lower factor, their in-order sum; b, D and 1/D -- is fetched and computed here for the next step, in
+// the shadow of this step's dependent chain
+//     ring -> mul -> add -> add -> sub -> 5 x (mul | fma) -> ring.
+// (A lower factor adds the two late products LAST, so its chain is two adds long.  An upper factor's storage
+// order starts with them: every other product has to be added after them, thirteen dependent adds -- the
+// summation order is the reference's and is not negotiable.)
+// So that the eleven early operands of step ls+1 are in the rings during step ls, the values of the previous
+// plane enter one step earlier than a plain schedule would need them (row ls + 5 at the end of step ls).
+// MAIN: every step of the block lies in [0, S - NST - 2): the range tests of the general form are constants.
+template <int U, bool UPPER, bool MAIN>
+__device__ __forceinline__ void step(const Args &a, State &st, const int s0, const int S) {
+    const int ls = s0 + U;
+    // ---- waits (rarely taken loops), before the straight-line part ---------------------------------------
+    if ((MAIN || (ls + 1 >= 0 && ls + 1 < S)) && !WAVE_DBG(a, 1 | 32)) tma::mbar_wait(&st.full[(U + 1) % NST], (uint32_t)(((ls + 1) / NST) & 1));
+    if (!WAVE_DBG(a, 2)) cp_async_wait<BD - 2>();
+    unsigned long long vm = st.qm[U % GA], ve = st.qe[U % GA];
+    if (__any_sync(0xffffffffu, vm == SENT || ve == SENT)) {
+        const double *pm = st.pm + (U - GA) * 32, *pe = st.pe + (U - GA) * 32;   // where they were requested from
+        unsigned int spins = 0;
+        unsigned long long t_wd = 0;
+        for (;;) {
+            if (vm == SENT) vm = ld_relaxed(pm);
+            if (ve == SENT) ve = ld_relaxed(pe);
+            if (!__any_sync(0xffffffffu, vm == SENT || ve == SENT)) break;
+            if (spins > 8) __nanosleep(spins > 64 ? 400 : 100);   // a group far ahead of the wavefront: stay off the L2
+            bool give_up = false;
+            if ((++spins & 1023u) == 0) {
+                if (t_wd == 0) t_wd = bis_globaltimer();
+                give_up = *reinterpret_cast<volatile int *>(a.errflag) != 0 || bis_globaltimer() - t_wd > WATCHDOG_NS;
+            }
+            if (__any_sync(0xffffffffu, give_up)) {
+                atomicExch(a.errflag, 6);
+                vm = ve = 0ull;
+                break;
+            }
+        }
+    }
+    const int xp = st.xp + U;
+    const bool act = (unsigned)xp < (unsigned)st.nx_eff;
+    const bool in_range = MAIN || (ls >= 0 && ls < S);          // warp-uniform
+    // ======== one basic block: this step's dependent chain and, in its shadow, the next step's operands ========
+    // (x+1, y-1) of this plane: ring row ls - 1, column of the lane to the left
+    const double op_nb = st.ringR[((U + RING - 1) % RING) * RW + 0];
+    double sum;
+    if (!UPPER) {
+        sum = add_rn(st.pre, mul_rn(st.v_nb, op_nb));
+        sum = add_rn(sum, mul_rn(st.v_own, st.r_prev));
+    } else {
+        sum = add_rn(0.0, mul_rn(st.v_own, st.r_prev));
+        sum = add_rn(sum, mul_rn(st.v_nb, op_nb));
+#pragma unroll
+        for (int k = 0; k < K - 2; ++k) sum = add_rn(sum, st.pp[k]);
+    }
+    // a lane without a row divides 1 by 1 (a zero numerator takes the IEEE division) and publishes 0.0
+    const double dd = st.dd;
+    const double num = act ? sub_rn(st.bb, sum) : 1.0;
+    double q = div_by_rcp(num, dd, st.rcp);
+    const bool need_ieee = st.ieee || div_guard_a(num);
+    // for the next step (independent of the chain above)
+    {
+        const double *rv = st.recs + (size_t)((U + 1) % NST) * REC_DOUBLES;
+        double v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = rv[k * 32];
+        const bool act1 = (unsigned)(xp + 1) < (unsigned)st.nx_eff;
+        double pre = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int kk = UPPER ? K - 1 - k : k;       // plane k of the record is stencil slot kk
+            const int dz = kk / 9 - 1, dy = (kk / 3) % 3 - 1, dx = kk % 3 - 1;
+            if (kk == K - 1) {
+                st.v_own = v[k];
+            } else if (kk == K - 2) {
+                st.v_nb = v[k];
+            } else {
+                // produced at step (ls + 1) + dx + 2 dy of the producing line: that is the ring row
+                const double *ring = dz < 0 ? st.ringG : st.ringR;
+                const double o = ring[((U + 1 + dx + 2 * dy + 2 * RING) % RING) * RW + 1 + dy];
+                if (!UPPER) pre = add_rn(pre, mul_rn(v[k], o));
+                else st.pp[k - 2] = mul_rn(v[k], o);
+            }
+        }
+        st.pre = pre;
+        st.bb = act1 ? st.ringB[((U + 1) % BD) * 32] : 0.0;
+        const double d1 = act1 ? st.ringD[((U + 1) % BD) * 32] : 1.0;
+        st.dd = d1;
+        st.ieee = div_guard_d(d1);
+        st.rcp = rcp_exact(st.ieee ? 1.0 : d1);
+    }
+    // ======== end of the block ==============================================================================
+    if (__any_sync(0xffffffffu, need_ieee)) {     // rare: exponents far from 0, an exactly zero numerator, ...
+        if (need_ieee) q = div_rn(num, dd);
+    }
+    const double r = act ? q : 0.0;
+    st.r_prev = r;
+    st.ringR[(U % RING) * RW + 1] = r;
+    // ---- results out ----------------------------------------------------------------------------------------
+    if (in_range && !WAVE_DBG(a, 16)) {
+        __stcg(st.w_out + U * 32, r);                                      // inactive lanes publish 0.0
+        st.wc_out[U * 32] = SENT;
+    }
+    if (act && !WAVE_DBG(a, 4)) st.x_out[UPPER ? -U : U] = a.post_mul_d ? mul_rn(r, dd) : r;
+    // ---- L2 operands requested GA steps ago enter the rings -------------------------------------------------
+    st.ringG[((U + 5) % RING) * RW + 1] = __longlong_as_double((long long)vm);
+    // lane 0: R ring, column 0, row U; lane 1: G ring, column 0, row U + 1; lane 2: G ring, column 33, row U + 5
+    st.ring_edge[(st.lane == 2 ? (U + 5) % RING : (st.lane == 1 ? (U + 1) % RING : U % RING)) * RW] = __longlong_as_double((long long)ve);
+    // ---- requests for later steps ---------------------------------------------------------------------------
+    st.qm[U % GA] = (ls >= st.pm_lo && ls < st.pm_hi && !WAVE_DBG(a, 8)) ? ld_relaxed(st.pm + U * 32) : 0ull;
+    st.qe[U % GA] = (ls >= st.pe_lo && ls < st.pe_hi && !WAVE_DBG(a, 8)) ? ld_relaxed(st.pe + U * 32) : 0ull;
+    if ((unsigned)(xp + BD) < (unsigned)st.nx_eff && !WAVE_DBG(a, 2)) {   // b and D of step ls + BD
+        cp_async8(st.ringB + (U % BD) * 32, st.b_req + (UPPER ? -U : U));
+        cp_async8(st.ringD + (U % BD) * 32, st.d_req + (UPPER ? -U : U));
+    }
+    cp_async_commit();
+    __syncwarp();
+    // the record stage read in this step (that of step ls + 1) is free again: step ls + 1 + NST goes there
+    if (st.lane == 0 && !WAVE_DBG(a, 32)) {
+        if (MAIN || (ls + 1 + NST >= 0 && ls + 1 + NST < S)) {
+            tma::mbar_expect_tx(&st.full[(U + 1) % NST], (uint32_t)(REC_DOUBLES * 8));
+            tma::bulk_g2s(st.recs + (size_t)((U + 1) % NST) * REC_DOUBLES, st.rec_next + (size_t)U * REC_DOUBLES,
+                          (uint32_t)(REC_DOUBLES * 8), &st.full[(U + 1) % NST], st.pol);
+        }
+        // the record stream comes from HBM with nothing but this warp asking for it: it is pulled into L2 well ahead
+        if (PF > 0 && U % 4 == 0 && ls + 1 + NST + PF < S)
+            prefetch_l2_bulk(st.rec_next + (size_t)(U + PF) * REC_DOUBLES, (uint32_t)(4 * REC_DOUBLES * 8));
+    }
+}
+
+// the bases move by one block of RING steps
+template <bool UPPER>
+__device__ __forceinline__ void advance_block(State &st) {
+    st.pm += RING * 32;
+    st.pe += RING * 32;
+    st.w_out += RING * 32;
+    st.wc_out += RING * 32;
+    st.x_out += UPPER ? -RING : RING;
+    st.b_req += UPPER ? -RING : RING;
+    st.d_req += UPPER ? -RING : RING;
+    st.rec_next += (size_t)RING * REC_DOUBLES;
+    st.xp += RING;
+}
+
+template <bool UPPER, bool MAIN>
+__device__ __forceinline__ void block_of_steps(const Args &a, State &st, const int s0, const int S) {
+    step<0, UPPER, MAIN>(a, st, s0, S);
+    step<1, UPPER, MAIN>(a, st, s0, S);
+    step<2, UPPER, MAIN>(a, st, s0, S);
+    step<3, UPPER, MAIN>(a, st, s0, S);
+    step<4, UPPER, MAIN>(a, st, s0, S);
+    step<5, UPPER, MAIN>(a, st, s0, S);
+    step<6, UPPER, MAIN>(a, st, s0, S);
+    step<7, UPPER, MAIN>(a, st, s0, S);
+    advance_block<UPPER>(st);
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(WARPS * 32, 1) wave_kernel(Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *base = smem + (size_t)warp * SMEM_PER_WARP;
+    State st;
+    double *recs0 = reinterpret_cast<double *>(base);
+    double *ringR0 = recs0 + (size_t)NST * REC_DOUBLES;
+    double *ringG0 = ringR0 + RING * RW;
+    double *ringB0 = ringG0 + RING * RW;
+    double *ringD0 = ringB0 + BD * 32;
+    double *scratch = ringG0 + 48;             // a ring column nobody reads (columns 34..63 are padding)
+    st.full = reinterpret_cast<uint64_t *>(ringD0 + BD * 32);
+    st.recs = recs0 + lane;
+    st.ringR = ringR0 + lane;
+    st.ringG = ringG0 + lane;
+    st.ringB = ringB0 + lane;
+    st.ringD = ringD0 + lane;
+    st.ring_edge = lane == 0 ? ringR0 : (lane == 1 ? ringG0 : (lane == 2 ? ringG0 + 33 : scratch));
+    st.lane = lane;
+    st.pol = tma::policy_evict_first();
+    const Grid g = a.g;
+    const int S = g.S;
+    const long long ng = n_groups(g);
+    // records and rings start finite: steps before the first record multiply whatever the stage holds
+    for (int i = lane; i < (int)(SMEM_PER_WARP / 8); i += 32) recs0[i] = 0.0;
+    __syncwarp();
+    for (;;) {
+        long long grp = 0;
+        if (lane == 0) grp = (long long)atomicAdd(a.ticket, 1u);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if (grp >= ng) break;
+        const int z = (int)(grp / g.W), wi = (int)(grp % g.W);
+        const int y = wi * 32 + lane;
+        const long long line_p0 = ((long long)z * g.ny + y) * g.nx;
+        const bool has_left = wi > 0, has_prev = z > 0, has_right = z > 0 && wi + 1 < g.W;
+        const int ls0 = -2 * RING;               // first step of the group (request / ring-fill machinery only)
+        st.nx_eff = y < g.ny ? g.nx : 0;
+        st.xp = ls0 - 2 * lane;
+        st.r_prev = 0.0;
+        st.pre = 0.0;
+        st.v_own = st.v_nb = 0.0;
+        st.bb = 0.0;
+        st.dd = st.rcp = 1.0;
+        st.ieee = false;
+#pragma unroll
+        for (int i = 0; i < K - 2; ++i) st.pp[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < GA; ++i) st.qm[i] = st.qe[i] = 0ull;
+        // main ghost: the own line in the previous plane; requested at step ls for ring row ls + 5 + GA
+        st.pm = a.w + ((long long)(has_prev ? grp - g.W : 0) * S + (ls0 + 5 + GA)) * 32 + lane;
+        st.pm_lo = -(5 + GA);
+        st.pm_hi = has_prev ? S - (5 + GA) : -(1 << 30);
+        // edge values, requested GA steps before they enter their ring.
+        // Lane 0: the line left of the warp (last lane of the previous warp) in THIS plane: ring row rho = ls + GA
+        //   holds position xx = rho + 2, which that warp produced at its step xx + 62.
+        // Lane 1: the same line in the PREVIOUS plane, one step earlier: row rho = ls + GA + 1.
+        // Lane 2: the line right of the warp (lane 0 of the next warp) in the previous plane: row rho = ls + 5 + GA
+        //   holds position xx = rho - 64, produced at that warp's step xx.
+        st.pe = a.w;
+        st.pe_lo = 0;
+        st.pe_hi = -(1 << 30);
+        if (lane == 0 && has_left) {
+            st.pe = a.w + ((long long)(grp - 1) * S + (ls0 + GA + 2 + 62)) * 32 + 31;
+            st.pe_lo = -(GA + 2);
+            st.pe_hi = g.nx - (GA + 2);
+        } else if (lane == 1 && has_left && has_prev) {
+            st.pe = a.w + ((long long)(grp - g.W - 1) * S + (ls0 + GA + 1 + 2 + 62)) * 32 + 31;
+            st.pe_lo = -(GA + 3);
+            st.pe_hi = g.nx - (GA + 3);
+        } else if (lane == 2 && has_right) {
+            st.pe = a.w + ((long long)(grp - g.W + 1) * S + (ls0 + 5 + GA - 64)) * 32;
+            st.pe_lo = 64 - (5 + GA);
+            st.pe_hi = g.nx + 64 - (5 + GA);
+        }
+        st.w_out = a.w + ((long long)grp * S + ls0) * 32 + lane;
+        st.wc_out = reinterpret_cast<unsigned long long *>(a.w_clean) + ((long long)grp * S + ls0) * 32 + lane;
+        {
+            // row of this lane at position xp: p = line_p0 + xp (lower), n - 1 - p (upper)
+            const long long p_now = line_p0 + st.xp;
+            const long long row_now = UPPER ? g.n - 1 - p_now : p_now;
+            st.x_out = a.x + row_now;
+            st.b_req = a.b + (UPPER ? row_now - BD : row_now + BD);
+            st.d_req = a.D + (UPPER ? row_now - BD : row_now + BD);
+        }
+        st.rec_next = a.rec + ((long long)grp * S + (ls0 + 1 + NST)) * REC_DOUBLES;
+        for (int i = lane; i < 2 * RING * RW; i += 32) ringR0[i] = 0.0;   // ringR and ringG are adjacent
+        if (lane == 0) {
+            for (int i = 0; i < NST; ++i) tma::mbar_init(&st.full[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        // the steps before 0 only run the request / ring-fill / prefetch machinery; their number is a multiple of
+        // RING, so that step & 7 is a compile-time constant in step<U>
+        int s0 = ls0;
+        for (; s0 < 0; s0 += RING) block_of_steps<UPPER, false>(a, st, s0, S);
+        for (; s0 + RING + NST + 2 <= S; s0 += RING) block_of_steps<UPPER, true>(a, st, s0, S);
+        for (; s0 < S; s0 += RING) block_of_steps<UPPER, false>(a, st, s0, S);
+        cp_async_wait<0>();
+        __syncwarp();
+        if (lane == 0)
+            for (int i = 0; i < NST; ++i) mbar_inval(&st.full[i]);
+        __syncwarp();
+    }
+}
+
+}  // namespace wave
