@@ -468,13 +468,12 @@ static int build_levels_now(bis_context *c, bis_matrix *T) {
     return rc;
 }
 
-// What a triangular solve needs beyond the CRS arrays.  A factor of a structured-grid matrix gets the
-// records of the stencil wavefront (bis_sptrsv_wave.cuh) and NO level analysis / level-ordered copy (it
-// would double the factor's footprint: HPCG-512 -p sgs fits one GPU only without it); everything else,
-// and any factor a caller forces another variant on, gets the level sets of the dataflow solve.
+// What a triangular solve needs beyond the CRS arrays: the level sets of the dataflow solve, or -- when
+// the stencil wavefront is selected (trsv_variant = 5, opt-in: DESIGN.md 3.2) and the factor is a stencil
+// on a structured grid -- its records (bis_sptrsv_wave.cuh) and NO level analysis / level-ordered copy.
 int bis_build_levels_device(bis_context *c, bis_matrix *T) {
     T->lv.n_slots = T->n_rows;
-    if (c->opt_trsv_variant == 0 || c->opt_trsv_variant == 5) {
+    if (c->opt_trsv_variant == 5) {
         BIS_CHECK(bis_wave_build(c, T));
         if (T->lv.wave.state == 1) {
             // validation is the wavefront's own (strictly triangular, ascending columns, stencil slots)

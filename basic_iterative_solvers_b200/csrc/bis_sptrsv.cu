@@ -444,6 +444,7 @@ int wave_try_grid(bis_context *c, const bis_matrix *T, int nx, int ny, int nz, b
     const int64_t n = T->n_rows;
     if (nx < 1 || ny < 1 || nz < 1 || (int64_t)nx * ny * nz != n) return 0;
     if (nx < 4 && n > 64) return 0;               // the lane skew assumes lines, not dots
+    if ((ny + 31) / 32 > wave::MAX_WARPS) return 0;  // a plane must fit one CTA (its lines share the CTA's rings)
     wave::Grid g;
     g.nx = nx; g.ny = ny; g.nz = nz;
     g.W = (ny + 31) / 32;
@@ -591,16 +592,16 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     wf.w_clean[p] = 0;
     wf.w_clean[1 - p] = c->capturing ? 0 : 1;
     BIS_CUDA(cudaMemsetAsync(wf.d_ticket, 0, sizeof(unsigned int), c->stream));
-    const size_t smem = wave::SMEM_PER_WARP * wave::WARPS;
-    const long long warps_needed = wf.n_groups;
+    // one CTA per plane in flight, all of a plane's 32-line blocks in it (one warp each)
+    const size_t smem = wave::smem_bytes(wf.W);
     int blocks = c->sm_count;
-    if ((long long)blocks * wave::WARPS > warps_needed) blocks = (int)((warps_needed + wave::WARPS - 1) / wave::WARPS);
+    if (blocks > wf.nz) blocks = wf.nz;
     if (a.g.upper) {
         BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<true>), smem));
-        wave::wave_kernel<true><<<blocks, wave::WARPS * 32, smem, c->stream>>>(a);
+        wave::wave_kernel<true><<<blocks, wf.W * 32, smem, c->stream>>>(a);
     } else {
         BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<false>), smem));
-        wave::wave_kernel<false><<<blocks, wave::WARPS * 32, smem, c->stream>>>(a);
+        wave::wave_kernel<false><<<blocks, wf.W * 32, smem, c->stream>>>(a);
     }
     BIS_LAUNCH_CHECK(c);
     return 0;
@@ -626,7 +627,8 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     BIS_CUDA(cudaSetDevice(c->device));
     LevelSets &lv = T->lv;
     if (T->n_rows == 0) return 0;
-    if ((c->opt_trsv_variant == 0 || c->opt_trsv_variant == 5) && lv.wave.state == 1) {
+    if (c->opt_trsv_variant == 5 && lv.wave.state == 0) BIS_CHECK(bis_wave_build(c, T));   // selected after the factor was made
+    if (c->opt_trsv_variant == 5 && lv.wave.state == 1) {
         BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPTRSV));
         BIS_CHECK(wave_solve(c, T, x, D, b, post_mul_d));
         c->wave_solves++;

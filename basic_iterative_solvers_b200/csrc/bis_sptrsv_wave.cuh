@@ -39,7 +39,7 @@ constexpr int K = 13;          // slots of a lower (<= 27-point) stencil, lexico
 constexpr int RING = 8;        // ring rows (steps); the step loop is unrolled by it
 constexpr int RW = 64;         // ring width: column = lane + 1 + dy (0: line left of the warp, 33: right of it)
 #ifndef WAVE_NST
-#define WAVE_NST 8
+#define WAVE_NST 4
 #endif
 #ifndef WAVE_WARPS
 #define WAVE_WARPS 5
@@ -49,15 +49,13 @@ constexpr int RW = 64;         // ring width: column = lane + 1 + dy (0: line le
 #endif
 constexpr int NST = WAVE_NST;  // matrix records in flight per warp (shared memory); divides RING
 constexpr int PF = WAVE_PF;    // steps a record is prefetched into L2 ahead of its bulk copy (0: off)
-constexpr int GA = 4;          // steps between the request of an L2 operand and its entry into a ring
+constexpr int GA = 2;          // steps between the request of an L2 operand and its entry into a ring
 constexpr int BD = 8;          // steps b and D are requested ahead
-constexpr int WARPS = WAVE_WARPS;
+constexpr int MAX_WARPS = 8;   // 32-line blocks per plane a CTA can hold (ny <= 256)
 constexpr int REC_DOUBLES = K * 32;
 constexpr unsigned long long SENT = 0xFFF87E5E7E5E7E5EULL;
 constexpr unsigned long long WATCHDOG_NS = 60000000000ull;
 
-// per warp: records, the two rings, b and D rings, the record barriers
-constexpr size_t SMEM_PER_WARP = (size_t)NST * REC_DOUBLES * 8 + 2 * (size_t)RING * RW * 8 + 2 * (size_t)BD * 32 * 8 + 64;
 
 struct Grid {
     int nx, ny, nz;            // lines of nx rows, planes of ny lines
@@ -239,19 +237,19 @@ __device__ __forceinline__ double div_by_rcp(double a, double d, double r) {
     return fma(e1, r, q1);
 }
 
-// everything a warp keeps across the steps of a group.  Addresses are base pointers of the current block of
+// everything a warp keeps across the steps of a plane.  Addresses are base pointers of the current block of
 // RING steps: step U of the block adds a compile-time multiple of the stride (an immediate offset in the load /
 // store), and the bases move once per block -- no pointer arithmetic inside a step.
 struct State {
-    // shared memory of this warp (lane's column already added where it is fixed)
-    double *recs;              // [NST][K][32] + lane
-    double *ringR;             // [RING][RW] results of this plane, + lane
-    double *ringG;             // [RING][RW] values of the previous plane, + lane
-    double *ringB, *ringD;     // [BD][32] + lane
-    double *ring_edge;         // lanes 0..2: the cell (row 0) their edge value goes to; other lanes: a scratch cell
-    uint64_t *full;            // [NST]
+    // shared memory (lane's column already added where it is fixed)
+    double *recs;              // this warp's [NST][K][32] + lane
+    double *ringR;             // the CTA's [RING][rw] results of this plane, + column of this lane
+    double *ringG;             // the CTA's [RING][rw] values of the previous plane, + column of this lane
+    double *ringB, *ringD;     // this warp's [BD][32] + lane
+    uint64_t *full;            // this warp's [NST]
+    int rw;                    // ring width in doubles
     int lane;
-    int xp;                    // position of this lane in its line at step U = 0 of the block: s0 - 2 * lane
+    int xp;                    // position of this lane in its line at step U = 0 of the block
     int nx_eff;                // nx, or 0 for a lane without a line (y >= ny): "0 <= xp < nx_eff" is "active"
     double r_prev;             // own result of the previous step
     // what the previous step prepared for this one (software pipeline, see step())
@@ -260,47 +258,49 @@ struct State {
     double v_own, v_nb;        // matrix values of the two late slots: own predecessor (x-1) and (x+1, y-1)
     double bb, dd, rcp;        // b, D and RN(1/D) of this step's row (0, 1, 1 for a lane without a row)
     bool ieee;                 // this step's divisor needs the IEEE division
-    unsigned long long qm[GA], qe[GA];   // requested L2 operands (main ghost; lanes 0..2: edge values)
-    const double *pm;          // main request at step U = 0 of the block (+ U * 32)
-    int pm_lo, pm_hi;          // ... valid while pm_lo <= ls < pm_hi
-    const double *pe;          // edge request (lanes 0..2), same stride
-    int pe_lo, pe_hi;
-    double *w_out;             // w[grp][s0][lane] (+ U * 32)
+    unsigned long long qm[GA]; // requested values of the previous plane
+    const double *pm;          // request at step U = 0 of the block (+ U * 32)
+    int pm_lo, pm_hi;          // ... valid while pm_lo <= ls < pm_hi (ls: the warp's LOCAL step)
+    double *w_out;             // w[grp][ls][lane] at U = 0 (+ U * 32)
     unsigned long long *wc_out;
-    double *x_out;             // x[row of this lane at step s0] (+- U)
-    const double *b_req, *d_req;   // b / D of the row this lane has at step s0 + BD (+- U)
+    double *x_out;             // x[row of this lane] at U = 0 (+- U)
+    const double *b_req, *d_req;   // b / D of the row this lane has BD steps later (+- U)
     uint64_t pol;
-    const double *rec_next;    // record of step s0 + 1 + NST (+ U records)
+    const double *rec_next;    // record of local step ls + 1 + NST at U = 0 (+ U records)
 };
 
-// One step, software-pipelined.  Of the 13 products of a row only TWO depend on results of the previous step:
-// the own predecessor (x-1, in a register) and (x+1, y-1), which the lane to the left stored in the ring one
-// step ago.  Everything else -- the record of the NEXT step, its eleven other operands (rings), their products
-// and, for a lower factor, their in-order sum; b, D and 1/D -- is fetched and computed here for the next step, in
-// the shadow of this step's dependent chain
+// One step of one warp, software-pipelined.  A CTA owns a whole plane (all its 32-line blocks, one warp each,
+// warp w running 64 steps behind warp w-1), so every operand that is not a value of the previous plane comes
+// out of the CTA's shared-memory rings: the lines left and right of a warp belong to its neighbour warps.
+// Of the 13 products of a row only TWO depend on results of the previous step: the own predecessor (x-1, in a
+// register) and (x+1, y-1), which the lane to the left stored in the ring one step ago.  Everything else --
+// the record of the NEXT step, its eleven other operands (rings), their products and, for a lower factor, their
+// in-order sum; b, D and 1/D -- is fetched and computed here for the next step, in the shadow of this step's
+// dependent chain
 //     ring -> mul -> add -> add -> sub -> 5 x (mul | fma) -> ring.
 // (A lower factor adds the two late products LAST, so its chain is two adds long.  An upper factor's storage
 // order starts with them: every other product has to be added after them, thirteen dependent adds -- the
 // summation order is the reference's and is not negotiable.)
-// So that the eleven early operands of step ls+1 are in the rings during step ls, the values of the previous
-// plane enter one step earlier than a plain schedule would need them (row ls + 5 at the end of step ls).
-// MAIN: every step of the block lies in [0, S - NST - 2): the range tests of the general form are constants.
+// So that the eleven early operands of step s+1 are in the rings during step s, the values of the previous plane
+// enter one step earlier than a plain schedule would need them (ring row s + 5 at the end of step s).
+// Ring rows are indexed by the CTA's GLOBAL step: the warps' local steps differ by multiples of 64 = 0 mod RING.
+// MAIN: every step of the block lies in [0, Sw - NST - 2) of the warp's local range.
 template <int U, bool UPPER, bool MAIN>
-__device__ __forceinline__ void step(const Args &a, State &st, const int s0, const int S) {
-    const int ls = s0 + U;
+__device__ __forceinline__ void step(const Args &a, State &st, const int l0, const int Sw) {
+    const int ls = l0 + U;                      // local step of this warp
+    const int rw = st.rw;
     // ---- waits (rarely taken loops), before the straight-line part ---------------------------------------
-    if ((MAIN || (ls + 1 >= 0 && ls + 1 < S)) && !WAVE_DBG(a, 1 | 32)) tma::mbar_wait(&st.full[(U + 1) % NST], (uint32_t)(((ls + 1) / NST) & 1));
+    if ((MAIN || (ls + 1 >= 0 && ls + 1 < Sw)) && !WAVE_DBG(a, 1 | 32)) tma::mbar_wait(&st.full[(U + 1) % NST], (uint32_t)(((ls + 1) / NST) & 1));
     if (!WAVE_DBG(a, 2)) cp_async_wait<BD - 2>();
-    unsigned long long vm = st.qm[U % GA], ve = st.qe[U % GA];
-    if (__any_sync(0xffffffffu, vm == SENT || ve == SENT)) {
-        const double *pm = st.pm + (U - GA) * 32, *pe = st.pe + (U - GA) * 32;   // where they were requested from
+    unsigned long long vm = st.qm[U % GA];
+    if (__any_sync(0xffffffffu, vm == SENT)) {
+        const double *pm = st.pm + (U - GA) * 32;   // where it was requested from
         unsigned int spins = 0;
         unsigned long long t_wd = 0;
         for (;;) {
             if (vm == SENT) vm = ld_relaxed(pm);
-            if (ve == SENT) ve = ld_relaxed(pe);
-            if (!__any_sync(0xffffffffu, vm == SENT || ve == SENT)) break;
-            if (spins > 8) __nanosleep(spins > 64 ? 400 : 100);   // a group far ahead of the wavefront: stay off the L2
+            if (!__any_sync(0xffffffffu, vm == SENT)) break;
+            if (spins > 32) __nanosleep(200);   // a plane far ahead of the wavefront: stay off the L2
             bool give_up = false;
             if ((++spins & 1023u) == 0) {
                 if (t_wd == 0) t_wd = bis_globaltimer();
@@ -308,17 +308,17 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int s0, con
             }
             if (__any_sync(0xffffffffu, give_up)) {
                 atomicExch(a.errflag, 6);
-                vm = ve = 0ull;
+                vm = 0ull;
                 break;
             }
         }
     }
     const int xp = st.xp + U;
     const bool act = (unsigned)xp < (unsigned)st.nx_eff;
-    const bool in_range = MAIN || (ls >= 0 && ls < S);          // warp-uniform
+    const bool in_range = MAIN || (ls >= 0 && ls < Sw);          // warp-uniform
     // ======== one basic block: this step's dependent chain and, in its shadow, the next step's operands ========
-    // (x+1, y-1) of this plane: ring row ls - 1, column of the lane to the left
-    const double op_nb = st.ringR[((U + RING - 1) % RING) * RW + 0];
+    // (x+1, y-1) of this plane: ring row s - 1, column of the lane to the left
+    const double op_nb = st.ringR[((U + RING - 1) % RING) * rw + 0];
     double sum;
     if (!UPPER) {
         sum = add_rn(st.pre, mul_rn(st.v_nb, op_nb));
@@ -351,9 +351,9 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int s0, con
             } else if (kk == K - 2) {
                 st.v_nb = v[k];
             } else {
-                // produced at step (ls + 1) + dx + 2 dy of the producing line: that is the ring row
+                // produced at step (s + 1) + dx + 2 dy of the producing line: that is the ring row
                 const double *ring = dz < 0 ? st.ringG : st.ringR;
-                const double o = ring[((U + 1 + dx + 2 * dy + 2 * RING) % RING) * RW + 1 + dy];
+                const double o = ring[((U + 1 + dx + 2 * dy + 2 * RING) % RING) * rw + 1 + dy];
                 if (!UPPER) pre = add_rn(pre, mul_rn(v[k], o));
                 else st.pp[k - 2] = mul_rn(v[k], o);
             }
@@ -371,35 +371,36 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int s0, con
     }
     const double r = act ? q : 0.0;
     st.r_prev = r;
-    st.ringR[(U % RING) * RW + 1] = r;
+    st.ringR[(U % RING) * rw + 1] = r;
     // ---- results out ----------------------------------------------------------------------------------------
     if (in_range && !WAVE_DBG(a, 16)) {
         __stcg(st.w_out + U * 32, r);                                      // inactive lanes publish 0.0
         st.wc_out[U * 32] = SENT;
     }
     if (act && !WAVE_DBG(a, 4)) st.x_out[UPPER ? -U : U] = a.post_mul_d ? mul_rn(r, dd) : r;
-    // ---- L2 operands requested GA steps ago enter the rings -------------------------------------------------
-    st.ringG[((U + 5) % RING) * RW + 1] = __longlong_as_double((long long)vm);
-    // lane 0: R ring, column 0, row U; lane 1: G ring, column 0, row U + 1; lane 2: G ring, column 33, row U + 5
-    st.ring_edge[(st.lane == 2 ? (U + 5) % RING : (st.lane == 1 ? (U + 1) % RING : U % RING)) * RW] = __longlong_as_double((long long)ve);
+    // ---- the value of the previous plane requested GA steps ago enters the ring ----------------------------
+    st.ringG[((U + 5) % RING) * rw + 1] = __longlong_as_double((long long)vm);
     // ---- requests for later steps ---------------------------------------------------------------------------
     st.qm[U % GA] = (ls >= st.pm_lo && ls < st.pm_hi && !WAVE_DBG(a, 8)) ? ld_relaxed(st.pm + U * 32) : 0ull;
-    st.qe[U % GA] = (ls >= st.pe_lo && ls < st.pe_hi && !WAVE_DBG(a, 8)) ? ld_relaxed(st.pe + U * 32) : 0ull;
     if ((unsigned)(xp + BD) < (unsigned)st.nx_eff && !WAVE_DBG(a, 2)) {   // b and D of step ls + BD
         cp_async8(st.ringB + (U % BD) * 32, st.b_req + (UPPER ? -U : U));
         cp_async8(st.ringD + (U % BD) * 32, st.d_req + (UPPER ? -U : U));
     }
     cp_async_commit();
-    __syncwarp();
-    // the record stage read in this step (that of step ls + 1) is free again: step ls + 1 + NST goes there
+}
+
+// after the CTA's barrier of the step: the record stage read in it (that of local step ls + 1) is free again
+template <int U, bool MAIN>
+__device__ __forceinline__ void refill(const Args &a, State &st, const int l0, const int Sw) {
+    const int ls = l0 + U;
     if (st.lane == 0 && !WAVE_DBG(a, 32)) {
-        if (MAIN || (ls + 1 + NST >= 0 && ls + 1 + NST < S)) {
+        if (MAIN || (ls + 1 + NST >= 0 && ls + 1 + NST < Sw)) {
             tma::mbar_expect_tx(&st.full[(U + 1) % NST], (uint32_t)(REC_DOUBLES * 8));
             tma::bulk_g2s(st.recs + (size_t)((U + 1) % NST) * REC_DOUBLES, st.rec_next + (size_t)U * REC_DOUBLES,
                           (uint32_t)(REC_DOUBLES * 8), &st.full[(U + 1) % NST], st.pol);
         }
         // the record stream comes from HBM with nothing but this warp asking for it: it is pulled into L2 well ahead
-        if (PF > 0 && U % 4 == 0 && ls + 1 + NST + PF < S)
+        if (PF > 0 && U % 4 == 0 && ls + 1 + NST + PF < Sw)
             prefetch_l2_bulk(st.rec_next + (size_t)(U + PF) * REC_DOUBLES, (uint32_t)(4 * REC_DOUBLES * 8));
     }
 }
@@ -408,7 +409,6 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int s0, con
 template <bool UPPER>
 __device__ __forceinline__ void advance_block(State &st) {
     st.pm += RING * 32;
-    st.pe += RING * 32;
     st.w_out += RING * 32;
     st.wc_out += RING * 32;
     st.x_out += UPPER ? -RING : RING;
@@ -418,56 +418,65 @@ __device__ __forceinline__ void advance_block(State &st) {
     st.xp += RING;
 }
 
-template <bool UPPER, bool MAIN>
-__device__ __forceinline__ void block_of_steps(const Args &a, State &st, const int s0, const int S) {
-    step<0, UPPER, MAIN>(a, st, s0, S);
-    step<1, UPPER, MAIN>(a, st, s0, S);
-    step<2, UPPER, MAIN>(a, st, s0, S);
-    step<3, UPPER, MAIN>(a, st, s0, S);
-    step<4, UPPER, MAIN>(a, st, s0, S);
-    step<5, UPPER, MAIN>(a, st, s0, S);
-    step<6, UPPER, MAIN>(a, st, s0, S);
-    step<7, UPPER, MAIN>(a, st, s0, S);
-    advance_block<UPPER>(st);
+// One block of RING global steps of the CTA.  `mode`: 0 this warp has nothing to do in the block (it only keeps
+// the CTA's barriers), 1 general steps, 2 MAIN steps.
+template <bool UPPER>
+__device__ __forceinline__ void block_of_steps(const Args &a, State &st, const int mode, const int l0, const int Sw) {
+#define WAVE_STEP(U)                                                                   \
+    if (mode == 2) step<U, UPPER, true>(a, st, l0, Sw);                                \
+    else if (mode == 1) step<U, UPPER, false>(a, st, l0, Sw);                          \
+    __syncthreads();                                                                   \
+    if (mode == 2) refill<U, true>(a, st, l0, Sw);                                     \
+    else if (mode == 1) refill<U, false>(a, st, l0, Sw);
+    WAVE_STEP(0) WAVE_STEP(1) WAVE_STEP(2) WAVE_STEP(3) WAVE_STEP(4) WAVE_STEP(5) WAVE_STEP(6) WAVE_STEP(7)
+#undef WAVE_STEP
+    if (mode != 0) advance_block<UPPER>(st);
 }
 
+// shared memory of a CTA of W warps: per warp records + b/D rings + barriers, then the two rings
+__host__ __device__ inline size_t smem_per_warp() { return (size_t)NST * REC_DOUBLES * 8 + 2 * (size_t)BD * 32 * 8 + 64; }
+__host__ __device__ inline int ring_width(int W) { return 32 * W + 32; }
+__host__ __device__ inline size_t smem_bytes(int W) { return (size_t)W * smem_per_warp() + 2 * (size_t)RING * ring_width(W) * 8; }
+
 template <bool UPPER>
-__global__ void __launch_bounds__(WARPS * 32, 1) wave_kernel(Args a) {
+__global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ long long s_plane;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *base = smem + (size_t)warp * SMEM_PER_WARP;
+    const Grid g = a.g;
+    const int W = g.W;
+    const int Sw = g.S;                                  // local steps of a warp: nx + 62
+    const int rw = ring_width(W);
+    unsigned char *base = smem + (size_t)warp * smem_per_warp();
+    double *ringR0 = reinterpret_cast<double *>(smem + (size_t)W * smem_per_warp());
+    double *ringG0 = ringR0 + RING * rw;
     State st;
     double *recs0 = reinterpret_cast<double *>(base);
-    double *ringR0 = recs0 + (size_t)NST * REC_DOUBLES;
-    double *ringG0 = ringR0 + RING * RW;
-    double *ringB0 = ringG0 + RING * RW;
+    double *ringB0 = recs0 + (size_t)NST * REC_DOUBLES;
     double *ringD0 = ringB0 + BD * 32;
-    double *scratch = ringG0 + 48;             // a ring column nobody reads (columns 34..63 are padding)
     st.full = reinterpret_cast<uint64_t *>(ringD0 + BD * 32);
     st.recs = recs0 + lane;
-    st.ringR = ringR0 + lane;
-    st.ringG = ringG0 + lane;
     st.ringB = ringB0 + lane;
     st.ringD = ringD0 + lane;
-    st.ring_edge = lane == 0 ? ringR0 : (lane == 1 ? ringG0 : (lane == 2 ? ringG0 + 33 : scratch));
+    st.rw = rw;
+    st.ringR = ringR0 + 32 * warp + lane;                // column y + 1 is at [+1]; column y (the line to the left) at [+0]
+    st.ringG = ringG0 + 32 * warp + lane;
     st.lane = lane;
     st.pol = tma::policy_evict_first();
-    const Grid g = a.g;
-    const int S = g.S;
-    const long long ng = n_groups(g);
-    // records and rings start finite: steps before the first record multiply whatever the stage holds
-    for (int i = lane; i < (int)(SMEM_PER_WARP / 8); i += 32) recs0[i] = 0.0;
-    __syncwarp();
+    // records start finite: steps before the first record multiply whatever the stage holds
+    for (int i = lane; i < (int)(smem_per_warp() / 8); i += 32) recs0[i] = 0.0;
+    const int y = warp * 32 + lane;
     for (;;) {
-        long long grp = 0;
-        if (lane == 0) grp = (long long)atomicAdd(a.ticket, 1u);
-        grp = __shfl_sync(0xffffffffu, grp, 0);
-        if (grp >= ng) break;
-        const int z = (int)(grp / g.W), wi = (int)(grp % g.W);
-        const int y = wi * 32 + lane;
-        const long long line_p0 = ((long long)z * g.ny + y) * g.nx;
-        const bool has_left = wi > 0, has_prev = z > 0, has_right = z > 0 && wi + 1 < g.W;
-        const int ls0 = -2 * RING;               // first step of the group (request / ring-fill machinery only)
+        __syncthreads();
+        if (threadIdx.x == 0) s_plane = (long long)atomicAdd(a.ticket, 1u);
+        for (int i = threadIdx.x; i < 2 * RING * rw; i += blockDim.x) ringR0[i] = 0.0;   // ringR and ringG are adjacent
+        __syncthreads();
+        const long long z = s_plane;
+        if (z >= g.nz) break;
+        const long long grp = z * W + warp;
+        const long long line_p0 = (z * g.ny + y) * g.nx;
+        const bool has_prev = z > 0;
+        const int ls0 = -2 * RING;               // first local step of a warp (request / ring-fill machinery only)
         st.nx_eff = y < g.ny ? g.nx : 0;
         st.xp = ls0 - 2 * lane;
         st.r_prev = 0.0;
@@ -479,35 +488,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_kernel(Args a) {
 #pragma unroll
         for (int i = 0; i < K - 2; ++i) st.pp[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < GA; ++i) st.qm[i] = st.qe[i] = 0ull;
-        // main ghost: the own line in the previous plane; requested at step ls for ring row ls + 5 + GA
-        st.pm = a.w + ((long long)(has_prev ? grp - g.W : 0) * S + (ls0 + 5 + GA)) * 32 + lane;
+        for (int i = 0; i < GA; ++i) st.qm[i] = 0ull;
+        // the own line in the previous plane; requested at local step ls for ring row ls + 5 + GA
+        st.pm = a.w + ((has_prev ? grp - W : 0) * Sw + (ls0 + 5 + GA)) * 32 + lane;
         st.pm_lo = -(5 + GA);
-        st.pm_hi = has_prev ? S - (5 + GA) : -(1 << 30);
-        // edge values, requested GA steps before they enter their ring.
-        // Lane 0: the line left of the warp (last lane of the previous warp) in THIS plane: ring row rho = ls + GA
-        //   holds position xx = rho + 2, which that warp produced at its step xx + 62.
-        // Lane 1: the same line in the PREVIOUS plane, one step earlier: row rho = ls + GA + 1.
-        // Lane 2: the line right of the warp (lane 0 of the next warp) in the previous plane: row rho = ls + 5 + GA
-        //   holds position xx = rho - 64, produced at that warp's step xx.
-        st.pe = a.w;
-        st.pe_lo = 0;
-        st.pe_hi = -(1 << 30);
-        if (lane == 0 && has_left) {
-            st.pe = a.w + ((long long)(grp - 1) * S + (ls0 + GA + 2 + 62)) * 32 + 31;
-            st.pe_lo = -(GA + 2);
-            st.pe_hi = g.nx - (GA + 2);
-        } else if (lane == 1 && has_left && has_prev) {
-            st.pe = a.w + ((long long)(grp - g.W - 1) * S + (ls0 + GA + 1 + 2 + 62)) * 32 + 31;
-            st.pe_lo = -(GA + 3);
-            st.pe_hi = g.nx - (GA + 3);
-        } else if (lane == 2 && has_right) {
-            st.pe = a.w + ((long long)(grp - g.W + 1) * S + (ls0 + 5 + GA - 64)) * 32;
-            st.pe_lo = 64 - (5 + GA);
-            st.pe_hi = g.nx + 64 - (5 + GA);
-        }
-        st.w_out = a.w + ((long long)grp * S + ls0) * 32 + lane;
-        st.wc_out = reinterpret_cast<unsigned long long *>(a.w_clean) + ((long long)grp * S + ls0) * 32 + lane;
+        st.pm_hi = has_prev ? Sw - (5 + GA) : -(1 << 30);
+        st.w_out = a.w + (grp * Sw + ls0) * 32 + lane;
+        st.wc_out = reinterpret_cast<unsigned long long *>(a.w_clean) + (grp * Sw + ls0) * 32 + lane;
         {
             // row of this lane at position xp: p = line_p0 + xp (lower), n - 1 - p (upper)
             const long long p_now = line_p0 + st.xp;
@@ -516,24 +503,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_kernel(Args a) {
             st.b_req = a.b + (UPPER ? row_now - BD : row_now + BD);
             st.d_req = a.D + (UPPER ? row_now - BD : row_now + BD);
         }
-        st.rec_next = a.rec + ((long long)grp * S + (ls0 + 1 + NST)) * REC_DOUBLES;
-        for (int i = lane; i < 2 * RING * RW; i += 32) ringR0[i] = 0.0;   // ringR and ringG are adjacent
+        st.rec_next = a.rec + (grp * Sw + (ls0 + 1 + NST)) * REC_DOUBLES;
         if (lane == 0) {
             for (int i = 0; i < NST; ++i) tma::mbar_init(&st.full[i], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        // the steps before 0 only run the request / ring-fill / prefetch machinery; their number is a multiple of
-        // RING, so that step & 7 is a compile-time constant in step<U>
-        int s0 = ls0;
-        for (; s0 < 0; s0 += RING) block_of_steps<UPPER, false>(a, st, s0, S);
-        for (; s0 + RING + NST + 2 <= S; s0 += RING) block_of_steps<UPPER, true>(a, st, s0, S);
-        for (; s0 < S; s0 += RING) block_of_steps<UPPER, false>(a, st, s0, S);
+        // global steps of the CTA: warp w's local step is s - 64 w (its lane 0 is "lane 32 w" of the plane);
+        // all warps walk the same blocks and keep the same barriers
+        const int s_end = 64 * (W - 1) + Sw;
+        for (int s0 = ls0; s0 < s_end; s0 += RING) {
+            const int l0 = s0 - 64 * warp;
+            int mode = 0;
+            if (l0 >= ls0 && l0 < Sw) mode = (l0 >= 0 && l0 + RING + NST + 2 <= Sw) ? 2 : 1;
+            block_of_steps<UPPER>(a, st, mode, l0, Sw);
+        }
         cp_async_wait<0>();
         __syncwarp();
         if (lane == 0)
             for (int i = 0; i < NST; ++i) mbar_inval(&st.full[i]);
-        __syncwarp();
     }
 }
 
