@@ -83,6 +83,7 @@ static int context_init(bis_context *c, int device) {
     if (const char *e = getenv("BIS_SPMV_FUSED")) c->opt_spmv_fused = atoi(e);
     if (const char *e = getenv("BIS_TRSV_VARIANT")) c->opt_trsv_variant = atoi(e);
     if (const char *e = getenv("BIS_GRAPH")) c->opt_graph = atoi(e);
+    if (const char *e = getenv("BIS_PRECOND_INNER_ITERS")) c->opt_precond_inner_iters = atoi(e);
     return 0;
 }
 
@@ -407,6 +408,7 @@ extern "C" int bis_context_get_option(bis_context *c, const char *key, int *valu
     BIS_REQUIRE(c && key && value, "null argument");
     std::string k(key);
     if (k == "graph") *value = (c->opt_graph && c->nranks == 1) ? 1 : 0;
+    else if (k == "precond_inner_iters") *value = c->opt_precond_inner_iters;
     else if (k == "spmv_variant") *value = c->opt_spmv_variant;
     else if (k == "trsv_variant") *value = c->opt_trsv_variant;
     else if (k == "spmv_fused") *value = c->opt_spmv_fused;
@@ -440,6 +442,10 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     }
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
     else if (k == "graph") c->opt_graph = value;
+    else if (k == "precond_inner_iters") {
+        BIS_REQUIRE(value >= 0 && value <= 64, "precond_inner_iters outside [0, 64]");
+        c->opt_precond_inner_iters = value;
+    }
     else if (k == "trsv_variant") c->opt_trsv_variant = value;
     else if (k == "trsv_debug") c->opt_trsv_debug = value;
     else if (k == "vector_cache") {

@@ -100,6 +100,21 @@ struct EpiSub {
     }
 };
 
+// One inner iteration of the two-stage Gauss-Seidel preconditioner (kernels.hpp:321-331):
+// tmp = T work ; tmp = (D_inv * -1) * tmp ; output = output + tmp (sum_vectors: one rounding)
+struct EpiTwoStage {
+    static constexpr int NRED = 0;
+    const double *D_inv;
+    double *w_out;
+    double *out;
+    __device__ __forceinline__ EpiPre load(int64_t r) const { return EpiPre{D_inv[r], out[r], 0.0}; }
+    __device__ __forceinline__ void operator()(int64_t r, double s, const EpiPre &p, double *) const {
+        const double t = mul_rn(mul_rn(p.a, -1.0), s);
+        w_out[r] = t;
+        out[r] = fma(1.0, t, p.b);
+    }
+};
+
 template <typename RP, int LPR, bool GHOST, class Epi>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_vec_kernel(SpmvIn in, Epi epi, RedArgs ra) {
@@ -684,6 +699,15 @@ extern "C" int bis_spmv_sub(bis_context *c, const bis_matrix *T, const double *x
     BIS_REQUIRE(b && out, "bis_spmv_sub: null argument");
     EpiSub e{b, out};
     return spmv_driver(c, T, x, e, -1, -1);
+}
+
+// two_stage_gauss_seidel's inner iteration (kernels.hpp:321-331): work_out = -(D_inv . (T work_in)), output += work_out
+extern "C" int bis_spmv_two_stage(bis_context *c, const bis_matrix *T, const double *D_inv, const double *work_in,
+                                  double *work_out, double *output) {
+    BIS_REQUIRE(D_inv && work_out && output, "bis_spmv_two_stage: null argument");
+    BIS_REQUIRE(work_in != work_out && work_in != output, "bis_spmv_two_stage: the input vector is read by other rows");
+    EpiTwoStage e{D_inv, work_out, output};
+    return spmv_driver(c, T, work_in, e, -1, -1);
 }
 
 // compute_residual, kernels.hpp:155-162 (tmp is materialised as the reference does)

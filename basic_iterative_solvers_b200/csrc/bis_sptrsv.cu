@@ -739,8 +739,25 @@ extern "C" int bis_bsptrsv(bis_context *c, const bis_matrix *U, double *x, const
     return trsv_solve(c, U, x, D, b, 2);
 }
 
-// apply_preconditioner, kernels.hpp:336-414 with PRECOND_OUTER_ITERS = 1 and
-// PRECOND_INNER_ITERS = 0 (CMakeLists.txt:24-25).
+// two_stage_gauss_seidel, kernels.hpp:312-333: a truncated Neumann series for (D + T)^-1 -- SpMV only, no
+// dependency chain.  PRECOND_INNER_ITERS is a compile-time -D of the reference (0 in its default build); here
+// the context option "precond_inner_iters".  work and tmp trade places locally, as the reference's by-value
+// std::swap does; one fused launch per inner iteration (bis_spmv_two_stage).
+static int two_stage_gauss_seidel(bis_context *c, const bis_matrix *strict, double *tmp, double *work,
+                                  const double *D_inv, const double *in, double *out, int64_t n) {
+    BIS_CHECK(bis_elemwise_mult_vectors(c, work, D_inv, in, n, 1.0));
+    BIS_CHECK(bis_copy_vector(c, out, work, n));
+    const int inner = c->opt_precond_inner_iters;
+    if (inner > 0) BIS_REQUIRE(strict && tmp, "bis_apply_preconditioner: 2st with inner iterations needs the strict factor and tmp");
+    for (int it = 1; it <= inner; ++it) {
+        BIS_CHECK(bis_spmv_two_stage(c, strict, D_inv, work, tmp, out));
+        std::swap(work, tmp);
+    }
+    return 0;
+}
+
+// apply_preconditioner, kernels.hpp:336-414 with PRECOND_OUTER_ITERS = 1 (CMakeLists.txt:24); the inner
+// iterations of the two-stage variants follow the context option "precond_inner_iters" (reference default 0).
 extern "C" int bis_apply_preconditioner(bis_context *c, int precond, int64_t n,
                                         const bis_matrix *L, const bis_matrix *U,
                                         const double *A_D, const double *A_D_inv,
@@ -762,15 +779,12 @@ extern "C" int bis_apply_preconditioner(bis_context *c, int precond, int64_t n,
         return bis_bsptrsv(c, U, out, A_D, tmp);                    // out <- (D+U)^-1 tmp
     case BIS_PRECOND_2ST:
         BIS_REQUIRE(work && A_D_inv, "bis_apply_preconditioner: 2st needs work and A_D_inv");
-        BIS_CHECK(bis_elemwise_mult_vectors(c, work, A_D_inv, in, n, 1.0));
-        return bis_copy_vector(c, out, work, n);
+        return two_stage_gauss_seidel(c, L, tmp, work, A_D_inv, in, out, n);
     case BIS_PRECOND_S2ST:
         BIS_REQUIRE(work && A_D_inv, "bis_apply_preconditioner: s2st needs work and A_D_inv");
-        BIS_CHECK(bis_elemwise_mult_vectors(c, work, A_D_inv, in, n, 1.0));
-        BIS_CHECK(bis_copy_vector(c, out, work, n));
+        BIS_CHECK(two_stage_gauss_seidel(c, L, tmp, work, A_D_inv, in, out, n));
         BIS_CHECK(bis_elemwise_mult_vectors(c, out, out, A_D, n, 1.0));
-        BIS_CHECK(bis_elemwise_mult_vectors(c, work, A_D_inv, out, n, 1.0));
-        return bis_copy_vector(c, out, work, n);
+        return two_stage_gauss_seidel(c, U, tmp, work, A_D_inv, out, out, n);
     case BIS_PRECOND_ILU0:
         BIS_REQUIRE(tmp, "bis_apply_preconditioner: ilu0 needs tmp");
         BIS_CHECK(bis_sptrsv(c, L, tmp, L_D, in));   // tmp <- L^-1 in (L_D == 1)

@@ -35,6 +35,9 @@
 #ifndef B_VAL
 #define B_VAL 1.0
 #endif
+#ifndef PRECOND_INNER_ITERS
+#define PRECOND_INNER_ITERS 0   // inner sweeps of -p 2st / s2st (kernels.hpp:321); a context option overrides it
+#endif
 #ifndef ILU0_PIVOT_TOLERANCE
 #define ILU0_PIVOT_TOLERANCE 1e-8
 #endif

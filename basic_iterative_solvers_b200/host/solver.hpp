@@ -70,6 +70,7 @@ class Solver {
         time_per_iteration = new double[max_iters * 2]();
         int v = 0;
         if (dev && bis_context_get_option(dev, "graph", &v) == 0) graphs_on = v != 0;
+        if (dev && bis_context_get_option(dev, "precond_inner_iters", &v) == 0) precond_inner_iters = v;
     }
 
     // ---- CUDA graphs (new in the build) ------------------------------------------------------------
@@ -121,8 +122,11 @@ class Solver {
     virtual void iterate(Timers *) = 0;
     virtual void exchange() = 0;
 
+    int precond_inner_iters = PRECOND_INNER_ITERS;   // the reference's -DPRECOND_INNER_ITERS; here the context option
     bool needs_triangular_factors() const {
-        return method == SolverType::GaussSeidel || method == SolverType::SymmetricGaussSeidel ||
+        const bool two_stage = preconditioner == PrecondType::TwoStageGS || preconditioner == PrecondType::SymmetricTwoStageGS;
+        return (two_stage && precond_inner_iters > 0) ||   // their inner sweeps multiply by the strict factors
+               method == SolverType::GaussSeidel || method == SolverType::SymmetricGaussSeidel ||
                preconditioner == PrecondType::GaussSeidel ||
                preconditioner == PrecondType::BackwardsGaussSeidel ||
                preconditioner == PrecondType::SymmetricGaussSeidel ||

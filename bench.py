@@ -290,9 +290,13 @@ def main():
         print(json.dumps(out), flush=True)
         return
 
-    # NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+    # NCCL prints "NCCL version ..." on stdout: everything but the ONE JSON line goes to stderr (the process's
+    # file descriptor 1 is pointed at stderr for the run; the line is written to the saved descriptor at the end)
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from basic_iterative_solvers_b200 import capi, host
@@ -513,7 +517,7 @@ def main():
                                    "sample": f"unavailable: {ex}"}
     ctx.close()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -309,6 +309,11 @@ int bis_spmv_jacobi(bis_context *ctx, const bis_matrix *A, const double *D,
 /* out = b - T x for a strictly triangular T: gauss_seidel.hpp:30-34, 44-48. */
 int bis_spmv_sub(bis_context *ctx, const bis_matrix *T, const double *x,
                  const double *b, double *out);
+/* One inner iteration of two_stage_gauss_seidel (kernels.hpp:321-331), fused:
+ * work_out = (D_inv * -1) * (T work_in) ; output = output + work_out. */
+int bis_spmv_two_stage(bis_context *ctx, const bis_matrix *T, const double *D_inv /* [dev] */,
+                       const double *work_in /* [dev] */, double *work_out /* [dev] */,
+                       double *output /* [dev] */);
 
 /* CG, methods/cg.hpp:6-54.
  * alpha = s[rz]/s[pAp]; x_new = x_old + alpha p_old; r_new = r_old - alpha Ap;

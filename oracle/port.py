@@ -127,6 +127,11 @@ def factor(rp, col, val, precond="none") -> Factors:
     return f
 
 
+def set_precond_inner_iters(k: int) -> None:
+    """PRECOND_INNER_ITERS of the reference (kernels.hpp:321) for the two-stage GS preconditioners."""
+    load().o_set_precond_inner_iters(int(k))
+
+
 def apply_preconditioner(precond, fac: Factors, inp, inplace=False):
     lib = load()
     n = fac.A_D.size

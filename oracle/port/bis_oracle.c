@@ -184,11 +184,24 @@ static void o_dgemv(const double *A, const double *x, double *y, int nr, int nc)
     }
 }
 
-/* kernels.hpp:312-333 with PRECOND_INNER_ITERS = 0 (CMakeLists.txt:25) */
-static void o_two_stage_gs(double *work, const double *D_inv, const double *in,
-                           double *out, int n) {
+/* kernels.hpp:312-333.  PRECOND_INNER_ITERS is a compile-time -D of the reference (0 in its default build,
+ * CMakeLists.txt:25); here a run-time setting so that one library serves the fixtures of the 0 / 1 / 2
+ * flavours (oracle/_ref/libbis_ref_in1.so, _in2.so).  work / tmp swap LOCALLY (std::swap on by-value
+ * pointers), the caller's buffers keep their roles. */
+static int g_precond_inner_iters = 0;
+void o_set_precond_inner_iters(int k) { g_precond_inner_iters = k; }
+static void o_two_stage_gs(const crs_t *strict, double *tmp, double *work, const double *D_inv,
+                           const double *in, double *out, int n) {
     o_elemwise_mult_vectors(work, D_inv, in, n, 1.0);
     o_copy_vector(out, work, n);
+    for (int inner = 1; inner <= g_precond_inner_iters; ++inner) {
+        o_spmv(strict->n, strict->rp, strict->col, strict->val, work, tmp);
+        o_elemwise_mult_vectors(tmp, D_inv, tmp, n, -1.0);
+        double *t = work;
+        work = tmp;
+        tmp = t;
+        o_sum_vectors(out, out, work, n, 1.0);
+    }
 }
 
 /* kernels.hpp:336-414 (PRECOND_OUTER_ITERS = 1) */
@@ -212,12 +225,12 @@ void o_apply_preconditioner(int p, int n, const crs_t *Ls, const crs_t *Us,
         o_bsptrsv(n, Us->rp, Us->col, Us->val, out, A_D, tmp);
         break;
     case P_2ST:
-        o_two_stage_gs(work, A_D_inv, in, out, n);
+        o_two_stage_gs(Ls, tmp, work, A_D_inv, in, out, n);
         break;
     case P_S2ST:
-        o_two_stage_gs(work, A_D_inv, in, out, n);
+        o_two_stage_gs(Ls, tmp, work, A_D_inv, in, out, n);
         o_elemwise_mult_vectors(out, out, A_D, n, 1.0);
-        o_two_stage_gs(work, A_D_inv, out, out, n);
+        o_two_stage_gs(Us, tmp, work, A_D_inv, out, out, n);
         break;
     case P_ILU0:
         o_sptrsv(n, Ls->rp, Ls->col, Ls->val, tmp, L_D, in);

@@ -24,18 +24,20 @@ _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
-def lib_path(det: bool = False) -> str:
-    return os.path.join(HERE, "_ref", "libbis_ref_det.so" if det else "libbis_ref.so")
+def lib_path(det=False) -> str:
+    """det: False stock flavour, True pinned codegen, "in1" / "in2": -DPRECOND_INNER_ITERS=1 / 2 (two-stage GS)."""
+    name = {False: "libbis_ref.so", True: "libbis_ref_det.so", "in1": "libbis_ref_in1.so", "in2": "libbis_ref_in2.so"}[det]
+    return os.path.join(HERE, "_ref", name)
 
 
-def available(det: bool = False) -> bool:
+def available(det=False) -> bool:
     return os.path.exists(lib_path(det))
 
 
-_libs: dict[bool, C.CDLL] = {}
+_libs: dict = {}
 
 
-def load(det: bool = False) -> C.CDLL:
+def load(det=False) -> C.CDLL:
     if det in _libs:
         return _libs[det]
     lib = C.CDLL(lib_path(det))

@@ -159,9 +159,41 @@ def scale_fixtures():
     np.savez_compressed(os.path.join(OUT, "anderson_dd_12_10_8_scale.npz"), **d)
 
 
-if __name__ == "__main__":
-    import sys
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "twostage"):
     if len(sys.argv) > 1 and sys.argv[1] == "scale":
         scale_fixtures()
         raise SystemExit(0)
     main()
+
+
+def twostage_fixtures():
+    """-p 2st / s2st with PRECOND_INNER_ITERS = 1 and 2: the reference fixes the number of inner sweeps at compile
+    time (kernels.hpp:321, 0 in its default build), so the fixtures come from the flavours oracle/_ref/libbis_ref_in1.so
+    and _in2.so (oracle/Makefile).  Preconditioner applications (bit-exact targets) and whole solves.
+
+        python tests/golden/make_golden.py twostage
+    """
+    d = {}
+    rng = np.random.default_rng(23)
+    for name, (rp, col, val) in (("hpcg12", matgen.hpcg(12)), ("hpcg_10_7_5", matgen.hpcg(10, 7, 5))):
+        n = rp.size - 1
+        x = rng.uniform(-1.0, 1.0, n)
+        d[f"{name}__x"] = x
+        for inner in (1, 2):
+            flav = f"in{inner}"
+            assert refshim.available(flav), "build oracle/_ref first: make -C oracle ref"
+            refshim.load(flav).ref_omp_set_threads(1)
+            fac = refshim.factor(rp, col, val, "sgs", det=flav)
+            for pre in ("2st", "s2st"):
+                d[f"{name}__in{inner}__precond__{pre}"] = refshim.apply_preconditioner(pre, fac, x, det=flav)
+            for method, pre in (("cg", "2st"), ("cg", "s2st"), ("gm", "s2st"), ("bi", "2st")):
+                r = refshim.solve(rp, col, val, method, pre, det=flav, threads=1)
+                key = f"{name}__in{inner}__{method}__{pre}"
+                d[key + "__history"] = r.history
+                d[key + "__meta"] = np.array([r.iter_count, int(r.converged), r.restarts], np.int64)
+                print(f"  {key}: its={r.iter_count} conv={int(r.converged)} r0={r.history[0]:.6e}")
+    np.savez_compressed(os.path.join(OUT, "twostage.npz"), **d)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "twostage":
+    twostage_fixtures()
