@@ -60,6 +60,7 @@ _SIGS = {
     "bis_vector_download": ([c_ctx, C.c_void_p, c_dev, i64], cint),
     "bis_matrix_upload_crs": ([c_ctx, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_mat)], cint),
     "bis_matrix_upload_crs64": ([c_ctx, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_mat)], cint),
+    "bis_matrix_upload_coo": ([c_ctx, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, cint, C.POINTER(c_mat)], cint),
     "bis_matrix_upload_crs_distributed": ([c_ctx, i64, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_mat)], cint),
     "bis_matrix_upload_triangular": ([c_ctx, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, cint, C.POINTER(c_mat)], cint),
     "bis_matrix_generate_hpcg": ([c_ctx, cint, cint, cint, C.POINTER(c_mat)], cint),
@@ -70,6 +71,12 @@ _SIGS = {
     "bis_matrix_extract_diagonal": ([c_ctx, c_mat, c_dev, c_dev], cint),
     "bis_matrix_split_triangular": ([c_ctx, c_mat, C.POINTER(c_mat), C.POINTER(c_mat)], cint),
     "bis_matrix_scale_symmetric": ([c_ctx, c_mat, c_dev], cint),
+    "bis_matrix_colouring_permutation": ([c_ctx, c_mat, C.c_void_p, C.c_void_p, C.POINTER(cint)], cint),
+    "bis_matrix_permute_symmetric": ([c_ctx, c_mat, C.c_void_p, C.c_void_p, C.POINTER(c_mat)], cint),
+    "bis_vector_permute": ([c_ctx, c_dev, c_dev, C.c_void_p, i64], cint),
+    "bis_index_alloc": ([c_ctx, i64, C.POINTER(C.c_void_p)], cint),
+    "bis_index_free": ([c_ctx, C.c_void_p], cint),
+    "bis_index_download": ([c_ctx, C.c_void_p, C.c_void_p, i64], cint),
     "bis_matrix_ilu0": ([c_ctx, c_mat, C.c_double, C.c_double, C.POINTER(c_mat), C.POINTER(c_mat), c_dev, c_dev], cint),
     "bis_spmv": ([c_ctx, c_mat, c_dev, c_dev], cint),
     "bis_sptrsv": ([c_ctx, c_mat, c_dev, c_dev, c_dev], cint),
@@ -286,6 +293,30 @@ class Context:
             self.call("bis_matrix_upload_crs", n, n if n_cols is None else n_cols, int(rp[-1]),
                       _np_ptr(rp), _np_ptr(col), _np_ptr(val), C.byref(m))
         return Matrix(self, m)
+
+    def colouring_permutation(self, A: Matrix):
+        """(perm, inv_perm, n_colours) of the multicolouring permutation of A (host arrays)."""
+        n = A.info()["n_rows"]
+        dp, di = C.c_void_p(), C.c_void_p()
+        self.call("bis_index_alloc", n, C.byref(dp))
+        self.call("bis_index_alloc", n, C.byref(di))
+        nc = cint(0)
+        self.call("bis_matrix_colouring_permutation", A.h, dp, di, C.byref(nc))
+        perm, inv = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.call("bis_index_download", _np_ptr(perm), dp, n)
+        self.call("bis_index_download", _np_ptr(inv), di, n)
+        self.call("bis_index_free", dp)
+        self.call("bis_index_free", di)
+        return perm, inv, int(nc.value)
+
+    def upload_coo(self, n_rows, n_cols, I, J, V, sorted_by_row=False) -> Matrix:
+        I = np.ascontiguousarray(I, np.int32)
+        J = np.ascontiguousarray(J, np.int32)
+        V = np.ascontiguousarray(V, np.float64)
+        h = c_mat()
+        self.call("bis_matrix_upload_coo", int(n_rows), int(n_cols), int(V.size), _np_ptr(I), _np_ptr(J), _np_ptr(V),
+                  int(sorted_by_row), C.byref(h))
+        return Matrix(self, h)
 
     def upload_crs_distributed(self, row_begin, n_global, rp, col, val) -> Matrix:
         rp = np.ascontiguousarray(rp, dtype=np.int64)

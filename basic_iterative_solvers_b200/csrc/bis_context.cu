@@ -84,6 +84,7 @@ static int context_init(bis_context *c, int device) {
     if (const char *e = getenv("BIS_TRSV_VARIANT")) c->opt_trsv_variant = atoi(e);
     if (const char *e = getenv("BIS_GRAPH")) c->opt_graph = atoi(e);
     if (const char *e = getenv("BIS_PRECOND_INNER_ITERS")) c->opt_precond_inner_iters = atoi(e);
+    if (const char *e = getenv("BIS_PERM_MODE")) c->opt_perm_mode = (e[0] == 'C' || e[0] == 'c' || e[0] == '1') ? 1 : 0;
     return 0;
 }
 
@@ -409,6 +410,7 @@ extern "C" int bis_context_get_option(bis_context *c, const char *key, int *valu
     std::string k(key);
     if (k == "graph") *value = (c->opt_graph && c->nranks == 1) ? 1 : 0;
     else if (k == "precond_inner_iters") *value = c->opt_precond_inner_iters;
+    else if (k == "perm_mode") *value = c->opt_perm_mode;
     else if (k == "spmv_variant") *value = c->opt_spmv_variant;
     else if (k == "trsv_variant") *value = c->opt_trsv_variant;
     else if (k == "spmv_fused") *value = c->opt_spmv_fused;
@@ -442,6 +444,10 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     }
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
     else if (k == "graph") c->opt_graph = value;
+    else if (k == "perm_mode") {
+        BIS_REQUIRE(value == 0 || value == 1, "perm_mode: 0 (NONE) or 1 (C, multicolouring)");
+        c->opt_perm_mode = value;
+    }
     else if (k == "precond_inner_iters") {
         BIS_REQUIRE(value >= 0 && value <= 64, "precond_inner_iters outside [0, 64]");
         c->opt_precond_inner_iters = value;

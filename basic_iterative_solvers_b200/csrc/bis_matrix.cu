@@ -6,6 +6,8 @@
 #include <thrust/copy.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
+#include <thrust/iterator/zip_iterator.h>
+#include <thrust/tuple.h>
 #include <thrust/scan.h>
 #include <thrust/sort.h>
 #include <thrust/unique.h>
@@ -142,6 +144,123 @@ extern "C" int bis_matrix_upload_crs_distributed(bis_context *c, int64_t row_beg
         delete A;
         return 1;
     }
+    *out = A;
+    return bis_spmv_prepare(c, A);
+}
+
+// ---- COO -> CRS on the device (convert_coo_to_crs, utilities/utilities.hpp:326-367) -----------------------
+// The reference's reader sorts the entries by row with a STABLE sort (sort_perm, sparse_matrix.hpp:20-30,
+// :332-344) and convert_coo_to_crs counts rows: inside a row the entries keep their order of appearance in the
+// file, which is the summation order of every kernel.  Same here: stable sort by row of (col, val), then
+// row_ptr by binary search.  `sorted` != 0: the entries are already grouped by row (the reference's is_sorted).
+namespace {
+__global__ void coo_row_ptr_kernel(int64_t n_rows, int64_t nnz, const int *I, int *rp32, int64_t *rp64, int *bad) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nnz;     // first entry with I >= r
+        while (lo < hi) {
+            const int64_t m = (lo + hi) >> 1;
+            if (I[m] < r) lo = m + 1;
+            else hi = m;
+        }
+        if (rp32) rp32[r] = (int)lo;
+        else rp64[r] = lo;
+    }
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        if (I[k] < 0 || I[k] >= n_rows) atomicExch(bad, 1);
+        if (k > 0 && I[k - 1] > I[k]) atomicExch(bad, 2);
+    }
+}
+} // namespace
+
+namespace {
+template <typename RP> __global__ void max_row_kernel(int64_t n, const RP *rp, int *out) {
+    int m = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, (int)(rp[r + 1] - rp[r]));
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+} // namespace
+
+// max_row / mean_row of a device CRS (what the SpMV planners look at)
+int bis_matrix_stats(bis_context *c, bis_matrix *A) {
+    int *d_m = nullptr;
+    BIS_CHECK(dev_alloc(&d_m, 1));
+    BIS_CUDA(cudaMemsetAsync(d_m, 0, sizeof(int), c->stream));
+    const int blocks = bis_blocks_for(A->n_rows, 256, c->sm_count * 8);
+    if (A->rp_bytes == 8) max_row_kernel<int64_t><<<blocks, 256, 0, c->stream>>>(A->n_rows, static_cast<const int64_t *>(A->d_rp), d_m);
+    else max_row_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(A->n_rows, static_cast<const int32_t *>(A->d_rp), d_m);
+    BIS_LAUNCH_CHECK(c);
+    int m = 0;
+    BIS_CUDA(cudaMemcpyAsync(&m, d_m, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_m);
+    A->max_row = m;
+    A->mean_row = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
+    return 0;
+}
+
+extern "C" int bis_matrix_upload_coo(bis_context *c, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *I,
+                                     const int32_t *J, const double *V, int sorted, bis_matrix **out) {
+    BIS_REQUIRE(c && out, "bis_matrix_upload_coo: null argument");
+    BIS_REQUIRE(c->nranks == 1, "bis_matrix_upload_coo: single-GPU contexts only");
+    BIS_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && (nnz == 0 || (I && J && V)), "bis_matrix_upload_coo: bad argument");
+    BIS_REQUIRE(n_rows < INT32_MAX && n_cols < INT32_MAX, "bis_matrix_upload_coo: more than 2^31-1 rows");
+    BIS_CUDA(cudaSetDevice(c->device));
+    bis_vector_cache_trim(c);
+    cudaStream_t st = c->stream;
+    bis_matrix *A = new bis_matrix;
+    A->n_rows = n_rows;
+    A->n_cols = n_cols;
+    A->n_rows_global = n_rows;
+    A->nnz = A->nnz_global = nnz;
+    A->rp_bytes = nnz >= (int64_t)INT32_MAX ? 8 : 4;
+    int *d_I = nullptr, *d_bad = nullptr;
+    int rc = dev_alloc(&d_I, (size_t)nnz) | dev_alloc(&d_bad, 1) | dev_alloc(&A->d_col, (size_t)nnz + 8) | dev_alloc(&A->d_val, (size_t)nnz + 8);
+    if (A->rp_bytes == 8) rc |= dev_alloc(reinterpret_cast<int64_t **>(&A->d_rp), (size_t)n_rows + 1 + 8);
+    else rc |= dev_alloc(reinterpret_cast<int32_t **>(&A->d_rp), (size_t)n_rows + 1 + 8);
+    auto fail = [&](int code) {
+        cudaFree(d_I);
+        cudaFree(d_bad);
+        free_matrix_storage(A);
+        delete A;
+        return code;
+    };
+    if (rc) return fail(1);
+    if (nnz) {
+        if (cudaMemcpyAsync(d_I, I, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(A->d_col, J, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(A->d_val, V, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            bis_set_error("bis_matrix_upload_coo: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(1);
+        }
+        if (!sorted) {
+            auto vals = thrust::make_zip_iterator(thrust::make_tuple(thrust::device_pointer_cast(A->d_col), thrust::device_pointer_cast(A->d_val)));
+            thrust::stable_sort_by_key(thrust::cuda::par.on(st), thrust::device_pointer_cast(d_I), thrust::device_pointer_cast(d_I) + nnz, vals);
+        }
+    }
+    cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    coo_row_ptr_kernel<<<bis_blocks_for(std::max<int64_t>(nnz, n_rows + 1), 256, c->sm_count * 8), 256, 0, st>>>(
+        n_rows, nnz, d_I, A->rp_bytes == 4 ? static_cast<int *>(A->d_rp) : nullptr,
+        A->rp_bytes == 8 ? static_cast<int64_t *>(A->d_rp) : nullptr, d_bad);
+    c->launches++;
+    int bad = 0;
+    if (cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        bis_set_error("bis_matrix_upload_coo: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(1);
+    }
+    if (bad) {
+        bis_set_error(bad == 1 ? "bis_matrix_upload_coo: row index outside [0, n_rows)" : "ERROR: converting to CRS.");
+        return fail(2);
+    }
+    cudaFree(d_I);
+    cudaFree(d_bad);
+    if (bis_matrix_stats(c, A) != 0) {
+        free_matrix_storage(A);
+        delete A;
+        return 1;
+    }
+    bis_partition_set(c, n_rows, 0, 0, n_rows);
     *out = A;
     return bis_spmv_prepare(c, A);
 }

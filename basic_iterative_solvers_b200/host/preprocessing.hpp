@@ -48,6 +48,30 @@ inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
         BIS_OK(bis_elemwise_mult_vectors(dev, solver->b, solver->A_D_scale, solver->b, n, 1.0));
     }
 
+    // Permutation seam (preprocessing.hpp:52-65, permute_mat of utilities/smax_helpers.hpp:44-80): with the context
+    // option "perm_mode" = 1 (the reference's PERM_MODE = C) A, b and x_0 are permuted by a multicolouring of A's
+    // graph before factoring -- a LABELLED mode: iteration counts differ from the unpermuted solve, and x_star stays
+    // in the permuted numbering as in the reference.  Like there, the solver's own copy of x_0 (init_structs, above)
+    // is not touched.
+    int perm_mode = 0;
+    if (bis_context_get_option(dev, "perm_mode", &perm_mode) == 0 && perm_mode != 0) {
+        int *d_perm = nullptr, *d_inv = nullptr;
+        BIS_OK(bis_index_alloc(dev, n, &d_perm));
+        BIS_OK(bis_index_alloc(dev, n, &d_inv));
+        BIS_OK(bis_matrix_colouring_permutation(dev, solver->dA->handle, d_perm, d_inv, &solver->n_colours));
+        bis_matrix *pa = nullptr;
+        BIS_OK(bis_matrix_permute_symmetric(dev, solver->dA->handle, d_perm, d_inv, &pa));
+        solver->dA = adopt_device_matrix(dev, pa);
+        BIS_OK(bis_vector_permute(dev, solver->tmp, solver->x_0, d_perm, n));
+        copy_vector(dev, solver->x_0, solver->tmp, n);
+        BIS_OK(bis_vector_permute(dev, solver->tmp, solver->b, d_perm, n));
+        copy_vector(dev, solver->b, solver->tmp, n);
+        init_vector(dev, solver->tmp, 0.0, n);
+        BIS_OK(bis_context_synchronize(dev));
+        bis_index_free(dev, d_perm);
+        bis_index_free(dev, d_inv);
+    }
+
     timers->preprocessing_factor_time.start();
     // peel_diag_crs on the device: A_D and 1/A_D (LU_factors.hpp:827-869); fatal on a missing or zero diagonal
     BIS_OK(bis_matrix_extract_diagonal(dev, solver->dA->handle, solver->A_D, solver->A_D_inv));

@@ -35,9 +35,19 @@ inline void obtain_matrix(const Args *cli_args, Interface *dev, std::unique_ptr<
     const MatrixSpec spec = parse_matrix_spec(cli_args->matrix_file_name);
     if (spec.kind == MatrixSpec::File) {
         MatrixCOO coo;
-        coo.read_from_mtx(spec.path);
-        A = std::make_unique<MatrixCRS>();
-        convert_coo_to_crs(&coo, A.get());
+        if (on_host || !dev) {
+            coo.read_from_mtx(spec.path);
+            A = std::make_unique<MatrixCRS>();
+            convert_coo_to_crs(&coo, A.get());
+            return;
+        }
+        // the entries go to the device in file order; the stable sort by row and the CRS conversion happen there
+        coo.read_from_mtx(spec.path, /*sort_by_row=*/false);
+        dA = std::make_unique<DeviceCRS>();
+        dA->dev = dev;
+        BIS_OK(bis_matrix_upload_coo(dev, coo.n_rows, coo.n_cols, coo.nnz, coo.I.data(), coo.J.data(), coo.values.data(), 0,
+                                     &dA->handle));
+        dA->refresh_info();
         return;
     }
     if (on_host) {

@@ -101,7 +101,8 @@ struct MatrixCOO {
     // MatrixMarket "coordinate" reader: real / integer / pattern, general /
     // symmetric; throws std::runtime_error on I/O problems like the reference
     // (sparse_matrix.hpp:263-299).
-    void read_from_mtx(const std::string &path) {
+    // sort_by_row = false keeps the file's order (the device sorts: bis_matrix_upload_coo)
+    void read_from_mtx(const std::string &path, const bool sort_by_row = true) {
         std::ifstream f(path);
         if (!f) throw std::runtime_error("Unable to open file: " + path);
         std::string line;
@@ -150,7 +151,7 @@ struct MatrixCOO {
         const size_t m = vals.size();
         std::vector<size_t> perm(m);
         std::iota(perm.begin(), perm.end(), 0);
-        std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return rows[a] < rows[b]; });
+        if (sort_by_row) std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return rows[a] < rows[b]; });
         I.resize(m);
         J.resize(m);
         values.resize(m);
@@ -162,7 +163,7 @@ struct MatrixCOO {
         n_rows = nr;
         n_cols = nc;
         nnz = (long)m;
-        is_sorted = true;
+        is_sorted = sort_by_row;
         is_symmetric = false;
     }
 };

@@ -157,6 +157,13 @@ int bis_matrix_upload_crs64(bis_context *ctx, int64_t n_rows, int64_t n_cols,
                             int64_t nnz, const int64_t *row_ptr /* [host] */,
                             const int32_t *col /* [host] */,
                             const double *val /* [host] */, bis_matrix **A);
+/* convert_coo_to_crs (utilities/utilities.hpp:326-367) together with the reader's stable sort by row
+ * (sparse_matrix.hpp:20-30, 332-344), on the device: entries in any order (sorted = 0) or already grouped
+ * by row (sorted != 0, the reference's is_sorted); inside a row they keep their order of appearance,
+ * which is the summation order of every kernel.  0-based indices. */
+int bis_matrix_upload_coo(bis_context *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                          const int32_t *I /* [host] */, const int32_t *J /* [host] */,
+                          const double *V /* [host] */, int sorted, bis_matrix **A /* out */);
 int bis_matrix_upload_crs_distributed(bis_context *ctx, int64_t row_begin,
                                       int64_t n_rows_local,
                                       int64_t n_rows_global, int64_t nnz_local,
@@ -204,6 +211,23 @@ int bis_matrix_extract_diagonal(bis_context *ctx, const bis_matrix *A,
  * ghost columns from the owners. */
 int bis_matrix_scale_symmetric(bis_context *ctx, bis_matrix *A,
                                double *D_scale /* [dev] out */);
+
+/* ---- permutation seam ---------------------------------------------------
+ * The reference permutes A, b and x_0 before factoring when built with SMAX and a PERM_MODE other than NONE
+ * (preprocessing.hpp:52-65; generate_perm / apply_mat_perm / apply_vec_perm, utilities/smax_helpers.hpp:44-80;
+ * modes RS, BFS, C, ...: CMakeLists.txt:129-133).  SMAX is absent, so this is a LABELLED mode of the build with
+ * its own fixtures (option "perm_mode" = 1, the reference's PERM_MODE = C "colouring"): rows ordered by
+ * (colour, row) of a multicolouring of A's graph -- a triangular factor of P A P^T has one level per colour.
+ * Iteration counts differ from the unpermuted solve; x_star stays in the permuted numbering, as in the reference. */
+int bis_matrix_colouring_permutation(bis_context *ctx, const bis_matrix *A, int *perm /* [dev] int32[n], perm[new] = old */,
+                                     int *inv_perm /* [dev] int32[n] */, int *n_colours /* [host] */);
+int bis_matrix_permute_symmetric(bis_context *ctx, const bis_matrix *A, const int *perm /* [dev] */,
+                                 const int *inv_perm /* [dev] */, bis_matrix **B /* out: P A P^T */);
+int bis_vector_permute(bis_context *ctx, double *out /* [dev] */, const double *in /* [dev] */,
+                       const int *perm /* [dev] */, int64_t n);     /* out[i] = in[perm[i]] */
+int bis_index_alloc(bis_context *ctx, int64_t n, int **p /* out [dev] */);
+int bis_index_free(bis_context *ctx, int *p /* [dev] */);
+int bis_index_download(bis_context *ctx, int32_t *dst /* [host] */, const int *src /* [dev] */, int64_t n);
 /* Device split of A into strictly lower / upper triangular matrices with level
  * sets (split_LU_new, LU_factors.hpp:122-309), single-GPU contexts only. */
 int bis_matrix_split_triangular(bis_context *ctx, const bis_matrix *A,

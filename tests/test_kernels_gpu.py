@@ -733,3 +733,42 @@ def test_bad_arguments_fail_loudly(ctx):
         ctx.upload_crs(i32(0, 2, 1), i32(0, 0), f64(1, 1))     # row_ptr not monotone / != nnz
     with pytest.raises(capi.BisError):
         ctx.set_option("no_such_option", 1)
+
+
+def test_device_coo_to_crs_matches_reference_conversion(ctx):
+    """bis_matrix_upload_coo = the reader's stable sort by row + convert_coo_to_crs (utilities.hpp:326-367): entries in
+    file order (shuffled here, several per row, a symmetric pair, an empty row) must come out grouped by row with
+    their order of appearance kept inside a row -- the summation order -- and SpMV on the result must give the
+    oracle's bits on the same CRS."""
+    rng = np.random.default_rng(41)
+    n = 300
+    lens = rng.integers(0, 9, size=n)
+    lens[17] = 0
+    I = np.repeat(np.arange(n), lens).astype(np.int32)
+    J = rng.integers(0, n, size=I.size).astype(np.int32)
+    V = rng.uniform(-1.0, 1.0, size=I.size)
+    perm = rng.permutation(I.size)
+    I, J, V = I[perm], J[perm], V[perm]
+    order = np.argsort(I, kind="stable")
+    rp = np.zeros(n + 1, np.int64)
+    np.add.at(rp, I + 1, 1)
+    rp = np.cumsum(rp)
+    A = ctx.upload_coo(n, n, I, J, V)
+    got_rp, got_col, got_val = A.download()
+    assert np.array_equal(got_rp, rp)
+    assert np.array_equal(got_col, J[order]) and np.array_equal(got_val, V[order])
+    x = rng.uniform(-1.0, 1.0, n)
+    dx, dy = ctx.upload(x), ctx.alloc(n)
+    ctx.call("bis_spmv", A.h, dx, dy)
+    assert np.array_equal(ctx.download(dy, n), port.spmv(rp.astype(np.int32), J[order], V[order], x))
+    # already grouped by row: no sort, same result
+    B = ctx.upload_coo(n, n, I[order], J[order], V[order], sorted_by_row=True)
+    b_rp, b_col, b_val = B.download()
+    assert np.array_equal(b_rp, rp) and np.array_equal(b_col, J[order]) and np.array_equal(b_val, V[order])
+    # a row index out of range is an error, as is an unsorted list passed as sorted
+    with pytest.raises(capi.BisError):
+        ctx.upload_coo(n, n, np.array([0, n], np.int32), np.array([0, 0], np.int32), np.array([1.0, 1.0]))
+    with pytest.raises(capi.BisError):
+        ctx.upload_coo(n, n, np.array([5, 2], np.int32), np.array([0, 0], np.int32), np.array([1.0, 1.0]), sorted_by_row=True)
+    A.free()
+    B.free()
