@@ -575,12 +575,20 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     a.post_mul_d = post_mul_d;
 #ifdef BIS_PERF_DEBUG
     a.dbg = c->opt_wave_debug;
+    a.stamps = nullptr;
+    const char *stamp_file = (c->opt_wave_debug & 64) ? getenv("BIS_WAVE_STAMPS") : nullptr;
+    if (stamp_file) BIS_CUDA(bis_cuda_malloc(&a.stamps, sizeof(unsigned long long) * 2 * (size_t)wf.nz));
 #endif
     if (wf.w_epoch != c->graph_epoch || c->capturing) {   // a graph replay may have used either vector since
         wf.w_clean[0] = wf.w_clean[1] = 0;
         wf.w_epoch = c->graph_epoch;
     }
     int p = wf.w_clean[0] ? 0 : (wf.w_clean[1] ? 1 : -1);
+#ifdef BIS_PERF_DEBUG
+    static bool dbg128_armed = false;   // experiment below: the first such solve fills d_w[0], the later ones only read it
+    if ((c->opt_wave_debug & 128) && dbg128_armed) p = 0;
+    if (c->opt_wave_debug & 128) dbg128_armed = true;
+#endif
     if (p < 0) {
         wave::fill_u64_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((long long)wf.n_groups * wf.S * 32,
                                                                       reinterpret_cast<unsigned long long *>(wf.d_w[0]), wave::SENT);
@@ -591,6 +599,13 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     a.w_clean = wf.d_w[1 - p];
     wf.w_clean[p] = 0;
     wf.w_clean[1 - p] = c->capturing ? 0 : 1;
+#ifdef BIS_PERF_DEBUG
+    if (c->opt_wave_debug & 128) {   // experiment: read the values the PREVIOUS identical solve left (nobody waits)
+        a.w = wf.d_w[0];
+        a.w_clean = wf.d_w[1];
+        wf.w_clean[0] = wf.w_clean[1] = 0;
+    }
+#endif
     BIS_CUDA(cudaMemsetAsync(wf.d_ticket, 0, sizeof(unsigned int), c->stream));
     // one CTA per plane in flight, all of a plane's 32-line blocks in it (one warp each)
     const size_t smem = wave::smem_bytes(wf.W);
@@ -604,6 +619,18 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
         wave::wave_kernel<false><<<blocks, wf.W * 32, smem, c->stream>>>(a);
     }
     BIS_LAUNCH_CHECK(c);
+#ifdef BIS_PERF_DEBUG
+    if (a.stamps) {
+        std::vector<unsigned long long> h(2 * (size_t)wf.nz);
+        BIS_CUDA(cudaMemcpyAsync(h.data(), a.stamps, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+        BIS_CUDA(cudaStreamSynchronize(c->stream));
+        if (FILE *f = fopen(stamp_file, "wb")) {
+            fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+            fclose(f);
+        }
+        cudaFree(a.stamps);
+    }
+#endif
     return 0;
 }
 

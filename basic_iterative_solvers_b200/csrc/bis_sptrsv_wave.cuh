@@ -49,7 +49,10 @@ constexpr int RW = 64;         // ring width: column = lane + 1 + dy (0: line le
 #endif
 constexpr int NST = WAVE_NST;  // matrix records in flight per warp (shared memory); divides RING
 constexpr int PF = WAVE_PF;    // steps a record is prefetched into L2 ahead of its bulk copy (0: off)
-constexpr int GA = 2;          // steps between the request of an L2 operand and its entry into a ring
+#ifndef WAVE_GA
+#define WAVE_GA 3
+#endif
+constexpr int GA = WAVE_GA;    // steps between the request of a value of the previous plane and its entry into a ring
 constexpr int BD = 8;          // steps b and D are requested ahead
 constexpr int MAX_WARPS = 8;   // 32-line blocks per plane a CTA can hold (ny <= 256)
 constexpr int REC_DOUBLES = K * 32;
@@ -171,6 +174,7 @@ struct Args {
 #ifdef BIS_PERF_DEBUG
     int dbg;                   // perf experiments (results invalid): 1 no record wait, 2 no b/D wait, 4 no x store,
                                // 8 no L2 operand requests, 16 no w stores, 32 no record copies
+    unsigned long long *stamps;   // [2 * nz] globaltimer at the first / after the last step of every plane, or nullptr
 #endif
 };
 #ifdef BIS_PERF_DEBUG
@@ -190,6 +194,10 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const double *p) {
 }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// 16 bytes global -> shared through L2 only (cp.async.cg: coherent with what other SMs have stored, unlike .ca)
+__device__ __forceinline__ void cp_async16_cg(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -258,8 +266,8 @@ struct State {
     double v_own, v_nb;        // matrix values of the two late slots: own predecessor (x-1) and (x+1, y-1)
     double bb, dd, rcp;        // b, D and RN(1/D) of this step's row (0, 1, 1 for a lane without a row)
     bool ieee;                 // this step's divisor needs the IEEE division
-    unsigned long long qm[GA]; // requested values of the previous plane
-    const double *pm;          // request at step U = 0 of the block (+ U * 32)
+    double *ringS;             // this warp's [RING][32] staging of requested values of the previous plane (by cp.async)
+    const double *pm;          // request at step U = 0 of the block (+ U * 32), WITHOUT the lane offset
     int pm_lo, pm_hi;          // ... valid while pm_lo <= ls < pm_hi (ls: the warp's LOCAL step)
     double *w_out;             // w[grp][ls][lane] at U = 0 (+ U * 32)
     unsigned long long *wc_out;
@@ -291,10 +299,14 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int l0, con
     const int rw = st.rw;
     // ---- waits (rarely taken loops), before the straight-line part ---------------------------------------
     if ((MAIN || (ls + 1 >= 0 && ls + 1 < Sw)) && !WAVE_DBG(a, 1 | 32)) tma::mbar_wait(&st.full[(U + 1) % NST], (uint32_t)(((ls + 1) / NST) & 1));
-    if (!WAVE_DBG(a, 2)) cp_async_wait<BD - 2>();
-    unsigned long long vm = st.qm[U % GA];
+    // the asynchronous copies of step ls - GA (and older) have landed: the requested values of the previous plane, and
+    // b / D further ahead than they are needed (they were pulled into L2 sixteen steps before their copy)
+    if (!WAVE_DBG(a, 2)) cp_async_wait<GA - 1>();
+    // the value of the previous plane requested GA steps ago.  It travels global -> shared by an asynchronous copy
+    // through L2 only (no register is tied up while it is in flight, and sixteen lanes fetch the row's 256 bytes)
+    unsigned long long vm = reinterpret_cast<const unsigned long long *>(st.ringS)[((U + RING - GA) % RING) * 32 + st.lane];
     if (__any_sync(0xffffffffu, vm == SENT)) {
-        const double *pm = st.pm + (U - GA) * 32;   // where it was requested from
+        const double *pm = st.pm + (U - GA) * 32 + st.lane;   // where it was requested from
         unsigned int spins = 0;
         unsigned long long t_wd = 0;
         for (;;) {
@@ -381,10 +393,18 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int l0, con
     // ---- the value of the previous plane requested GA steps ago enters the ring ----------------------------
     st.ringG[((U + 5) % RING) * rw + 1] = __longlong_as_double((long long)vm);
     // ---- requests for later steps ---------------------------------------------------------------------------
-    st.qm[U % GA] = (ls >= st.pm_lo && ls < st.pm_hi && !WAVE_DBG(a, 8)) ? ld_relaxed(st.pm + U * 32) : 0ull;
+    if (ls >= st.pm_lo && ls < st.pm_hi && !WAVE_DBG(a, 8)) {
+        if (st.lane < 16) cp_async16_cg(st.ringS + (U % RING) * 32 + 2 * st.lane, st.pm + U * 32 + 2 * st.lane);
+    } else {
+        st.ringS[(U % RING) * 32 + st.lane] = 0.0;     // no such value: 0.0 (never "not ready")
+    }
     if ((unsigned)(xp + BD) < (unsigned)st.nx_eff && !WAVE_DBG(a, 2)) {   // b and D of step ls + BD
         cp_async8(st.ringB + (U % BD) * 32, st.b_req + (UPPER ? -U : U));
         cp_async8(st.ringD + (U % BD) * 32, st.d_req + (UPPER ? -U : U));
+    }
+    if (U % 4 == 0 && (unsigned)(xp + BD + 16) < (unsigned)st.nx_eff) {   // ... and the sectors of sixteen steps later into L2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.b_req + (UPPER ? -(U + 16) : (U + 16))));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.d_req + (UPPER ? -(U + 16) : (U + 16))));
     }
     cp_async_commit();
 }
@@ -434,7 +454,7 @@ __device__ __forceinline__ void block_of_steps(const Args &a, State &st, const i
 }
 
 // shared memory of a CTA of W warps: per warp records + b/D rings + barriers, then the two rings
-__host__ __device__ inline size_t smem_per_warp() { return (size_t)NST * REC_DOUBLES * 8 + 2 * (size_t)BD * 32 * 8 + 64; }
+__host__ __device__ inline size_t smem_per_warp() { return (size_t)NST * REC_DOUBLES * 8 + 2 * (size_t)BD * 32 * 8 + (size_t)RING * 32 * 8 + 64; }
 __host__ __device__ inline int ring_width(int W) { return 32 * W + 32; }
 __host__ __device__ inline size_t smem_bytes(int W) { return (size_t)W * smem_per_warp() + 2 * (size_t)RING * ring_width(W) * 8; }
 
@@ -454,7 +474,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
     double *recs0 = reinterpret_cast<double *>(base);
     double *ringB0 = recs0 + (size_t)NST * REC_DOUBLES;
     double *ringD0 = ringB0 + BD * 32;
-    st.full = reinterpret_cast<uint64_t *>(ringD0 + BD * 32);
+    st.ringS = ringD0 + BD * 32;
+    st.full = reinterpret_cast<uint64_t *>(st.ringS + RING * 32);
     st.recs = recs0 + lane;
     st.ringB = ringB0 + lane;
     st.ringD = ringD0 + lane;
@@ -487,10 +508,9 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
         st.ieee = false;
 #pragma unroll
         for (int i = 0; i < K - 2; ++i) st.pp[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < GA; ++i) st.qm[i] = 0ull;
+        for (int i = lane; i < RING * 32; i += 32) st.ringS[i] = 0.0;
         // the own line in the previous plane; requested at local step ls for ring row ls + 5 + GA
-        st.pm = a.w + ((has_prev ? grp - W : 0) * Sw + (ls0 + 5 + GA)) * 32 + lane;
+        st.pm = a.w + ((has_prev ? grp - W : 0) * Sw + (ls0 + 5 + GA)) * 32;
         st.pm_lo = -(5 + GA);
         st.pm_hi = has_prev ? Sw - (5 + GA) : -(1 << 30);
         st.w_out = a.w + (grp * Sw + ls0) * 32 + lane;
@@ -512,6 +532,9 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
         // global steps of the CTA: warp w's local step is s - 64 w (its lane 0 is "lane 32 w" of the plane);
         // all warps walk the same blocks and keep the same barriers
         const int s_end = 64 * (W - 1) + Sw;
+#ifdef BIS_PERF_DEBUG
+        if (a.stamps && threadIdx.x == 0) a.stamps[2 * z] = bis_globaltimer();
+#endif
         for (int s0 = ls0; s0 < s_end; s0 += RING) {
             const int l0 = s0 - 64 * warp;
             int mode = 0;
@@ -522,6 +545,9 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
         __syncwarp();
         if (lane == 0)
             for (int i = 0; i < NST; ++i) mbar_inval(&st.full[i]);
+#ifdef BIS_PERF_DEBUG
+        if (a.stamps && threadIdx.x == 0) a.stamps[2 * z + 1] = bis_globaltimer();
+#endif
     }
 }
 

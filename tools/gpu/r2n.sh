@@ -1,0 +1,13 @@
+#!/bin/bash
+# round-2 GPU batch: full suite after variant 5 / two-stage / COO / permutation, configs table, perm comparison, bench
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+timeout 1700 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/r2n_pytest.log 2>&1
+echo "pytest rc=$?"; tail -n 15 gpurun_out/r2n_pytest.log | cut -c1-250
+timeout 600 python tools/perm_compare.py 128 256 > gpurun_out/r2n_perm.jsonl 2> gpurun_out/r2n_perm.err; echo "perm rc=$?"; cat gpurun_out/r2n_perm.jsonl | cut -c1-900; tail -n 3 gpurun_out/r2n_perm.err
+timeout 600 python tools/bench_configs.py --skip-cpu > gpurun_out/r2n_configs.jsonl 2> gpurun_out/r2n_configs.err; echo "configs rc=$?"
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2n_configs.jsonl'):
+    d=json.loads(l); print(d['config'], d['matrix'][:12], d['method'], d['precond'], 'ms/iter', round(d['gpu_ms_per_iter'],4), 'eager+prof', round(d['gpu_ms_per_iter_profiled_eager'],4), 'spmv', round(d['spmv_ms_per_iter'],4),'trsv', round(d['sptrsv_ms_per_iter'],4), 'vec', round(d['vector_ms_per_iter'],4), 'launches/it', d['launches_per_iter'])
+PY

@@ -15,6 +15,7 @@ with capi.Context(0) as ctx:
     D = ctx.alloc(N)
     ctx.call("bis_matrix_extract_diagonal", A.h, D, None)
     b, x = ctx.upload(np.ones(N)), ctx.alloc(N)
+    ctx.set_option("trsv_variant", 5)
     if dbg:
         ctx.set_option("wave_debug", dbg)
     ctx.call("bis_sptrsv", L.h, x, D, b)
