@@ -468,9 +468,10 @@ static int build_levels_now(bis_context *c, bis_matrix *T) {
     return rc;
 }
 
-// What a triangular solve needs beyond the CRS arrays: the level sets of the dataflow solve, or -- when
-// the stencil wavefront is selected (trsv_variant = 5, opt-in: DESIGN.md 3.2) and the factor is a stencil
-// on a structured grid -- its records (bis_sptrsv_wave.cuh) and NO level analysis / level-ordered copy.
+// What a triangular solve needs beyond the CRS arrays: the level sets of the dataflow solve and -- when the
+// factor is a stencil on a structured grid and the wavefront is expected to be faster (trsv_variant = 0, the
+// default: the cost model in wave_build_t; = 5 forces it and then skips the level analysis) -- the records of
+// the stencil wavefront (bis_sptrsv_wave.cuh).
 int bis_build_levels_device(bis_context *c, bis_matrix *T) {
     T->lv.n_slots = T->n_rows;
     if (c->opt_trsv_variant == 5) {
@@ -480,7 +481,9 @@ int bis_build_levels_device(bis_context *c, bis_matrix *T) {
             return 0;
         }
     }
-    return build_levels_now(c, T);
+    BIS_CHECK(build_levels_now(c, T));
+    if (c->opt_trsv_variant == 0) BIS_CHECK(bis_wave_build(c, T));
+    return 0;
 }
 
 int bis_ensure_levels(bis_context *c, const bis_matrix *T) {

@@ -54,6 +54,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Before a bulk copy OVERWRITES shared memory that was read with ordinary loads: those reads went through the generic
+// proxy, the copy writes through the async proxy, and only this fence orders the two (after whatever barrier told the
+// issuing thread that the readers are done).  Seen to matter in bis_sptrsv_wave.cuh.
+__device__ __forceinline__ void fence_reads_before_bulk_write() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(1024) spmv_tma_kernel(SpmvTmaIn in, Epi epi, R
             tma::mbar_arrive(&bars[st]);
             return;
         }
+        tma::fence_reads_before_bulk_write();
         tma::mbar_expect_tx(&bars[st], n_el * 12u);
         tma::bulk_g2s(sval + (size_t)st * in.cap, in.val + s_al, n_el * 8u, &bars[st], policy);
         tma::bulk_g2s(scol + (size_t)st * in.cap, in.col + s_al, n_el * 4u, &bars[st], policy);

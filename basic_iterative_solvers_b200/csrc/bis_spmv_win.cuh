@@ -429,7 +429,10 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             // the stage must have been released by every consumer warp
-            if (s >= in.nstage) tma::mbar_wait(&empty[st], (uint32_t)(((s / in.nstage) - 1) & 1));
+            if (s >= in.nstage) {
+                tma::mbar_wait(&empty[st], (uint32_t)(((s / in.nstage) - 1) & 1));
+                tma::fence_reads_before_bulk_write();
+            }
             unsigned char *sb = stages + (size_t)st * in.stage_bytes;
             if (lane == 0) tma::mbar_expect_tx(&full[st], total);
             __syncwarp();

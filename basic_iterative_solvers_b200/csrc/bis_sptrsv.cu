@@ -534,6 +534,17 @@ int wave_build_t(bis_context *c, const bis_matrix *T) {
         }
     }
     if (!ok) return 0;
+    if (c->opt_trsv_variant != 5) {
+        // automatic choice (the level analysis has run): the wavefront pays ~5 us per PLANE (hand-over from plane to
+        // plane) plus ~0.5 us per step of one plane, the dataflow solve ~1.3 us per LEVEL (measured on B200,
+        // profiles/r02_wave_*).  27-point factors have 4 levels per plane and win; 7-point factors have 1 and do not.
+        const double est_wave = 5.0 * wf.nz + 0.5 * (wf.nx + 2.0 * wf.ny + 64.0 * (wf.W - 1));
+        const double est_flow = 1.3 * T->lv.n_levels;
+        if (!T->lv.built || est_wave >= est_flow) {
+            wf.state = -2;      // a stencil, but not worth it
+            return 0;
+        }
+    }
     // records (zeros where a neighbour does not exist) and the two working vectors, both "not ready"
     const size_t rec_doubles = (size_t)wf.n_groups * wf.S * wave::REC_DOUBLES;
     const size_t w_doubles = (size_t)wf.n_groups * wf.S * 32;
@@ -613,10 +624,10 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     if (blocks > wf.nz) blocks = wf.nz;
     if (a.g.upper) {
         BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<true>), smem));
-        wave::wave_kernel<true><<<blocks, wf.W * 32, smem, c->stream>>>(a);
+        wave::wave_kernel<true><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
     } else {
         BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<false>), smem));
-        wave::wave_kernel<false><<<blocks, wf.W * 32, smem, c->stream>>>(a);
+        wave::wave_kernel<false><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
     }
     BIS_LAUNCH_CHECK(c);
 #ifdef BIS_PERF_DEBUG
@@ -654,8 +665,11 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     BIS_CUDA(cudaSetDevice(c->device));
     LevelSets &lv = T->lv;
     if (T->n_rows == 0) return 0;
-    if (c->opt_trsv_variant == 5 && lv.wave.state == 0) BIS_CHECK(bis_wave_build(c, T));   // selected after the factor was made
-    if (c->opt_trsv_variant == 5 && lv.wave.state == 1) {
+    if (c->opt_trsv_variant == 5 && (lv.wave.state == 0 || lv.wave.state == -2)) {   // forced after the factor was made
+        lv.wave.state = 0;
+        BIS_CHECK(bis_wave_build(c, T));
+    }
+    if ((c->opt_trsv_variant == 5 || c->opt_trsv_variant == 0) && lv.wave.state == 1) {
         BIS_CHECK(bis_prof_begin(c, BIS_PROF_SPTRSV));
         BIS_CHECK(wave_solve(c, T, x, D, b, post_mul_d));
         c->wave_solves++;

@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(WARPS * 32) chain_kernel(Args a, double *w) {
     __syncwarp();
     auto fetch = [&](int s) {   // lane 0: record of step s into its stage
         const int st = s % NST;
+        tma::fence_reads_before_bulk_write();
         tma::mbar_expect_tx(&full[st], (uint32_t)rb);
         tma::bulk_g2s(base + (size_t)st * rb, a.recs + (size_t)(g0 + s) * rb, (uint32_t)rb, &full[st], pol);
     };

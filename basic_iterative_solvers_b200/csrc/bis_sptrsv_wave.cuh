@@ -1,28 +1,29 @@
-// bis_sptrsv_wave.cuh -- triangular solve, variant 5 ("stencil wavefront"): the default for factors of
-// matrices on a structured grid (<= 27-point stencils in natural ordering: HPCG, Anderson / 7-point, 2-D
-// 5- and 9-point), see DESIGN.md 3.2.  Same row semantics and the same bits as native_sptrsv /
-// native_bsptrsv (kernels.hpp:54-76, 88-107): products separately rounded and added in storage order.
+// bis_sptrsv_wave.cuh -- triangular solve, variant 5 ("stencil wavefront"): chosen automatically for factors of
+// matrices on a structured grid (<= 27-point stencils in natural ordering: HPCG, 2-D 9-point, ...) when the cost
+// model in bis_sptrsv.cu expects it to beat the dataflow solve, see DESIGN.md 3.2.  Same row semantics and the
+// same bits as native_sptrsv / native_bsptrsv (kernels.hpp:54-76, 88-107): products separately rounded and added
+// in storage order.
 //
 // Why: the general dataflow solve (bis_sptrsv.cu) pays one L2 round trip per LEVEL, and HPCG-n has 7n-6
 // of them (1.28 us per level measured, 2.3 ms per sweep at n = 256).  In a stencil factor the rows of an
 // x-line form a chain (row r reads r-1), and everything else a row reads lies in the neighbouring lines
 // y-1 (same plane) and y-1, y, y+1 (previous plane).  So:
-//   * a LANE owns an x-line and walks it one row per step; a WARP owns 32 consecutive lines of a plane,
-//     lane j running 2j steps behind lane 0 (row (x,y) needs (x+1,y-1): the level function is x+2y+4z);
-//   * what a row needs from its own line is a register, what it needs from the lines of its own warp are
-//     the results of at most three steps ago: a shared-memory ring indexed by STEP, so that for every lane
-//     the operand of stencil slot (dx,dy) sits in ring row (step + dx + 2 dy) -- a compile-time offset once
-//     the step loop is unrolled by the ring depth: no index arithmetic, no shuffles, no selects;
-//   * the values of the previous plane (same lines: one coalesced 256-byte load per step) and of the two
-//     neighbouring warps (one value each per step) come from the working vector in L2, requested 4 steps
-//     before they enter the rings and checked against the "not ready" pattern there (the value is its own
-//     ready flag, as in the dataflow solve): a producer only has to run a few steps AHEAD, the L2 latency
-//     is off the critical path, and the dependency chain of a step is register/shared-memory only;
-//   * matrix values arrive as one bulk copy (cp.async.bulk, SASS UBLKCP) per warp step from a record
+//   * a LANE owns an x-line and walks it one row per step; 32 consecutive lines of a plane form a block, lane j
+//     running 2j steps behind lane 0 (row (x,y) needs (x+1,y-1): the level function is x+2y+4z); a CTA owns a
+//     whole plane (up to 8 blocks, block w running 64 steps behind block w-1), two warps per block;
+//   * what a row needs from its own plane are the results of at most three steps ago: a shared-memory ring
+//     indexed by STEP, so that for every lane the operand of stencil slot (dx,dy) sits in ring row
+//     (step + dx + 2 dy) -- no shuffles, no selects;
+//   * the values of the previous plane (same lines: 256 contiguous bytes per block and step) come from the working
+//     vector in L2: an asynchronous copy (cp.async.cg) requested GA steps before they enter the ring, checked
+//     against the "not ready" pattern there (the value is its own ready flag, as in the dataflow solve) and polled
+//     only if the producer has not got that far: a producer only has to run a few steps AHEAD, the L2 latency is
+//     off the critical path, and the dependency chain of a step is register/shared-memory only;
+//   * matrix values arrive as one bulk copy (cp.async.bulk, SASS UBLKCP) per block and step from a record
 //     layout built once per factor ([group][step][slot][lane], zeros where a neighbour does not exist),
 //     b and D by 8-byte cp.async eight steps ahead.
-// Warps take (plane, 32-line block) groups in order from a ticket: everything a group waits for belongs
-// to an earlier ticket, i.e. to a warp that already runs -- no co-residency assumption, no deadlock.
+// CTAs take planes in order from a ticket: everything a plane waits for belongs to an earlier ticket, i.e. to a
+// CTA that already runs -- no co-residency assumption, no deadlock.
 //
 // Absent neighbours are stored as value +0.0; their products (+-0.0) do not change the running sum
 // (it starts at +0.0 and can never be -0.0), so the result is bit-identical to skipping them -- as long
@@ -37,12 +38,8 @@ namespace wave {
 
 constexpr int K = 13;          // slots of a lower (<= 27-point) stencil, lexicographic (dz, dy, dx)
 constexpr int RING = 8;        // ring rows (steps); the step loop is unrolled by it
-constexpr int RW = 64;         // ring width: column = lane + 1 + dy (0: line left of the warp, 33: right of it)
 #ifndef WAVE_NST
 #define WAVE_NST 4
-#endif
-#ifndef WAVE_WARPS
-#define WAVE_WARPS 5
 #endif
 #ifndef WAVE_PF
 #define WAVE_PF 24
@@ -50,10 +47,12 @@ constexpr int RW = 64;         // ring width: column = lane + 1 + dy (0: line le
 constexpr int NST = WAVE_NST;  // matrix records in flight per warp (shared memory); divides RING
 constexpr int PF = WAVE_PF;    // steps a record is prefetched into L2 ahead of its bulk copy (0: off)
 #ifndef WAVE_GA
-#define WAVE_GA 3
+#define WAVE_GA 2
 #endif
 constexpr int GA = WAVE_GA;    // steps between the request of a value of the previous plane and its entry into a ring
 constexpr int BD = 8;          // steps b and D are requested ahead
+constexpr int PH = 2;          // warps per 32-line block; they take its steps in turn (see solve / prepare)
+static_assert(GA % PH == 0 && GA >= PH && RING % PH == 0 && BD % PH == 0 && BD - PH - 1 >= 0, "a request is consumed by the warp that made it");
 constexpr int MAX_WARPS = 8;   // 32-line blocks per plane a CTA can hold (ny <= 256)
 constexpr int REC_DOUBLES = K * 32;
 constexpr unsigned long long SENT = 0xFFF87E5E7E5E7E5EULL;
@@ -245,30 +244,45 @@ __device__ __forceinline__ double div_by_rcp(double a, double d, double r) {
     return fma(e1, r, q1);
 }
 
-// everything a warp keeps across the steps of a plane.  Addresses are base pointers of the current block of
-// RING steps: step U of the block adds a compile-time multiple of the stride (an immediate offset in the load /
-// store), and the bases move once per block -- no pointer arithmetic inside a step.
+// ---- shared memory of a CTA (in doubles) ---------------------------------------------------------------------
+// per 32-line block: the record stages, the b / D rings, the staging of requested previous-plane values, the
+// stages' mbarriers; then the CTA's two rings.  A ring has RING logical rows (steps mod RING) and is stored TWICE
+// (physical rows j and j + RING are copies): a reader whose base is the physical row of an even step reaches every
+// logical row it needs (base - 3 .. base + 6) at a compile-time offset, without wrap-around arithmetic.
+constexpr int RWC = 32 * MAX_WARPS + 32;     // ring width: column y + 1 of the plane's line y, one spare column either side
+constexpr int RROWS = 2 * RING;
+constexpr int SROWS = 4;                     // staging rows (a value sits there GA = 2 steps)
+constexpr int O_RINGB = NST * REC_DOUBLES;
+constexpr int O_RINGD = O_RINGB + BD * 32;
+constexpr int O_RINGS = O_RINGD + BD * 32;
+constexpr int O_FULL = O_RINGS + SROWS * 32;
+constexpr int BLK_DOUBLES = O_FULL + 8;
+constexpr int O_GHOST = RROWS * RWC;         // ring of the previous plane's values, relative to the ring of results
+static_assert(NST == 4 && BD == 8 && GA == 2 && PH == 2 && RING == 8, "the slot arithmetic below is written for these");
+__host__ __device__ inline size_t smem_bytes(int W) { return ((size_t)W * BLK_DOUBLES + 2 * (size_t)RROWS * RWC) * 8; }
+
+extern __shared__ __align__(128) double wave_sm[];   // the CTA's dynamic shared memory (addressed directly: no generic pointers)
+
+// everything a warp keeps across the steps of a plane.  The step loop is unrolled by PH = 2 only (one step in each
+// role, see below): the whole loop body is ~4 KB of code per warp and stays in the instruction caches -- unrolled by
+// the ring depth it was 90 KB, and the warps spent a quarter of their cycles waiting for instructions (ncu,
+// profiles/r02_wave_*).  Addresses are those of the pair's even step; step U adds a compile-time offset.
 struct State {
-    // shared memory (lane's column already added where it is fixed)
-    double *recs;              // this warp's [NST][K][32] + lane
-    double *ringR;             // the CTA's [RING][rw] results of this plane, + column of this lane
-    double *ringG;             // the CTA's [RING][rw] values of the previous plane, + column of this lane
-    double *ringB, *ringD;     // this warp's [BD][32] + lane
-    uint64_t *full;            // this warp's [NST]
-    int rw;                    // ring width in doubles
+    int blk;                   // the block's shared memory (offset in doubles), + lane
+    int ring;                  // ring of results, physical row 0, column of the line LEFT of this lane's line
     int lane;
-    int xp;                    // position of this lane in its line at step U = 0 of the block
     int nx_eff;                // nx, or 0 for a lane without a line (y >= ny): "0 <= xp < nx_eff" is "active"
-    double r_prev;             // own result of the previous step
-    // what the previous step prepared for this one (software pipeline, see step())
+    int ls;                    // local step of the block at U = 0 (even)
+    int xp;                    // position of this lane in its line at U = 0
+    // what prepare<U-1> left for this warp's solve<U>
     double pre;                // lower: sum of the products of slots 0..10, in order
     double pp[K - 2];          // upper: the products of the slots that come AFTER the two late ones in the sum
     double v_own, v_nb;        // matrix values of the two late slots: own predecessor (x-1) and (x+1, y-1)
-    double bb, dd, rcp;        // b, D and RN(1/D) of this step's row (0, 1, 1 for a lane without a row)
-    bool ieee;                 // this step's divisor needs the IEEE division
-    double *ringS;             // this warp's [RING][32] staging of requested values of the previous plane (by cp.async)
-    const double *pm;          // request at step U = 0 of the block (+ U * 32), WITHOUT the lane offset
-    int pm_lo, pm_hi;          // ... valid while pm_lo <= ls < pm_hi (ls: the warp's LOCAL step)
+    // what solve<U-2> left for solve<U>
+    double bb, dd, rcp;        // b, D and RN(1/D) of the step's row (0, 1, 1 for a lane without a row)
+    bool ieee;                 // the step's divisor needs the IEEE division
+    const double *pm;          // request at U = 0 (+ U * 32), WITHOUT the lane offset
+    int pm_lo, pm_hi;          // ... valid while pm_lo <= ls < pm_hi
     double *w_out;             // w[grp][ls][lane] at U = 0 (+ U * 32)
     unsigned long long *wc_out;
     double *x_out;             // x[row of this lane] at U = 0 (+- U)
@@ -277,34 +291,106 @@ struct State {
     const double *rec_next;    // record of local step ls + 1 + NST at U = 0 (+ U records)
 };
 
-// One step of one warp, software-pipelined.  A CTA owns a whole plane (all its 32-line blocks, one warp each,
-// warp w running 64 steps behind warp w-1), so every operand that is not a value of the previous plane comes
-// out of the CTA's shared-memory rings: the lines left and right of a warp belong to its neighbour warps.
-// Of the 13 products of a row only TWO depend on results of the previous step: the own predecessor (x-1, in a
-// register) and (x+1, y-1), which the lane to the left stored in the ring one step ago.  Everything else --
-// the record of the NEXT step, its eleven other operands (rings), their products and, for a lower factor, their
-// in-order sum; b, D and 1/D -- is fetched and computed here for the next step, in the shadow of this step's
-// dependent chain
-//     ring -> mul -> add -> add -> sub -> 5 x (mul | fma) -> ring.
+// A CTA owns a whole plane: its 32-line blocks, PH = 2 warps each, block w running 64 steps behind block w-1.
+// Every operand that is not a value of the previous plane comes out of the CTA's shared-memory rings (the lines
+// left and right of a block belong to its neighbour blocks); ring rows are indexed by the CTA's GLOBAL step (the
+// blocks' local steps differ by multiples of 64 = 0 mod RING).
+//
+// Of the 13 products of a row only TWO depend on the previous step (the own predecessor x-1 and (x+1, y-1), both
+// results of step s-1).  So the two warps of a block take its steps in turn: while one SOLVES step s (solve<U>:
+// the two late products, the end of the sum, the division, the stores), the other PREPARES step s+1 (prepare<U>:
+// the record of s+1, its eleven early operands out of the rings, their products and, for a lower factor, their
+// in-order sum; the arrival of the previous plane's values).  What a warp prepares it solves itself one step
+// later: the hand-over is in registers, and the CTA's one barrier per step orders the rings.
 // (A lower factor adds the two late products LAST, so its chain is two adds long.  An upper factor's storage
 // order starts with them: every other product has to be added after them, thirteen dependent adds -- the
 // summation order is the reference's and is not negotiable.)
 // So that the eleven early operands of step s+1 are in the rings during step s, the values of the previous plane
 // enter one step earlier than a plain schedule would need them (ring row s + 5 at the end of step s).
-// Ring rows are indexed by the CTA's GLOBAL step: the warps' local steps differ by multiples of 64 = 0 mod RING.
-// MAIN: every step of the block lies in [0, Sw - NST - 2) of the warp's local range.
-template <int U, bool UPPER, bool MAIN>
-__device__ __forceinline__ void step(const Args &a, State &st, const int l0, const int Sw) {
-    const int ls = l0 + U;                      // local step of this warp
-    const int rw = st.rw;
+template <int U, bool UPPER>
+__device__ __forceinline__ void solve(const Args &a, State &st, const int Sw) {
+    const int ls = st.ls + U;
+    const int xp = st.xp + U;
+    const bool act = (unsigned)xp < (unsigned)st.nx_eff;
+    const bool in_range = ls >= 0 && ls < Sw;                    // warp-uniform
+    double *rp = wave_sm + st.ring + (st.ls & (RING - 1)) * RWC;      // physical row of the pair's even step
+    // results of step s - 1 (the block's other warp stored them before the barrier): the line to the left, the own line
+    constexpr int RM1 = (U == 0 ? RING - 1 : 0) * RWC;
+    const double op_nb = rp[RM1 + 0];
+    const double r_prev = rp[RM1 + 1];
+    double sum;
+    if (!UPPER) {
+        sum = add_rn(st.pre, mul_rn(st.v_nb, op_nb));
+        sum = add_rn(sum, mul_rn(st.v_own, r_prev));
+    } else {
+        sum = add_rn(0.0, mul_rn(st.v_own, r_prev));
+        sum = add_rn(sum, mul_rn(st.v_nb, op_nb));
+#pragma unroll
+        for (int k = 0; k < K - 2; ++k) sum = add_rn(sum, st.pp[k]);
+    }
+    // a lane without a row divides 1 by 1 (a zero numerator takes the IEEE division) and publishes 0.0
+    const double dd = st.dd;
+    const double num = act ? sub_rn(st.bb, sum) : 1.0;
+    double q = div_by_rcp(num, dd, st.rcp);
+    if (st.ieee || div_guard_a(num)) q = div_rn(num, dd);    // rare: exponents far from 0, an exactly zero numerator, ...
+    const double r = act ? q : 0.0;
+    rp[U * RWC + 1] = r;
+    rp[(U + RING) * RWC + 1] = r;
+    // ---- results out ----------------------------------------------------------------------------------------
+    if (in_range && !WAVE_DBG(a, 16)) {
+        __stcg(st.w_out + U * 32, r);                                      // inactive lanes publish 0.0
+        st.wc_out[U * 32] = SENT;
+    }
+    if (act && !WAVE_DBG(a, 4)) st.x_out[UPPER ? -U : U] = a.post_mul_d ? mul_rn(r, dd) : r;
+    // ---- b, D and 1/D of this warp's next step (ls + PH), off the chain ----------------------------------
+    // b / D were requested BD steps ahead: five younger copy groups of this thread may still be in flight
+    // (prepare / solve / prepare / solve / prepare)
+    if (!WAVE_DBG(a, 2)) cp_async_wait<BD - PH - 1>();
+    double *bd = wave_sm + st.blk + O_RINGB + ((st.ls + PH) & (BD - 1)) * 32 + U * 32;    // slot (ls + PH) % BD: no wrap, st.ls is even
+    {
+        const bool act2 = (unsigned)(xp + PH) < (unsigned)st.nx_eff;
+        st.bb = act2 ? bd[0] : 0.0;
+        double d2 = act2 ? bd[O_RINGD - O_RINGB] : 1.0;
+        if (WAVE_DBG(a, 512) && act2) {    // experiment: straight from global memory
+            st.bb = __ldcg(st.b_req + (UPPER ? -(U + PH - BD) : (U + PH - BD)));
+            d2 = __ldcg(st.d_req + (UPPER ? -(U + PH - BD) : (U + PH - BD)));
+        }
+        st.dd = d2;
+        st.ieee = div_guard_d(d2);
+        st.rcp = rcp_exact(st.ieee ? 1.0 : d2);
+    }
+    if ((unsigned)(xp + PH + BD) < (unsigned)st.nx_eff && !WAVE_DBG(a, 2)) {   // b and D of step ls + PH + BD, into the slots just read
+        cp_async8(bd, st.b_req + (UPPER ? -(U + PH) : (U + PH)));
+        cp_async8(bd + (O_RINGD - O_RINGB), st.d_req + (UPPER ? -(U + PH) : (U + PH)));
+    }
+    if ((ls & 2) == 0 && (unsigned)(xp + PH + BD + 16) < (unsigned)st.nx_eff) {   // ... and the sectors of sixteen steps later into L2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.b_req + (UPPER ? -(U + PH + 16) : (U + PH + 16))));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.d_req + (UPPER ? -(U + PH + 16) : (U + PH + 16))));
+    }
+    cp_async_commit();
+}
+
+// shared-memory places of the record of local step ls + 1 (stage (ls + 1) % NST), for st.ls even
+template <int U>
+__device__ __forceinline__ int rec_stage(const State &st) {
+    return U == 0 ? (st.ls & 2) + 1 : ((st.ls & 2) ^ 2);
+}
+
+// the block's other warp, during the same step: everything of step ls + 1 that does not need the result of step ls
+template <int U, bool UPPER>
+__device__ __forceinline__ void prepare(const Args &a, State &st, const int Sw) {
+    const int ls = st.ls + U;
+    const int stage = rec_stage<U>(st);
     // ---- waits (rarely taken loops), before the straight-line part ---------------------------------------
-    if ((MAIN || (ls + 1 >= 0 && ls + 1 < Sw)) && !WAVE_DBG(a, 1 | 32)) tma::mbar_wait(&st.full[(U + 1) % NST], (uint32_t)(((ls + 1) / NST) & 1));
-    // the asynchronous copies of step ls - GA (and older) have landed: the requested values of the previous plane, and
-    // b / D further ahead than they are needed (they were pulled into L2 sixteen steps before their copy)
-    if (!WAVE_DBG(a, 2)) cp_async_wait<GA - 1>();
-    // the value of the previous plane requested GA steps ago.  It travels global -> shared by an asynchronous copy
-    // through L2 only (no register is tied up while it is in flight, and sixteen lanes fetch the row's 256 bytes)
-    unsigned long long vm = reinterpret_cast<const unsigned long long *>(st.ringS)[((U + RING - GA) % RING) * 32 + st.lane];
+    if (ls + 1 >= 0 && ls + 1 < Sw && !WAVE_DBG(a, 1 | 32))
+        tma::mbar_wait(reinterpret_cast<uint64_t *>(wave_sm + (st.blk - st.lane) + O_FULL) + stage, (uint32_t)(((ls + 1) / NST) & 1));
+    // the value of the previous plane this warp requested GA steps ago: global -> shared by an asynchronous copy
+    // through L2 only (no register is tied up while it is in flight, sixteen lanes fetch the row's 256 bytes);
+    // GA - 1 younger copy groups of this thread may still be in flight
+    cp_async_wait<GA - 1>();
+    __syncwarp();
+    const int o_stage = st.blk + O_RINGS + U * 32;              // + slot * 32
+    unsigned long long vm = reinterpret_cast<const unsigned long long *>(wave_sm)[o_stage + ((st.ls & 2) ^ 2) * 32];   // slot (ls - GA) % SROWS
     if (__any_sync(0xffffffffu, vm == SENT)) {
         const double *pm = st.pm + (U - GA) * 32 + st.lane;   // where it was requested from
         unsigned int spins = 0;
@@ -325,34 +411,13 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int l0, con
             }
         }
     }
-    const int xp = st.xp + U;
-    const bool act = (unsigned)xp < (unsigned)st.nx_eff;
-    const bool in_range = MAIN || (ls >= 0 && ls < Sw);          // warp-uniform
-    // ======== one basic block: this step's dependent chain and, in its shadow, the next step's operands ========
-    // (x+1, y-1) of this plane: ring row s - 1, column of the lane to the left
-    const double op_nb = st.ringR[((U + RING - 1) % RING) * rw + 0];
-    double sum;
-    if (!UPPER) {
-        sum = add_rn(st.pre, mul_rn(st.v_nb, op_nb));
-        sum = add_rn(sum, mul_rn(st.v_own, st.r_prev));
-    } else {
-        sum = add_rn(0.0, mul_rn(st.v_own, st.r_prev));
-        sum = add_rn(sum, mul_rn(st.v_nb, op_nb));
-#pragma unroll
-        for (int k = 0; k < K - 2; ++k) sum = add_rn(sum, st.pp[k]);
-    }
-    // a lane without a row divides 1 by 1 (a zero numerator takes the IEEE division) and publishes 0.0
-    const double dd = st.dd;
-    const double num = act ? sub_rn(st.bb, sum) : 1.0;
-    double q = div_by_rcp(num, dd, st.rcp);
-    const bool need_ieee = st.ieee || div_guard_a(num);
-    // for the next step (independent of the chain above)
+    const int s8 = st.ls & (RING - 1);
+    const double *rp = wave_sm + st.ring + s8 * RWC;
     {
-        const double *rv = st.recs + (size_t)((U + 1) % NST) * REC_DOUBLES;
+        const double *rv = wave_sm + st.blk + stage * REC_DOUBLES;
         double v[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = rv[k * 32];
-        const bool act1 = (unsigned)(xp + 1) < (unsigned)st.nx_eff;
         double pre = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -363,144 +428,108 @@ __device__ __forceinline__ void step(const Args &a, State &st, const int l0, con
             } else if (kk == K - 2) {
                 st.v_nb = v[k];
             } else {
-                // produced at step (s + 1) + dx + 2 dy of the producing line: that is the ring row
-                const double *ring = dz < 0 ? st.ringG : st.ringR;
-                const double o = ring[((U + 1 + dx + 2 * dy + 2 * RING) % RING) * rw + 1 + dy];
+                // produced at step (s + 1) + dx + 2 dy of the producing line: logical ring row U + 1 + dx + 2 dy
+                // relative to the pair's even step, i.e. -2 .. 5: a copy of it sits at a fixed physical distance
+                const int d = U + 1 + dx + 2 * dy;
+                const double o = rp[(dz < 0 ? O_GHOST : 0) + (d < 0 ? d + RING : d) * RWC + 1 + dy];
                 if (!UPPER) pre = add_rn(pre, mul_rn(v[k], o));
                 else st.pp[k - 2] = mul_rn(v[k], o);
             }
         }
         st.pre = pre;
-        st.bb = act1 ? st.ringB[((U + 1) % BD) * 32] : 0.0;
-        const double d1 = act1 ? st.ringD[((U + 1) % BD) * 32] : 1.0;
-        st.dd = d1;
-        st.ieee = div_guard_d(d1);
-        st.rcp = rcp_exact(st.ieee ? 1.0 : d1);
     }
-    // ======== end of the block ==============================================================================
-    if (__any_sync(0xffffffffu, need_ieee)) {     // rare: exponents far from 0, an exactly zero numerator, ...
-        if (need_ieee) q = div_rn(num, dd);
+    // ---- the value of the previous plane requested GA steps ago enters the ring (logical row ls + 5) ------
+    {
+        int row = s8 + U + 5;
+        if (row >= RING) row -= RING;
+        double *gp = wave_sm + st.ring + O_GHOST + row * RWC + 1;
+        const double gv = __longlong_as_double((long long)vm);
+        gp[0] = gv;
+        gp[RING * RWC] = gv;
     }
-    const double r = act ? q : 0.0;
-    st.r_prev = r;
-    st.ringR[(U % RING) * rw + 1] = r;
-    // ---- results out ----------------------------------------------------------------------------------------
-    if (in_range && !WAVE_DBG(a, 16)) {
-        __stcg(st.w_out + U * 32, r);                                      // inactive lanes publish 0.0
-        st.wc_out[U * 32] = SENT;
-    }
-    if (act && !WAVE_DBG(a, 4)) st.x_out[UPPER ? -U : U] = a.post_mul_d ? mul_rn(r, dd) : r;
-    // ---- the value of the previous plane requested GA steps ago enters the ring ----------------------------
-    st.ringG[((U + 5) % RING) * rw + 1] = __longlong_as_double((long long)vm);
-    // ---- requests for later steps ---------------------------------------------------------------------------
+    // ---- request for a later step (consumed by this same warp: GA is a multiple of PH) ---------------------
+    const int o_req = (st.blk - st.lane) + O_RINGS + ((st.ls & 2) + U) * 32;     // slot ls % SROWS
     if (ls >= st.pm_lo && ls < st.pm_hi && !WAVE_DBG(a, 8)) {
-        if (st.lane < 16) cp_async16_cg(st.ringS + (U % RING) * 32 + 2 * st.lane, st.pm + U * 32 + 2 * st.lane);
+        if (st.lane < 16) cp_async16_cg(wave_sm + o_req + 2 * st.lane, st.pm + U * 32 + 2 * st.lane);
     } else {
-        st.ringS[(U % RING) * 32 + st.lane] = 0.0;     // no such value: 0.0 (never "not ready")
-    }
-    if ((unsigned)(xp + BD) < (unsigned)st.nx_eff && !WAVE_DBG(a, 2)) {   // b and D of step ls + BD
-        cp_async8(st.ringB + (U % BD) * 32, st.b_req + (UPPER ? -U : U));
-        cp_async8(st.ringD + (U % BD) * 32, st.d_req + (UPPER ? -U : U));
-    }
-    if (U % 4 == 0 && (unsigned)(xp + BD + 16) < (unsigned)st.nx_eff) {   // ... and the sectors of sixteen steps later into L2
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.b_req + (UPPER ? -(U + 16) : (U + 16))));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.d_req + (UPPER ? -(U + 16) : (U + 16))));
+        wave_sm[o_req + st.lane] = 0.0;     // no such value: 0.0 (never "not ready")
     }
     cp_async_commit();
 }
 
 // after the CTA's barrier of the step: the record stage read in it (that of local step ls + 1) is free again
-template <int U, bool MAIN>
-__device__ __forceinline__ void refill(const Args &a, State &st, const int l0, const int Sw) {
-    const int ls = l0 + U;
+template <int U>
+__device__ __forceinline__ void refill(const Args &a, State &st, const int Sw) {
+    const int ls = st.ls + U;
     if (st.lane == 0 && !WAVE_DBG(a, 32)) {
-        if (MAIN || (ls + 1 + NST >= 0 && ls + 1 + NST < Sw)) {
-            tma::mbar_expect_tx(&st.full[(U + 1) % NST], (uint32_t)(REC_DOUBLES * 8));
-            tma::bulk_g2s(st.recs + (size_t)((U + 1) % NST) * REC_DOUBLES, st.rec_next + (size_t)U * REC_DOUBLES,
-                          (uint32_t)(REC_DOUBLES * 8), &st.full[(U + 1) % NST], st.pol);
+        const int stage = rec_stage<U>(st);
+        uint64_t *bar = reinterpret_cast<uint64_t *>(wave_sm + st.blk + O_FULL) + stage;
+        if (ls + 1 + NST >= 0 && ls + 1 + NST < Sw) {
+            // the stage was read through the generic proxy (ld.shared, ordered before this point by the CTA's
+            // barrier); the bulk copy writes it through the async proxy.  Without this fence the copy of record
+            // ls + 1 + NST has been seen to overtake the last loads of record ls + 1 (a wrong row every ~100 solves
+            // at 8 blocks per plane; visible only where consecutive records differ, i.e. at line ends)
+            tma::fence_reads_before_bulk_write();
+            tma::mbar_expect_tx(bar, (uint32_t)(REC_DOUBLES * 8));
+            tma::bulk_g2s(wave_sm + st.blk + stage * REC_DOUBLES, st.rec_next + (size_t)U * REC_DOUBLES, (uint32_t)(REC_DOUBLES * 8), bar, st.pol);
         }
-        // the record stream comes from HBM with nothing but this warp asking for it: it is pulled into L2 well ahead
-        if (PF > 0 && U % 4 == 0 && ls + 1 + NST + PF < Sw)
-            prefetch_l2_bulk(st.rec_next + (size_t)(U + PF) * REC_DOUBLES, (uint32_t)(4 * REC_DOUBLES * 8));
+        // the record stream comes from HBM with nothing but this block asking for it: it is pulled into L2 well ahead
+        if (PF > 0 && ls + 1 + NST + PF < Sw)
+            prefetch_l2_bulk(st.rec_next + (size_t)(U + PF) * REC_DOUBLES, (uint32_t)(REC_DOUBLES * 8));
     }
 }
 
-// the bases move by one block of RING steps
+// the bases move by one pair of steps
 template <bool UPPER>
-__device__ __forceinline__ void advance_block(State &st) {
-    st.pm += RING * 32;
-    st.w_out += RING * 32;
-    st.wc_out += RING * 32;
-    st.x_out += UPPER ? -RING : RING;
-    st.b_req += UPPER ? -RING : RING;
-    st.d_req += UPPER ? -RING : RING;
-    st.rec_next += (size_t)RING * REC_DOUBLES;
-    st.xp += RING;
+__device__ __forceinline__ void advance_pair(State &st) {
+    st.ls += PH;
+    st.xp += PH;
+    st.pm += PH * 32;
+    st.w_out += PH * 32;
+    st.wc_out += PH * 32;
+    st.x_out += UPPER ? -PH : PH;
+    st.b_req += UPPER ? -PH : PH;
+    st.d_req += UPPER ? -PH : PH;
+    st.rec_next += (size_t)PH * REC_DOUBLES;
 }
 
-// One block of RING global steps of the CTA.  `mode`: 0 this warp has nothing to do in the block (it only keeps
-// the CTA's barriers), 1 general steps, 2 MAIN steps.
 template <bool UPPER>
-__device__ __forceinline__ void block_of_steps(const Args &a, State &st, const int mode, const int l0, const int Sw) {
-#define WAVE_STEP(U)                                                                   \
-    if (mode == 2) step<U, UPPER, true>(a, st, l0, Sw);                                \
-    else if (mode == 1) step<U, UPPER, false>(a, st, l0, Sw);                          \
-    __syncthreads();                                                                   \
-    if (mode == 2) refill<U, true>(a, st, l0, Sw);                                     \
-    else if (mode == 1) refill<U, false>(a, st, l0, Sw);
-    WAVE_STEP(0) WAVE_STEP(1) WAVE_STEP(2) WAVE_STEP(3) WAVE_STEP(4) WAVE_STEP(5) WAVE_STEP(6) WAVE_STEP(7)
-#undef WAVE_STEP
-    if (mode != 0) advance_block<UPPER>(st);
-}
-
-// shared memory of a CTA of W warps: per warp records + b/D rings + barriers, then the two rings
-__host__ __device__ inline size_t smem_per_warp() { return (size_t)NST * REC_DOUBLES * 8 + 2 * (size_t)BD * 32 * 8 + (size_t)RING * 32 * 8 + 64; }
-__host__ __device__ inline int ring_width(int W) { return 32 * W + 32; }
-__host__ __device__ inline size_t smem_bytes(int W) { return (size_t)W * smem_per_warp() + 2 * (size_t)RING * ring_width(W) * 8; }
-
-template <bool UPPER>
-__global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
-    extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
     __shared__ long long s_plane;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wl = warp / PH;                            // 32-line block of the plane
+    const int ph = warp % PH;                            // this warp solves the block's steps with ls % PH == ph
     const Grid g = a.g;
     const int W = g.W;
-    const int Sw = g.S;                                  // local steps of a warp: nx + 62
-    const int rw = ring_width(W);
-    unsigned char *base = smem + (size_t)warp * smem_per_warp();
-    double *ringR0 = reinterpret_cast<double *>(smem + (size_t)W * smem_per_warp());
-    double *ringG0 = ringR0 + RING * rw;
+    const int Sw = g.S;                                  // local steps of a block: nx + 62
     State st;
-    double *recs0 = reinterpret_cast<double *>(base);
-    double *ringB0 = recs0 + (size_t)NST * REC_DOUBLES;
-    double *ringD0 = ringB0 + BD * 32;
-    st.ringS = ringD0 + BD * 32;
-    st.full = reinterpret_cast<uint64_t *>(st.ringS + RING * 32);
-    st.recs = recs0 + lane;
-    st.ringB = ringB0 + lane;
-    st.ringD = ringD0 + lane;
-    st.rw = rw;
-    st.ringR = ringR0 + 32 * warp + lane;                // column y + 1 is at [+1]; column y (the line to the left) at [+0]
-    st.ringG = ringG0 + 32 * warp + lane;
     st.lane = lane;
+    st.blk = wl * BLK_DOUBLES + lane;
+    st.ring = W * BLK_DOUBLES + 32 * wl + lane;          // column y + 1 is at [+1]; column y (the line to the left) at [+0]
     st.pol = tma::policy_evict_first();
     // records start finite: steps before the first record multiply whatever the stage holds
-    for (int i = lane; i < (int)(smem_per_warp() / 8); i += 32) recs0[i] = 0.0;
-    const int y = warp * 32 + lane;
+    for (int i = threadIdx.x; i < W * BLK_DOUBLES; i += blockDim.x) wave_sm[i] = 0.0;
+    const int y = wl * 32 + lane;
+    uint64_t *full = reinterpret_cast<uint64_t *>(wave_sm + wl * BLK_DOUBLES + O_FULL);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_plane = (long long)atomicAdd(a.ticket, 1u);
-        for (int i = threadIdx.x; i < 2 * RING * rw; i += blockDim.x) ringR0[i] = 0.0;   // ringR and ringG are adjacent
+        for (int i = threadIdx.x; i < 2 * RROWS * RWC; i += blockDim.x) wave_sm[W * BLK_DOUBLES + i] = 0.0;   // both rings
+        for (int i = lane + 32 * ph; i < SROWS * 32; i += 32 * PH) wave_sm[wl * BLK_DOUBLES + O_RINGS + i] = 0.0;
+        if (lane == 0 && ph == 0) {
+            for (int i = 0; i < NST; ++i) tma::mbar_init(&full[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         __syncthreads();
         const long long z = s_plane;
         if (z >= g.nz) break;
-        const long long grp = z * W + warp;
+        const long long grp = z * W + wl;
         const long long line_p0 = (z * g.ny + y) * g.nx;
         const bool has_prev = z > 0;
-        const int ls0 = -2 * RING;               // first local step of a warp (request / ring-fill machinery only)
+        const int ls0 = -2 * RING;               // first local step of a block (request / ring-fill machinery only)
         st.nx_eff = y < g.ny ? g.nx : 0;
+        st.ls = ls0;
         st.xp = ls0 - 2 * lane;
-        st.r_prev = 0.0;
         st.pre = 0.0;
         st.v_own = st.v_nb = 0.0;
         st.bb = 0.0;
@@ -508,7 +537,6 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
         st.ieee = false;
 #pragma unroll
         for (int i = 0; i < K - 2; ++i) st.pp[i] = 0.0;
-        for (int i = lane; i < RING * 32; i += 32) st.ringS[i] = 0.0;
         // the own line in the previous plane; requested at local step ls for ring row ls + 5 + GA
         st.pm = a.w + ((has_prev ? grp - W : 0) * Sw + (ls0 + 5 + GA)) * 32;
         st.pm_lo = -(5 + GA);
@@ -524,27 +552,57 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) wave_kernel(Args a) {
             st.d_req = a.D + (UPPER ? row_now - BD : row_now + BD);
         }
         st.rec_next = a.rec + (grp * Sw + (ls0 + 1 + NST)) * REC_DOUBLES;
-        if (lane == 0) {
-            for (int i = 0; i < NST; ++i) tma::mbar_init(&st.full[i], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-        // global steps of the CTA: warp w's local step is s - 64 w (its lane 0 is "lane 32 w" of the plane);
-        // all warps walk the same blocks and keep the same barriers
+        // global steps of the CTA: block w's local step is s - 64 w (its lane 0 is "lane 32 w" of the plane);
+        // all warps walk the same steps and keep the same barriers
         const int s_end = 64 * (W - 1) + Sw;
 #ifdef BIS_PERF_DEBUG
         if (a.stamps && threadIdx.x == 0) a.stamps[2 * z] = bis_globaltimer();
 #endif
-        for (int s0 = ls0; s0 < s_end; s0 += RING) {
-            const int l0 = s0 - 64 * warp;
-            int mode = 0;
-            if (l0 >= ls0 && l0 < Sw) mode = (l0 >= 0 && l0 + RING + NST + 2 <= Sw) ? 2 : 1;
-            block_of_steps<UPPER>(a, st, mode, l0, Sw);
+#pragma unroll 1
+        for (int s = ls0; s < s_end; s += PH) {
+            const int l = s - 64 * wl;
+            const bool live = l >= ls0 && l < Sw;    // warp-uniform; st.ls == l while live
+#ifdef BIS_PERF_DEBUG
+            if (WAVE_DBG(a, 256)) {      // experiment: the two roles of a step one after the other
+                if (live && ph == 0) solve<0, UPPER>(a, st, Sw);
+                __syncthreads();
+                if (live && ph != 0) prepare<0, UPPER>(a, st, Sw);
+                __syncthreads();
+                if (live && ph != 0) refill<0>(a, st, Sw);
+                if (live && ph != 0) solve<1, UPPER>(a, st, Sw);
+                __syncthreads();
+                if (live && ph == 0) prepare<1, UPPER>(a, st, Sw);
+                __syncthreads();
+                if (live) {
+                    if (ph == 0) refill<1>(a, st, Sw);
+                    advance_pair<UPPER>(st);
+                }
+                continue;
+            }
+#endif
+            if (live) {
+                if (ph == 0) solve<0, UPPER>(a, st, Sw);
+                else prepare<0, UPPER>(a, st, Sw);
+            }
+            __syncthreads();
+            if (live) {
+                if (ph == 0) {
+                    prepare<1, UPPER>(a, st, Sw);
+                } else {
+                    refill<0>(a, st, Sw);
+                    solve<1, UPPER>(a, st, Sw);
+                }
+            }
+            __syncthreads();
+            if (live) {
+                if (ph == 0) refill<1>(a, st, Sw);
+                advance_pair<UPPER>(st);
+            }
         }
         cp_async_wait<0>();
-        __syncwarp();
-        if (lane == 0)
-            for (int i = 0; i < NST; ++i) mbar_inval(&st.full[i]);
+        __syncthreads();
+        if (lane == 0 && ph == 0)
+            for (int i = 0; i < NST; ++i) mbar_inval(&full[i]);
 #ifdef BIS_PERF_DEBUG
         if (a.stamps && threadIdx.x == 0) a.stamps[2 * z + 1] = bis_globaltimer();
 #endif

@@ -47,6 +47,11 @@ def check(ctx, name):
             print(f"{name}: variant 5 NOT used (not recognised as a stencil)")
             return False
     ok = all(np.array_equal(a, c) for a, c in zip(out[5], out[3]))
+    if not ok:
+        for what, a, c in zip(("forward", "backward", "in-place", "sgs-apply"), out[5], out[3]):
+            bad = np.nonzero(a != c)[0]
+            if bad.size:
+                print(f"   {what}: {bad.size} entries differ, first at row {bad[0]} last at row {bad[-1]}; first few {bad[:6]}", flush=True)
     worst = max(float(np.max(np.abs(a - c))) for a, c in zip(out[5], out[3]))
     print(f"{name}: n={n} forward/backward/in-place/SGS-apply {'BIT-IDENTICAL' if ok else 'DIFFER'} (max abs diff {worst:.3e})", flush=True)
     ctx.set_option("trsv_variant", 0)
@@ -58,6 +63,12 @@ def check(ctx, name):
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "check"
     with capi.Context(0) as ctx:
+        if mode == "grids":          # python tools/run_trsv5.py grids 64x256x4 64x64x160 ...
+            ok = True
+            for nm in sys.argv[2:]:
+                ok &= check(ctx, nm)
+            print("TRSV5_GRIDS", "PASS" if ok else "FAIL")
+            return 0 if ok else 1
         if mode == "check":
             names = ["8x8x8", "16x16x16", "20x14x11", "12x40x5", "33x70x3", "64x64x1", "7x9x1", "A12x10x8", "A40x36x7", "48x48x48"]
             ok = True
