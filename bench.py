@@ -28,6 +28,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -458,9 +460,25 @@ def main():
         s2 = host.BenchSession(ctx, "HPCG-256", "cg", "j")
         s2.prepare(W)
         r2 = s2.run(K)
+        h2 = s2.history(W + K + 1)
         s2.close()
         same = {"workload": "HPCG-256 -cg -p j", "gpu_ms_per_iter": r2["device_ms"] / K,
                 "gpu_e2e_ms_per_iter": e2["wall_ms"] / K}
+        # the residual norms of those W + K iterations against the UNMODIFIED reference's (committed fixture made by
+        # tests/golden/make_golden_large.py from the compiled reference at 1 and at 8 OpenMP threads)
+        gpath = os.path.join(ROOT, "tests", "golden", "large_hpcg256_cg_j.npz")
+        if os.path.exists(gpath):
+            g = np.load(gpath)
+            k = min(h2.size, g["history"].size, g["history8"].size)
+            r0 = float(g["history"][0])
+            same["parity_vs_reference"] = {
+                "golden": "tests/golden/large_hpcg256_cg_j.npz (reference, 1 OpenMP thread)",
+                "n_residuals": int(k),
+                "max_abs_diff_over_r0": float(np.max(np.abs(h2[:k] - g["history"][:k])) / r0),
+                "reference_1_vs_8_threads_over_r0": float(np.max(np.abs(g["history8"][:k] - g["history"][:k])) / r0),
+                "tolerance": "1e-10 * ||r0|| where the reference reproduces itself to that level (north_star); its own "
+                             "1-thread and 8-thread runs are reported beside the device's distance for scale",
+            }
 
     out = {
         "metric": METRIC, "value": ms_iter, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
