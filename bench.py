@@ -381,8 +381,8 @@ def main():
     if world > 1:
         ctx.dist_wait_read(reset=True)
     clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
+    clocks.start()      # BEFORE the barrier: NVML initialisation takes a rank-dependent 1 - 20 ms, and a rank that enters
+    barrier()           # the timed loop late makes every other rank wait for it inside the first reduction
     t_clk = time.time()
     r = sess.run(K)
     barrier()
