@@ -53,6 +53,7 @@ _SIGS = {
     "bis_graph_launch": ([c_ctx, C.c_void_p], cint),
     "bis_graph_free": ([c_ctx, C.c_void_p], cint),
     "bis_dist_wait_read": ([c_ctx, C.POINTER(dbl), cint], cint),
+    "bis_dist_stream_barrier": ([c_ctx], cint),
     "bis_partition_row_block": ([i64, i64, cint, cint, C.POINTER(i64), C.POINTER(i64)], cint),
     "bis_vector_alloc": ([c_ctx, i64, C.POINTER(c_dev)], cint),
     "bis_vector_free": ([c_ctx, c_dev], cint),

@@ -175,6 +175,7 @@ extern "C" int bis_context_destroy(bis_context *c) {
     cudaFree(c->d_partials);
     cudaFree(c->d_counter);
     cudaFree(c->d_errflag);
+    cudaFree(c->d_barrier_word);
     cudaFree(c->d_flush);
     for (int i = 0; i < BIS_PROF_NTAGS; ++i)
         for (cudaEvent_t e : c->prof[i].ev) cudaEventDestroy(e);

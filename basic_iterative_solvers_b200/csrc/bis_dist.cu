@@ -533,6 +533,21 @@ int bis_halo_fuse_args(bis_context *c, const bis_matrix *A, HaloFuse *hf) {
     return 0;
 }
 
+// Aligns the ranks' streams: everything enqueued after it starts only when every rank's stream has got here
+// (one 4-byte NCCL allreduce; a measurement aid -- a timed region opened right after it does not count the time a
+// late rank took to arrive -- not part of any solver path).
+extern "C" int bis_dist_stream_barrier(bis_context *c) {
+    BIS_REQUIRE(c, "null context");
+    if (c->nranks <= 1) return 0;
+    BIS_CUDA(cudaSetDevice(c->device));
+    if (!c->d_barrier_word) {
+        BIS_CUDA(bis_cuda_malloc(&c->d_barrier_word, sizeof(int)));
+        BIS_CUDA(cudaMemsetAsync(c->d_barrier_word, 0, sizeof(int), c->stream));
+    }
+    BIS_NCCL(ncclAllReduce(c->d_barrier_word, c->d_barrier_word, 1, ncclInt32, ncclSum, c->comm, c->stream));
+    return 0;
+}
+
 // In-kernel wait accounting (ns): out[0] total time the finalising blocks of reductions waited for the
 // other ranks' records, out[1] reductions, out[2] time CTA 0's producer warp of the fused SpMV waited
 // for the senders' halo flags, out[3] exchanges.

@@ -170,6 +170,7 @@ struct bis_context {
     unsigned long long halo_epoch = 0;              // halo exchanges so far (same on all ranks)
     unsigned int *d_pack_ticket = nullptr;
     unsigned long long *d_waitstat = nullptr;       // in-kernel wait accounting (bis_dist_wait_read)
+    int *d_barrier_word = nullptr;                  // operand of bis_dist_stream_barrier (always 0)
     std::vector<void *> ipc_opened;                 // mappings to close
     RowPartition part;                              // bis_partition_set (bis_context.cu)
     // CUDA graphs (bis_graph_*): `capturing` while the stream records; graph_epoch counts captures and

@@ -376,6 +376,7 @@ int bis_host_bench_run(void *h, int steps, double *out) {
         if (solver->iter_count + steps + 1 >= MAX_ITERS) bis_fatal("bench: warmup + steps exceed MAX_ITERS");
         int64_t i0[8], i1[8];
         BIS_OK(bis_context_info(s->dev, i0));
+        BIS_OK(bis_dist_stream_barrier(s->dev));   // all ranks' streams start the timed region together
         Stopwatch w;
         w.start();
         BIS_OK(bis_timer_start(s->dev));

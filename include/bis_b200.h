@@ -129,6 +129,9 @@ int bis_graph_free(bis_context *ctx, bis_graph *graph);
  * reductions waited for the other ranks' records, out[1] reductions counted, out[2] time the fused
  * SpMV's first producer warp waited for the senders' halo flags, out[3] exchanges counted. */
 int bis_dist_wait_read(bis_context *ctx, double out[4] /* [host] */, int reset);
+/* Measurement aid: everything enqueued on the context's stream after this call starts only when every rank's
+ * stream has reached it (no-op on a single-GPU context).  Used to open a timed region on all ranks together. */
+int bis_dist_stream_barrier(bis_context *ctx);
 int bis_partition_row_block(int64_t n_global, int64_t plane, int rank, int nranks,
                             int64_t *begin /* [host] */, int64_t *end /* [host] */);
 
