@@ -412,6 +412,7 @@ extern "C" int bis_context_get_option(bis_context *c, const char *key, int *valu
     if (k == "graph") *value = (c->opt_graph && c->nranks == 1) ? 1 : 0;
     else if (k == "precond_inner_iters") *value = c->opt_precond_inner_iters;
     else if (k == "perm_mode") *value = c->opt_perm_mode;
+    else if (k == "factor_keep_crs") *value = c->opt_factor_keep_crs;
     else if (k == "spmv_variant") *value = c->opt_spmv_variant;
     else if (k == "trsv_variant") *value = c->opt_trsv_variant;
     else if (k == "spmv_fused") *value = c->opt_spmv_fused;
@@ -468,6 +469,7 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "trsv_poll_ns") c->opt_trsv_poll_ns = value;
     else if (k == "spmv_rows") c->opt_spmv_rows = value;
     else if (k == "spmv_stages") c->opt_spmv_stages = value;
+    else if (k == "factor_keep_crs") c->opt_factor_keep_crs = value ? 1 : 0;
     else if (k == "spmv_smem_kb") c->opt_spmv_smem_kb = value;
     else if (k == "spmv_l2_mb") c->opt_spmv_l2_mb = value;
     else if (k == "spmv_blocked") c->opt_spmv_blocked = value;

@@ -190,6 +190,7 @@ struct bis_context {
     int opt_vector_cache = 1;
     int opt_spmv_fused = 1;     // distributed SpMV over peer memory as ONE kernel (0: pack / interior / wait / strips launches)
     int opt_dist_p2p = 1;       // 0: NCCL transport even when the peer-memory link is up
+    int opt_factor_keep_crs = 1;       // 0: a triangular factor gives up its natural-order CRS once its level-ordered copy exists
     int opt_perm_mode = 0;             // the reference's PERM_MODE: 0 NONE, 1 C (multicolouring), read by the host's preprocessing
     int opt_precond_inner_iters = 0;   // PRECOND_INNER_ITERS of the reference (kernels.hpp:321): inner sweeps of -p 2st / s2st
     int opt_graph = 1;          // the host stack records iteration bodies as CUDA graphs (bis_context_get_option)
@@ -262,6 +263,9 @@ struct LevelSets {
     int *d_col = nullptr;
     double *d_val = nullptr;
 };
+
+// entry points that read a matrix's natural-order CRS arrays
+#define BIS_REQUIRE_CRS(A) BIS_REQUIRE(!(A)->crs_released, "this factor gave up its natural-order CRS arrays (option factor_keep_crs = 0): only triangular solves can use it")
 
 struct HaloPlan {
     int64_t n_ghost = 0;                 // ghost elements appended after owned
@@ -339,6 +343,7 @@ struct bis_matrix {
     HaloPlan halo;
     mutable WinFormat win;
     bool distributed = false;
+    bool crs_released = false; // triangular factor whose natural-order d_rp / d_col / d_val were freed (option factor_keep_crs = 0)
 };
 
 // ---- internal entry points shared between translation units ---------------

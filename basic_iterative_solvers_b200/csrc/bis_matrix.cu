@@ -184,6 +184,7 @@ template <typename RP> __global__ void max_row_kernel(int64_t n, const RP *rp, i
 
 // max_row / mean_row of a device CRS (what the SpMV planners look at)
 int bis_matrix_stats(bis_context *c, bis_matrix *A) {
+    BIS_REQUIRE_CRS(A);
     int *d_m = nullptr;
     BIS_CHECK(dev_alloc(&d_m, 1));
     BIS_CUDA(cudaMemsetAsync(d_m, 0, sizeof(int), c->stream));
@@ -567,6 +568,7 @@ template <typename RP> __global__ void rp_to_i64_kernel(int64_t n1, const RP *rp
 extern "C" int bis_matrix_download_crs(bis_context *c, const bis_matrix *A, int64_t *rp, int32_t *col,
                                        double *val) {
     BIS_REQUIRE(c && A && rp, "null argument");
+    BIS_REQUIRE_CRS(A);
     BIS_CUDA(cudaSetDevice(c->device));
     int64_t *d_rp64 = nullptr;
     BIS_CHECK(dev_alloc(&d_rp64, (size_t)A->n_rows + 1));
@@ -617,6 +619,7 @@ __global__ void extract_diag_kernel(int64_t n, const RP *rp, const int *col, con
 
 extern "C" int bis_matrix_extract_diagonal(bis_context *c, const bis_matrix *A, double *D, double *D_inv) {
     BIS_REQUIRE(c && A && D, "null argument");
+    BIS_REQUIRE_CRS(A);
     BIS_CUDA(cudaSetDevice(c->device));
     int *d_missing = nullptr;
     BIS_CHECK(dev_alloc(&d_missing, 2));
@@ -668,6 +671,7 @@ __global__ void scale_apply_kernel(int64_t n, const RP *rp, const int *col, doub
 
 extern "C" int bis_matrix_scale_symmetric(bis_context *c, bis_matrix *A, double *D_scale) {
     BIS_REQUIRE(c && A && D_scale, "null argument");
+    BIS_REQUIRE_CRS(A);
     BIS_REQUIRE(A->triangular == 0, "bis_matrix_scale_symmetric: general matrices only");
     BIS_CUDA(cudaSetDevice(c->device));
     const int64_t n = A->n_rows;

@@ -110,6 +110,7 @@ template <typename T> int dalloc(T **p, size_t count) {
 // generate_perm (smax_helpers.hpp:51-53) for PERM_MODE = C: perm[new] = old, inv_perm[old] = new, both [dev] int32[n]
 extern "C" int bis_matrix_colouring_permutation(bis_context *c, const bis_matrix *A, int *d_perm, int *d_inv_perm, int *n_colours) {
     BIS_REQUIRE(c && A && d_perm && d_inv_perm, "bis_matrix_colouring_permutation: null argument");
+    BIS_REQUIRE_CRS(A);
     BIS_REQUIRE(!A->distributed && c->nranks == 1, "bis_matrix_colouring_permutation: single-GPU only");
     BIS_CUDA(cudaSetDevice(c->device));
     const int64_t n = A->n_rows;
@@ -185,6 +186,7 @@ extern "C" int bis_matrix_colouring_permutation(bis_context *c, const bis_matrix
 extern "C" int bis_matrix_permute_symmetric(bis_context *c, const bis_matrix *A, const int *d_perm, const int *d_inv_perm,
                                             bis_matrix **out) {
     BIS_REQUIRE(c && A && d_perm && d_inv_perm && out, "bis_matrix_permute_symmetric: null argument");
+    BIS_REQUIRE_CRS(A);
     BIS_REQUIRE(!A->distributed && c->nranks == 1 && A->triangular == 0 && A->n_rows == A->n_cols,
                 "bis_matrix_permute_symmetric: square general single-GPU matrices only");
     BIS_CUDA(cudaSetDevice(c->device));

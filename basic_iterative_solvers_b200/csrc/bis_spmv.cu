@@ -588,6 +588,7 @@ template <class Epi>
 static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, const Epi &epi,
                        int slot_a, int slot_b) {
     BIS_REQUIRE(c && A && x, "spmv: null argument");
+    BIS_REQUIRE_CRS(A);
     BisNvtxRange nvtx_range("spmv");
     BIS_CUDA(cudaSetDevice(c->device));
     RedArgs ra = bis_red_args(c, slot_a, slot_b);

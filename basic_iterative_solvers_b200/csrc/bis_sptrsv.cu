@@ -649,6 +649,10 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
 
 int bis_wave_build(bis_context *c, const bis_matrix *T) {
     if (T->lv.wave.state != 0) return 0;
+    if (T->crs_released) {      // nothing to build the records from any more
+        T->lv.wave.state = -1;
+        return 0;
+    }
     BIS_CUDA(cudaSetDevice(c->device));
     if (T->rp_bytes == 8) return wave_build_t<int64_t>(c, T);
     return wave_build_t<int32_t>(c, T);
@@ -702,7 +706,7 @@ static int trsv_solve(bis_context *c, const bis_matrix *T, double *x, const doub
     a.b = b;
     a.post_mul_d = post_mul_d;
     a.w_clean = nullptr;
-    if (c->opt_trsv_variant == 4 && T->lv.chain.state == 0) {
+    if (c->opt_trsv_variant == 4 && T->lv.chain.state == 0 && !T->crs_released) {
         if (T->rp_bytes == 8) BIS_CHECK(chain_build_t<int64_t>(c, T));
         else BIS_CHECK(chain_build_t<int32_t>(c, T));
     }

@@ -79,11 +79,24 @@ inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
         // factor_LU (LU_factors.hpp:900-934) on the device-resident matrix: strict split, or ILU(0)
         // (factor_ILU0_old) when it is the preconditioner; level analysis included.  L_D = U_D = 1 unless ILU(0).
         bis_matrix *l = nullptr, *u = nullptr;
+        // A Krylov method that uses the factors only inside gs / bgs / sgs / ilu0 preconditioner solves never multiplies
+        // by them: they may give up their natural-order CRS once the level-ordered copy exists (HPCG-512 -p sgs then
+        // fits one GPU).  Gauss-Seidel SWEEPS (b - T x) and the two-stage preconditioners keep it.
+        const bool krylov = solver->method == SolverType::ConjugateGradient || solver->method == SolverType::GMRES ||
+                            solver->method == SolverType::BiCGSTAB;
+        const bool solves_only = solver->preconditioner == PrecondType::GaussSeidel ||
+                                 solver->preconditioner == PrecondType::BackwardsGaussSeidel ||
+                                 solver->preconditioner == PrecondType::SymmetricGaussSeidel ||
+                                 solver->preconditioner == PrecondType::ILU0;
+        int keep_before = 1;
+        BIS_OK(bis_context_get_option(dev, "factor_keep_crs", &keep_before));
+        if (krylov && solves_only) BIS_OK(bis_context_set_option(dev, "factor_keep_crs", 0));
         if (solver->preconditioner == PrecondType::ILU0)
             BIS_OK(bis_matrix_ilu0(dev, solver->dA->handle, ILU0_PIVOT_TOLERANCE, ILU0_PIVOT_REPLACEMENT, &l, &u,
                                    solver->L_D, solver->U_D));
         else
             BIS_OK(bis_matrix_split_triangular(dev, solver->dA->handle, &l, &u));
+        BIS_OK(bis_context_set_option(dev, "factor_keep_crs", keep_before));
         solver->dL_strict = adopt_device_matrix(dev, l);
         solver->dU_strict = adopt_device_matrix(dev, u);
     }

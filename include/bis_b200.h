@@ -102,6 +102,11 @@ int bis_flush_l2(bis_context *ctx);
  * 2..32), "trsv_variant" (0 auto, 1 launch per level, 2 level counters,
  * 3 dataflow, 4 chains, 5 stencil wavefront), "graph" (0/1: the host stack
  * replays the iteration body as a CUDA graph; default 1 on one GPU),
+ * "factor_keep_crs" (default 1; 0: bis_matrix_split_triangular / bis_matrix_ilu0
+ * return factors that keep only their level-ordered copy -- bis_sptrsv /
+ * bis_bsptrsv / bis_apply_preconditioner(gs, bgs, sgs, ilu0) work, every entry
+ * point that reads the factor's CRS arrays fails loudly; the C++ host asks for
+ * it when a Krylov method uses the factors in such a preconditioner only),
  * "spmv_fused", "dist_p2p", "vector_cache", ... (bis_context.cu). */
 int bis_context_set_option(bis_context *ctx, const char *key, int value);
 int bis_context_get_option(bis_context *ctx, const char *key, int *value /* [host] */);

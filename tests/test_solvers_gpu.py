@@ -14,7 +14,7 @@ import pytest
 from conftest import HIST_TOL, check_against_fixture, golden
 from oracle import matgen, port
 
-from basic_iterative_solvers_b200 import host
+from basic_iterative_solvers_b200 import capi, host
 
 pytestmark = pytest.mark.gpu
 
@@ -203,3 +203,36 @@ def test_two_gpu_partition_matches_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", "tools/dist_check.py", "40"],
                          cwd=root, capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_factors_without_natural_crs_give_the_same_history(ctx):
+    """factor_keep_crs = 0 (what the C++ host selects for a Krylov method with a gs / sgs / ilu0 preconditioner):
+    the factors keep only their level-ordered copy; histories are bit-identical, and an entry point that needs the
+    factor's CRS arrays fails loudly instead of reading freed memory."""
+    for method, pre in (("cg", "sgs"), ("gm", "ilu0"), ("bi", "gs")):
+        a = host.solve(ctx, method, pre, matrix_name="HPCG-24", want_x=False, max_iters=60)
+        assert a.iter_count > 0
+    # the host turns the option on by itself; compare against an explicit split with the arrays kept
+    A = ctx.generate_hpcg(24)
+    n = A.info()["n_rows"]
+    D = ctx.alloc(n)
+    ctx.call("bis_matrix_extract_diagonal", A.h, D, None)
+    bh = np.random.default_rng(11).uniform(-1.0, 1.0, n)
+    out = {}
+    for keep in (1, 0):
+        ctx.set_option("factor_keep_crs", keep)
+        try:
+            L, U = ctx.split_triangular(A)
+        finally:
+            ctx.set_option("factor_keep_crs", 1)
+        b, x, y = ctx.upload(bh), ctx.alloc(n), ctx.alloc(n)
+        ctx.call("bis_sptrsv", L.h, x, D, b)
+        ctx.call("bis_bsptrsv", U.h, y, D, b)
+        ctx.sync()
+        out[keep] = (ctx.download(x, n), ctx.download(y, n))
+        if keep == 0:
+            with pytest.raises(capi.BisError):
+                ctx.call("bis_spmv", L.h, b, x)
+        for m in (L, U):
+            m.free()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
