@@ -83,6 +83,7 @@ static int context_init(bis_context *c, int device) {
     if (const char *e = getenv("BIS_SPMV_FUSED")) c->opt_spmv_fused = atoi(e);
     if (const char *e = getenv("BIS_TRSV_VARIANT")) c->opt_trsv_variant = atoi(e);
     if (const char *e = getenv("BIS_GRAPH")) c->opt_graph = atoi(e);
+    if (const char *e = getenv("BIS_WIN_ROWS")) c->opt_win_rows = atoi(e);
     if (const char *e = getenv("BIS_PRECOND_INNER_ITERS")) c->opt_precond_inner_iters = atoi(e);
     if (const char *e = getenv("BIS_PERM_MODE")) c->opt_perm_mode = (e[0] == 'C' || e[0] == 'c' || e[0] == '1') ? 1 : 0;
     return 0;

@@ -439,7 +439,7 @@ int win_build(bis_context *c, const bis_matrix *A) {
     w.state = -1;
     if (A->n_rows == 0 || A->nnz == 0 || A->max_row < 1) return 0;
     int R = c->opt_win_rows;
-    if (R != 32 && R != 64 && R != 128) {
+    if (R != 32 && R != 64 && R != 128 && R != 256) {
         R = 128;
         while (R > 32 && (size_t)R * A->max_row * 10 > (size_t)40 << 10) R >>= 1;   // ~<= 40 KB of val+lidx per stage
     }

@@ -223,7 +223,7 @@ struct SpmvWinIn {
 #endif
 
 // stage layout: [val cap*8][xwin xcap*8][rp (R+4)*8][lidx cap*2], every part 16-byte aligned
-constexpr int WIN_MAX_THREADS = 320;   // consumer groups (R x nstage) + the producer warp
+constexpr int WIN_MAX_THREADS = 544;   // consumer groups (R x nstage <= 512) + the producer warp
 
 // This CTA's sequence of tiles: the s-th one is position pos0[i] + b + (s - cum[i]) * G of slab i.
 struct WinSeq {
@@ -254,7 +254,7 @@ struct WinSeq {
 };
 
 template <typename RP, class Epi, bool DIST = false>
-__global__ void __launch_bounds__(WIN_MAX_THREADS, 2)
+__global__ void __launch_bounds__(WIN_MAX_THREADS, 1)
 spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIST, HaloFuse, NoHaloFuse>::type hf) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);            // [MAX_STAGES]
