@@ -28,6 +28,9 @@
 constexpr int WIN_MAXSEG = 28;       // x windows per tile (one producer lane each)
 constexpr int WIN_GAP = 8;           // columns closer than this share a window
 constexpr int WIN_BUILD_THREADS = 256;
+constexpr int WIN_FAST_HASH = 128;   // hash slots of the fast path (distinct col - row offsets of a tile)
+constexpr int WIN_FAST_OFFS = 64;    // ... and how many distinct offsets it accepts
+constexpr int WIN_FAST_EMPTY = (int)0x80000000;
 
 // ---- build: one CTA per tile ---------------------------------------------------------------
 struct WinBuildArgs {
@@ -59,6 +62,97 @@ __global__ void __launch_bounds__(WIN_BUILD_THREADS) win_build_kernel(WinBuildAr
     if (r1 > a.n_rows) r1 = a.n_rows;
     const int64_t s = (int64_t)rp[r0], e = (int64_t)rp[r1];
     const int m = (int)(e - s);
+    const int no = (int)a.n_owned;
+    // ---- fast path (banded / stencil tiles without ghost columns): the windows follow from the DISTINCT OFFSETS
+    // col - row of the tile.  Offset d contributes the columns [r0 + d, r1 - 1 + d]; offsets closer than the tile is
+    // long share a window.  The windows may be supersets of the exact ones (rows at a domain boundary lack some
+    // neighbours): harmless, every column a row reads is covered.  More than WIN_FAST_OFFS distinct offsets, a ghost
+    // column, or a full hash table: the sort below decides.
+    __shared__ int s_hash[WIN_FAST_HASH];
+    __shared__ int s_list[WIN_FAST_HASH];
+    __shared__ int s_sorted[WIN_FAST_OFFS];
+    __shared__ int s_nlist, s_fail, s_fast_runs;
+    for (int i = threadIdx.x; i < WIN_FAST_HASH; i += blockDim.x) s_hash[i] = WIN_FAST_EMPTY;
+    if (threadIdx.x == 0) {
+        s_nlist = 0;
+        s_fail = 0;
+        s_fast_runs = -1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int c = a.col[s + i];
+        if (c >= no) {
+            s_fail = 1;
+            continue;
+        }
+        // the row of nonzero s + i: last row whose rp <= s + i
+        int lo = 0, hi = (int)(r1 - r0) - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int64_t)rp[r0 + mid] <= s + i) lo = mid;
+            else hi = mid - 1;
+        }
+        const int d = c - (int)(r0 + lo);
+        unsigned int h = ((unsigned int)d * 2654435761u) >> 25;      // 7 bits
+        int probes = 0;
+        for (;; h = (h + 1) & (WIN_FAST_HASH - 1)) {
+            const int v = *reinterpret_cast<volatile int *>(&s_hash[h]);
+            if (v == d) break;
+            if (v == WIN_FAST_EMPTY) {
+                const int old = atomicCAS(&s_hash[h], WIN_FAST_EMPTY, d);
+                if (old == WIN_FAST_EMPTY || old == d) break;
+            }
+            if (++probes >= WIN_FAST_HASH) {
+                s_fail = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (!s_fail) {
+        for (int i = threadIdx.x; i < WIN_FAST_HASH; i += blockDim.x)
+            if (s_hash[i] != WIN_FAST_EMPTY) s_list[atomicAdd(&s_nlist, 1)] = s_hash[i];
+    }
+    __syncthreads();
+    const int n_offs = s_nlist;
+    const bool fast = !s_fail && n_offs >= 1 && n_offs <= WIN_FAST_OFFS;
+    if (fast) {
+        // rank sort of the distinct offsets
+        for (int i = threadIdx.x; i < n_offs; i += blockDim.x) {
+            const int v = s_list[i];
+            int rank = 0;
+            for (int j = 0; j < n_offs; ++j) rank += s_list[j] < v ? 1 : 0;
+            s_sorted[rank] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int span = (int)(r1 - r0) - 1 + WIN_GAP;
+            int nrun = 0;
+            bool too_many_runs = false;
+            int dmin = s_sorted[0], dmax = s_sorted[0];
+            for (int i = 1; i <= n_offs; ++i) {
+                if (i < n_offs && s_sorted[i] - dmax <= span) {
+                    dmax = s_sorted[i];
+                    continue;
+                }
+                if (nrun >= WIN_MAXSEG) {
+                    too_many_runs = true;
+                    break;
+                }
+                long long first = (long long)r0 + dmin, last = (long long)r1 - 1 + dmax;
+                if (first < 0) first = 0;
+                if (last > no - 1) last = no - 1;
+                s_start[nrun] = (int)first;
+                s_end[nrun] = (int)last;
+                ++nrun;
+                if (i < n_offs) dmin = dmax = s_sorted[i];
+            }
+            s_fast_runs = too_many_runs ? -1 : nrun;
+        }
+    }
+    __syncthreads();
+    const bool use_fast = s_fast_runs >= 0;
+    if (!use_fast) {
     for (int i = threadIdx.x; i < a.sort_cap; i += blockDim.x) s_keys[i] = i < m ? a.col[s + i] : 0x7fffffff;
     __syncthreads();
     // bitonic sort, ascending
@@ -83,7 +177,6 @@ __global__ void __launch_bounds__(WIN_BUILD_THREADS) win_build_kernel(WinBuildAr
     // the runs, the first / last key of each run is written by the thread that sees it.
     __shared__ int s_warp[WIN_BUILD_THREADS / 32];
     __shared__ int s_total;
-    const int no = (int)a.n_owned;
     const int per = (a.sort_cap + WIN_BUILD_THREADS - 1) / WIN_BUILD_THREADS;
     const int i0 = threadIdx.x * per, i1 = min(i0 + per, m);
     auto is_start = [&](int i) {
@@ -123,11 +216,14 @@ __global__ void __launch_bounds__(WIN_BUILD_THREADS) win_build_kernel(WinBuildAr
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) s_fast_runs = too_many ? -2 : n_runs;
+    }   // sort path
+    __syncthreads();
     // each window is widened to even bounds relative to its base pointer (16-byte bulk copies)
     if (threadIdx.x == 0) {
         int off = 0;
-        bool bad = too_many;
-        const int n = bad ? 0 : n_runs;
+        bool bad = s_fast_runs < 0;
+        const int n = bad ? 0 : s_fast_runs;
         for (int q = 0; q < n; ++q) {
             const int first = s_start[q], last = s_end[q];
             const int base = first >= no ? no : 0;
