@@ -104,6 +104,7 @@ _SIGS = {
     "bis_spmv_dot": ([c_ctx, c_mat, c_dev, c_dev, c_dev, cint, cint], cint),
     "bis_spmv_residual": ([c_ctx, c_mat, c_dev, c_dev, c_dev, c_dev, cint], cint),
     "bis_spmv_jacobi": ([c_ctx, c_mat, c_dev, c_dev, c_dev, c_dev], cint),
+    "bis_spmv_jacobi_residual": ([c_ctx, c_mat, c_dev, c_dev, c_dev, c_dev, c_dev, cint], cint),
     "bis_spmv_sub": ([c_ctx, c_mat, c_dev, c_dev, c_dev], cint),
     "bis_spmv_two_stage": ([c_ctx, c_mat, c_dev, c_dev, c_dev, c_dev], cint),
     "bis_cg_update": ([c_ctx, cint, i64] + [c_dev] * 8 + [cint] * 4, cint),

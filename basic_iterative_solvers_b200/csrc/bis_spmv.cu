@@ -90,6 +90,24 @@ struct EpiJacobi {
         x_new[r] = div_rn(sub_rn(p.c, adj), p.a);
     }
 };
+// Jacobi sweep AND the residual norm of the iterate it starts from, from ONE product A x_old (the reference's loop
+// computes A x twice per iteration: jacobi.hpp:27-52 for the sweep, :102-107 for the residual of the same vector one
+// harness pass earlier).  Both results are the bits of EpiJacobi / EpiResid.
+struct EpiJacobiResid {
+    static constexpr int NRED = 1;
+    const double *D, *b, *x_old;
+    double *x_new;
+    double *res;       // may be null
+    __device__ __forceinline__ EpiPre load(int64_t r) const { return EpiPre{D[r], x_old[r], b[r]}; }
+    __device__ __forceinline__ void operator()(int64_t r, double s, const EpiPre &p, double *acc) const {
+        const double scaled = mul_rn(p.a, p.b);
+        const double adj = sub_rn(s, scaled);
+        x_new[r] = div_rn(sub_rn(p.c, adj), p.a);
+        const double v = sub_rn(p.c, s);
+        if (res) res[r] = v;
+        acc[0] = fma(v, v, acc[0]);
+    }
+};
 struct EpiSub {
     static constexpr int NRED = 0;
     const double *b;
@@ -693,6 +711,15 @@ extern "C" int bis_spmv_jacobi(bis_context *c, const bis_matrix *A, const double
     BIS_REQUIRE(D && b && x_new, "bis_spmv_jacobi: null argument");
     EpiJacobi e{D, b, x_old, x_new};
     return spmv_driver(c, A, x_old, e, -1, -1);
+}
+
+extern "C" int bis_spmv_jacobi_residual(bis_context *c, const bis_matrix *A, const double *D, const double *b,
+                                        const double *x_old, double *x_new, double *res, int slot_rr) {
+    BIS_REQUIRE(D && b && x_new, "bis_spmv_jacobi_residual: null argument");
+    BIS_REQUIRE(slot_rr >= 0 && slot_rr < BIS_NUM_SCALARS, "bis_spmv_jacobi_residual: bad scalar slot %d", slot_rr);
+    BIS_REQUIRE(x_new != x_old, "bis_spmv_jacobi_residual: the sweep is not an in-place operation");
+    EpiJacobiResid e{D, b, x_old, x_new, res};
+    return spmv_driver(c, A, x_old, e, slot_rr, -1);
 }
 
 extern "C" int bis_spmv_sub(bis_context *c, const bis_matrix *T, const double *x, const double *b,

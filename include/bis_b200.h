@@ -338,6 +338,11 @@ int bis_spmv_residual(bis_context *ctx, const bis_matrix *A, const double *x,
 /* Jacobi sweep: x_new = (b - (A x_old - D x_old)) / D, jacobi.hpp:27-52. */
 int bis_spmv_jacobi(bis_context *ctx, const bis_matrix *A, const double *D,
                     const double *b, const double *x_old, double *x_new);
+/* The same sweep fused with the residual of the iterate it starts from: r = b - A x_old (stored if r != NULL),
+ * slot_rr <- (r,r), x_new as above -- one product A x_old serves jacobi.hpp:27-52 and the residual sampling of
+ * jacobi.hpp:102-107 that the reference's harness does with a second SpMV. */
+int bis_spmv_jacobi_residual(bis_context *ctx, const bis_matrix *A, const double *D, const double *b,
+                             const double *x_old, double *x_new, double *r, int slot_rr);
 /* out = b - T x for a strictly triangular T: gauss_seidel.hpp:30-34, 44-48. */
 int bis_spmv_sub(bis_context *ctx, const bis_matrix *T, const double *x,
                  const double *b, double *out);

@@ -222,6 +222,15 @@ def test_spmv_and_fused_forms_vs_reference_fixture(ctx, name):
     ctx.call("bis_normalize_x", dxn, dx, dD, dv, n)
     assert np.array_equal(fused, ctx.download(dxn, n))
     assert np.array_equal(fused, g["k__normalize_x"])
+    # sweep + residual of the starting iterate from ONE product (what JacobiSolver::iterate enqueues): the sweep's
+    # bits, the residual vector's bits, and the squared norm of the separate residual kernel bit for bit
+    ctx.call("bis_spmv_residual", A.h, dx, dv, dr, None, 22)
+    rr_sep = ctx.scalars(22)[0]
+    dxn2, dr2 = ctx.alloc(n), ctx.alloc(n)
+    ctx.call("bis_spmv_jacobi_residual", A.h, dD, dv, dx, dxn2, dr2, 23)
+    assert np.array_equal(ctx.download(dxn2, n), fused)
+    assert np.array_equal(ctx.download(dr2, n), r_ref)
+    assert ctx.scalars(23)[0] == rr_sep
     # b - T x on a strictly triangular factor (gauss_seidel.hpp:30-34)
     U = ctx.upload_triangular(f.u_rp, f.u_col, f.u_val, upper=True)
     ctx.call("bis_spmv_sub", U.h, dx, dv, dr)
