@@ -526,8 +526,10 @@ bool win_plan(const bis_context *c, const bis_matrix *A, WinPlan *p) {
         if (128 + 2 * stage > ((size_t)220 << 10)) return false;
         nstage = 2;
     }
-    while (nstage > 2 && w.R * nstage + 32 > WIN_MAX_THREADS) --nstage;      // kernel's launch bound
-    if (w.R * nstage + 32 > WIN_MAX_THREADS) return false;
+    // CTA size: at most 320 threads (two or more CTAs per SM) unless the tile itself is 256 rows long
+    const int max_threads = w.R > 128 ? WIN_MAX_THREADS : 320;
+    while (nstage > 2 && w.R * nstage + 32 > max_threads) --nstage;
+    if (w.R * nstage + 32 > max_threads) return false;
     p->nstage = nstage;
     p->stage_bytes = (int)stage;
     p->smem_bytes = 128 + stage * nstage;
