@@ -475,6 +475,7 @@ def main():
                 "golden": "tests/golden/large_hpcg256_cg_j.npz (reference, 1 OpenMP thread)",
                 "n_residuals": int(k),
                 "max_abs_diff_over_r0": float(np.max(np.abs(h2[:k] - g["history"][:k])) / r0),
+                "max_abs_diff_vs_8_thread_run_over_r0": float(np.max(np.abs(h2[:k] - g["history8"][:k])) / r0),
                 "reference_1_vs_8_threads_over_r0": float(np.max(np.abs(g["history8"][:k] - g["history"][:k])) / r0),
                 "tolerance": "1e-10 * ||r0|| where the reference reproduces itself to that level (north_star); its own "
                              "1-thread and 8-thread runs are reported beside the device's distance for scale",
