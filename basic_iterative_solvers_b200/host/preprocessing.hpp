@@ -90,13 +90,17 @@ inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
                                  solver->preconditioner == PrecondType::ILU0;
         int keep_before = 1;
         BIS_OK(bis_context_get_option(dev, "factor_keep_crs", &keep_before));
+        struct RestoreOption {      // also when factoring throws: the context outlives a failed solve (Python host API)
+            Interface *dev;
+            int value;
+            ~RestoreOption() { bis_context_set_option(dev, "factor_keep_crs", value); }
+        } restore_keep{dev, keep_before};
         if (krylov && solves_only) BIS_OK(bis_context_set_option(dev, "factor_keep_crs", 0));
         if (solver->preconditioner == PrecondType::ILU0)
             BIS_OK(bis_matrix_ilu0(dev, solver->dA->handle, ILU0_PIVOT_TOLERANCE, ILU0_PIVOT_REPLACEMENT, &l, &u,
                                    solver->L_D, solver->U_D));
         else
             BIS_OK(bis_matrix_split_triangular(dev, solver->dA->handle, &l, &u));
-        BIS_OK(bis_context_set_option(dev, "factor_keep_crs", keep_before));
         solver->dL_strict = adopt_device_matrix(dev, l);
         solver->dU_strict = adopt_device_matrix(dev, u);
     }
