@@ -588,7 +588,7 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     a.dbg = c->opt_wave_debug;
     a.stamps = nullptr;
     const char *stamp_file = (c->opt_wave_debug & 64) ? getenv("BIS_WAVE_STAMPS") : nullptr;
-    if (stamp_file) BIS_CUDA(bis_cuda_malloc(&a.stamps, sizeof(unsigned long long) * 2 * (size_t)wf.nz));
+    if (stamp_file) BIS_CUDA(bis_cuda_malloc(&a.stamps, sizeof(unsigned long long) * (2 * (size_t)wf.nz + 64)));
 #endif
     if (wf.w_epoch != c->graph_epoch || c->capturing) {   // a graph replay may have used either vector since
         wf.w_clean[0] = wf.w_clean[1] = 0;
@@ -632,7 +632,7 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     BIS_LAUNCH_CHECK(c);
 #ifdef BIS_PERF_DEBUG
     if (a.stamps) {
-        std::vector<unsigned long long> h(2 * (size_t)wf.nz);
+        std::vector<unsigned long long> h(2 * (size_t)wf.nz + 64);
         BIS_CUDA(cudaMemcpyAsync(h.data(), a.stamps, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
         BIS_CUDA(cudaStreamSynchronize(c->stream));
         if (FILE *f = fopen(stamp_file, "wb")) {

@@ -289,6 +289,9 @@ struct State {
     const double *b_req, *d_req;   // b / D of the row this lane has BD steps later (+- U)
     uint64_t pol;
     const double *rec_next;    // record of local step ls + 1 + NST at U = 0 (+ U records)
+#ifdef BIS_PERF_DEBUG
+    long long polls;
+#endif
 };
 
 // A CTA owns a whole plane: its 32-line blocks, PH = 2 warps each, block w running 64 steps behind block w-1.
@@ -392,6 +395,9 @@ __device__ __forceinline__ void prepare(const Args &a, State &st, const int Sw) 
     const int o_stage = st.blk + O_RINGS + U * 32;              // + slot * 32
     unsigned long long vm = reinterpret_cast<const unsigned long long *>(wave_sm)[o_stage + ((st.ls & 2) ^ 2) * 32];   // slot (ls - GA) % SROWS
     if (__any_sync(0xffffffffu, vm == SENT)) {
+#ifdef BIS_PERF_DEBUG
+        st.polls += 1;
+#endif
         const double *pm = st.pm + (U - GA) * 32 + st.lane;   // where it was requested from
         unsigned int spins = 0;
         unsigned long long t_wd = 0;
@@ -558,6 +564,10 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
 #ifdef BIS_PERF_DEBUG
         if (a.stamps && threadIdx.x == 0) a.stamps[2 * z] = bis_globaltimer();
 #endif
+#ifdef BIS_PERF_DEBUG
+        long long dbg_acc[5] = {0, 0, 0, 0, 0};
+        st.polls = 0;
+#endif
 #pragma unroll 1
         for (int s = ls0; s < s_end; s += PH) {
             const int l = s - 64 * wl;
@@ -580,11 +590,20 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
                 continue;
             }
 #endif
+#ifdef BIS_PERF_DEBUG
+            const long long tc0 = clock64();
+#endif
             if (live) {
                 if (ph == 0) solve<0, UPPER>(a, st, Sw);
                 else prepare<0, UPPER>(a, st, Sw);
             }
+#ifdef BIS_PERF_DEBUG
+            const long long tc1 = clock64();
+#endif
             __syncthreads();
+#ifdef BIS_PERF_DEBUG
+            const long long tc2 = clock64();
+#endif
             if (live) {
                 if (ph == 0) {
                     prepare<1, UPPER>(a, st, Sw);
@@ -593,7 +612,21 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
                     solve<1, UPPER>(a, st, Sw);
                 }
             }
+#ifdef BIS_PERF_DEBUG
+            const long long tc3 = clock64();
+#endif
             __syncthreads();
+#ifdef BIS_PERF_DEBUG
+            if (live && l >= 64 && l + 64 < Sw) {
+                const long long tc4 = clock64();
+                // ph 0: phase A = solve, phase B = prepare ; ph 1: phase A = prepare, phase B = refill + solve
+                dbg_acc[0] += tc1 - tc0;
+                dbg_acc[1] += tc2 - tc1;
+                dbg_acc[2] += tc3 - tc2;
+                dbg_acc[3] += tc4 - tc3;
+                dbg_acc[4] += 1;
+            }
+#endif
             if (live) {
                 if (ph == 0) refill<1>(a, st, Sw);
                 advance_pair<UPPER>(st);
@@ -605,6 +638,16 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
             for (int i = 0; i < NST; ++i) mbar_inval(&full[i]);
 #ifdef BIS_PERF_DEBUG
         if (a.stamps && threadIdx.x == 0) a.stamps[2 * z + 1] = bis_globaltimer();
+        if (a.stamps && lane == 0 && wl == (W > 1 ? 1 : 0)) {
+            int slot = -1;
+            const long long zs[5] = {1, 2, 8, 32, g.nz / 2};
+            for (int i = 0; i < 5; ++i)
+                if (z == zs[i]) slot = i;
+            if (slot >= 0) {
+                for (int i = 0; i < 5; ++i) a.stamps[2 * g.nz + (slot * 2 + ph) * 6 + i] = (unsigned long long)dbg_acc[i];
+                a.stamps[2 * g.nz + (slot * 2 + ph) * 6 + 5] = (unsigned long long)st.polls;
+            }
+        }
 #endif
     }
 }

@@ -28,7 +28,9 @@ with capi.Context(0) as ctx:
     ctx.set_option("wave_debug", 64 | extra)
     ctx.call("bis_sptrsv", L.h, x, D, b)
     ctx.sync()
-t = np.fromfile(path, dtype=np.uint64).reshape(-1, 2).astype(np.int64)
+raw = np.fromfile(path, dtype=np.uint64).astype(np.int64)
+acc = raw[-64:]
+t = raw[:-64].reshape(-1, 2)
 t0 = t[:, 0].min()
 start, end = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3
 print(f"HPCG-{n}: {t.shape[0]} planes; plane 0 runs {end[0] - start[0]:.1f} us; last plane ends at {end[-1]:.1f} us")
@@ -37,3 +39,11 @@ print(f"end-to-end lag between consecutive planes: median {np.median(d_end):.2f}
 print(f"duration of a plane (start to end): median {np.median(end - start):.1f} us, first {end[0]-start[0]:.1f}, last {end[-1]-start[-1]:.1f}")
 for z in list(range(0, 6)) + [t.shape[0] // 2, t.shape[0] - 1]:
     print(f"  plane {z:4d}: start {start[z]:9.1f} us, end {end[z]:9.1f} us")
+
+for slot, zname in enumerate(("1", "2", "8", "32", "nz/2")):
+    for ph in (0, 1):
+        a = acc[(slot * 2 + ph) * 6: (slot * 2 + ph) * 6 + 6]
+        if a[4] > 0:
+            names = ("solve", "barrier", "prepare", "barrier") if ph == 0 else ("prepare", "barrier", "refill+solve", "barrier")
+            print(f"  plane {zname:>4s}, block 1, warp {ph}: per step pair " + ", ".join(f"{nm} {v / a[4]:.0f}" for nm, v in zip(names, a[:4]))
+                  + f" cycles; total {a[:4].sum() / a[4]:.0f}; {a[5]} polls in the whole plane ({a[4]} mid-plane pairs)")
