@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libbis_b200.so")
+LIB_PATH = os.environ.get("BIS_LIB_PATH") or os.path.join(HERE, "lib", "libbis_b200.so")   # BIS_LIB_PATH: experiment builds (tools/)
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "bis_b200.h")
 
 NUM_SCALARS = 128

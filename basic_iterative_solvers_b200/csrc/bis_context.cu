@@ -84,6 +84,8 @@ static int context_init(bis_context *c, int device) {
     if (const char *e = getenv("BIS_TRSV_VARIANT")) c->opt_trsv_variant = atoi(e);
     if (const char *e = getenv("BIS_GRAPH")) c->opt_graph = atoi(e);
     if (const char *e = getenv("BIS_WIN_ROWS")) c->opt_win_rows = atoi(e);
+    if (const char *e = getenv("BIS_WAVE_CLUSTER")) c->opt_wave_cluster = atoi(e);
+    if (const char *e = getenv("BIS_WAVE_BACKOFF_NS")) c->opt_wave_backoff_ns = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("BIS_PRECOND_INNER_ITERS")) c->opt_precond_inner_iters = atoi(e);
     if (const char *e = getenv("BIS_PERM_MODE")) c->opt_perm_mode = (e[0] == 'C' || e[0] == 'c' || e[0] == '1') ? 1 : 0;
     return 0;
@@ -476,6 +478,8 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_blocked") c->opt_spmv_blocked = value;
     else if (k == "spmv_mult") c->opt_spmv_mult = value;
     else if (k == "win_rows") c->opt_win_rows = value;
+    else if (k == "wave_cluster") c->opt_wave_cluster = value;
+    else if (k == "wave_backoff_ns") c->opt_wave_backoff_ns = value < 0 ? 0 : value;
 #ifdef BIS_PERF_DEBUG
     else if (k == "wave_debug") c->opt_wave_debug = value;
     else if (k == "spmv_debug") c->opt_spmv_debug = value;

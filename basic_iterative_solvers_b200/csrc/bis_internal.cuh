@@ -204,6 +204,9 @@ struct bis_context {
     int opt_trsv_debug = 0;     // dump per-row timestamps of each solve to $BIS_TRSV_DEBUG_FILE
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
+    int opt_wave_cluster = 8;   // stencil wavefront: planes per thread-block cluster (1: no clusters, every hand-over through L2)
+    int opt_wave_backoff_ns = 1500;   // ... nanoseconds a plane fed through L2 falls back after it had to poll (clusters only)
+    int wave_cluster_used = 0;  // ... what the last solve ran with
     int opt_wave_debug = 0;     // stencil-wavefront perf experiments (results invalid); only in -DBIS_PERF_DEBUG builds
     int opt_spmv_debug = 0;     // perf experiments (results invalid when non-zero); only in -DBIS_PERF_DEBUG builds
     int opt_win_rows = 0;       // variant 3: rows per tile (0 auto; fixed once a matrix's format is built)
@@ -237,7 +240,9 @@ struct WaveFormat {
     double *d_w[2] = {nullptr, nullptr};   // working vectors [n_groups][S][32]; solves alternate, each re-arms the other
     int w_clean[2] = {0, 0};
     uint64_t w_epoch = 0;
+    int w_cluster = 0;             // cluster size of the solves that left the working vectors in their present state
     unsigned int *d_ticket = nullptr;
+    int cluster_fit[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};   // clusters of that many CTAs the device holds at once (-1: not asked yet)
 };
 
 struct LevelSets {

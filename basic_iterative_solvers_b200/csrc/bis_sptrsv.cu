@@ -590,6 +590,48 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     const char *stamp_file = (c->opt_wave_debug & 64) ? getenv("BIS_WAVE_STAMPS") : nullptr;
     if (stamp_file) BIS_CUDA(bis_cuda_malloc(&a.stamps, sizeof(unsigned long long) * (2 * (size_t)wf.nz + 64)));
 #endif
+    const size_t smem = wave::smem_bytes(wf.W);
+    const void *fn = a.g.upper ? reinterpret_cast<const void *>(wave::wave_kernel<true>) : reinterpret_cast<const void *>(wave::wave_kernel<false>);
+    BIS_CHECK(bis_ensure_dynamic_smem(c, fn, smem));
+    // consecutive planes run in the CTAs of one thread-block cluster and hand their values over through distributed
+    // shared memory (option wave_cluster: planes per cluster, 1 = everything through L2): the largest size <= the
+    // option of which at least one cluster fits the device
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3((unsigned)(wf.W * wave::PH * 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int cl = c->opt_wave_cluster < 1 ? 1 : (c->opt_wave_cluster > 16 ? 16 : c->opt_wave_cluster);
+    if (cl > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        cl = 8;
+    }
+    while (cl > 1 && (cl & (cl - 1))) --cl;
+    while (cl > 1 && cl > wf.nz) cl >>= 1;
+    int n_clusters = 0;
+    for (; cl > 1; cl >>= 1) {
+        if (wf.cluster_fit[cl] < 0) {       // asked once per factor and size
+            attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3((unsigned)(cl * c->sm_count));
+            int fit = 0;
+            if (cudaOccupancyMaxActiveClusters(&fit, fn, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                fit = 0;
+            }
+            wf.cluster_fit[cl] = fit;
+        }
+        if (wf.cluster_fit[cl] > 0) {
+            n_clusters = wf.cluster_fit[cl];
+            break;
+        }
+    }
+    if (wf.w_cluster != cl) {      // which planes leave a copy in the working vectors depends on the cluster size
+        wf.w_clean[0] = wf.w_clean[1] = 0;
+        wf.w_cluster = cl;
+    }
     if (wf.w_epoch != c->graph_epoch || c->capturing) {   // a graph replay may have used either vector since
         wf.w_clean[0] = wf.w_clean[1] = 0;
         wf.w_epoch = c->graph_epoch;
@@ -618,17 +660,23 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     }
 #endif
     BIS_CUDA(cudaMemsetAsync(wf.d_ticket, 0, sizeof(unsigned int), c->stream));
-    // one CTA per plane in flight, all of a plane's 32-line blocks in it (one warp each)
-    const size_t smem = wave::smem_bytes(wf.W);
-    int blocks = c->sm_count;
-    if (blocks > wf.nz) blocks = wf.nz;
-    if (a.g.upper) {
-        BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<true>), smem));
-        wave::wave_kernel<true><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
+    // one CTA per plane in flight, all of a plane's 32-line blocks in it (two warps each)
+    a.backoff_ns = cl > 1 ? (unsigned int)c->opt_wave_backoff_ns : 0u;
+    if (cl > 1) {
+        const int need = (wf.nz + cl - 1) / cl;
+        if (n_clusters > need) n_clusters = need;
+        attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)(n_clusters * cl));
+        void *kargs[1] = {&a};
+        BIS_CUDA(cudaLaunchKernelExC(&cfg, fn, kargs));
     } else {
-        BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(wave::wave_kernel<false>), smem));
-        wave::wave_kernel<false><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
+        int blocks = c->sm_count;
+        if (blocks > wf.nz) blocks = wf.nz;
+        if (a.g.upper) wave::wave_kernel<true><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
+        else wave::wave_kernel<false><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
     }
+    c->wave_cluster_used = cl;
+    if (getenv("BIS_WAVE_VERBOSE")) fprintf(stderr, "[bis] wavefront: %d planes per cluster, %d clusters, %d threads, %zu bytes of shared memory per CTA\n", cl, n_clusters, wf.W * wave::PH * 32, smem);
     BIS_LAUNCH_CHECK(c);
 #ifdef BIS_PERF_DEBUG
     if (a.stamps) {

@@ -49,6 +49,9 @@ constexpr int PF = WAVE_PF;    // steps a record is prefetched into L2 ahead of 
 #ifndef WAVE_GA
 #define WAVE_GA 2
 #endif
+#ifndef WAVE_BD_REG
+#define WAVE_BD_REG 0          // b and D by plain loads two own steps ahead (registers) instead of cp.async rings, see solve
+#endif
 constexpr int GA = WAVE_GA;    // steps between the request of a value of the previous plane and its entry into a ring
 constexpr int BD = 8;          // steps b and D are requested ahead
 constexpr int PH = 2;          // warps per 32-line block; they take its steps in turn (see solve / prepare)
@@ -170,6 +173,7 @@ struct Args {
     const double *D;
     const double *b;
     int post_mul_d;
+    unsigned int backoff_ns;   // a plane fed through L2 that had to poll falls back by this much (clusters only, see prepare)
 #ifdef BIS_PERF_DEBUG
     int dbg;                   // perf experiments (results invalid): 1 no record wait, 2 no b/D wait, 4 no x store,
                                // 8 no L2 operand requests, 16 no w stores, 32 no record copies
@@ -202,6 +206,55 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_inval(uint64_t *bar) {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
+}
+// ---- thread-block cluster: consecutive planes in the CTAs of one cluster hand their values over through distributed
+// shared memory (a remote store is visible after ~0.1 us; the way through L2 costs ~1.5 us and a polling consumer)
+__device__ __forceinline__ unsigned int cluster_ctarank() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned int cluster_nctarank() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the shared::cluster address of `saddr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, unsigned int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t caddr, unsigned long long v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(caddr), "l"(v) : "memory");
+}
+// The progress word of the hand-over: plain (weak) remote store / volatile local load on purpose.  A release / acquire
+// pair at cluster scope also orders the warp's global stores (w, x: an L2 round trip) in front of the word and cost
+// more than the hand-over saves (measured: 2.6 instead of 1.96 ms per HPCG-256 sweep).  What has to be ordered is only
+// the consumer's own re-arming store to its LOCAL shared memory before the producer's next remote store to the same
+// row; the producer issues that store after it has seen the word, i.e. two trips through the cluster network after the
+// local store was issued.  Were it ever violated the consumer would wait for a value that has been overwritten by "not
+// ready": the watchdog reports it, no wrong value can be read.
+#ifndef WAVE_PROG_FENCED
+#define WAVE_PROG_FENCED 0
+#endif
+__device__ __forceinline__ void st_cluster_prog(uint32_t caddr, int v) {
+    if (WAVE_PROG_FENCED) asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(caddr), "r"(v) : "memory");
+    else asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(caddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_prog(uint32_t saddr) {
+    int v;
+    if (WAVE_PROG_FENCED) asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    else asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_shared_u64(uint32_t saddr) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(saddr) : "memory");
+    return v;
 }
 
 // ---- exact division off the critical path ---------------------------------------------------------------------
@@ -251,14 +304,16 @@ __device__ __forceinline__ double div_by_rcp(double a, double d, double r) {
 // logical row it needs (base - 3 .. base + 6) at a compile-time offset, without wrap-around arithmetic.
 constexpr int RWC = 32 * MAX_WARPS + 32;     // ring width: column y + 1 of the plane's line y, one spare column either side
 constexpr int RROWS = 2 * RING;
-constexpr int SROWS = 4;                     // staging rows (a value sits there GA = 2 steps)
+constexpr int SROWS = 8;                     // staging rows: a requested value sits there GA = 2 steps (rows 0..3); a plane whose
+                                             // predecessor runs in the same cluster uses all eight as its INBOX (see below)
+constexpr int IB = SROWS;                    // inbox depth in steps
 constexpr int O_RINGB = NST * REC_DOUBLES;
 constexpr int O_RINGD = O_RINGB + BD * 32;
 constexpr int O_RINGS = O_RINGD + BD * 32;
 constexpr int O_FULL = O_RINGS + SROWS * 32;
 constexpr int BLK_DOUBLES = O_FULL + 8;
 constexpr int O_GHOST = RROWS * RWC;         // ring of the previous plane's values, relative to the ring of results
-static_assert(NST == 4 && BD == 8 && GA == 2 && PH == 2 && RING == 8, "the slot arithmetic below is written for these");
+static_assert(NST == 4 && BD == 8 && (GA == 2 || GA == 4) && PH == 2 && RING == 8 && SROWS == 8, "the slot arithmetic below is written for these");
 __host__ __device__ inline size_t smem_bytes(int W) { return ((size_t)W * BLK_DOUBLES + 2 * (size_t)RROWS * RWC) * 8; }
 
 extern __shared__ __align__(128) double wave_sm[];   // the CTA's dynamic shared memory (addressed directly: no generic pointers)
@@ -280,6 +335,7 @@ struct State {
     double v_own, v_nb;        // matrix values of the two late slots: own predecessor (x-1) and (x+1, y-1)
     // what solve<U-2> left for solve<U>
     double bb, dd, rcp;        // b, D and RN(1/D) of the step's row (0, 1, 1 for a lane without a row)
+    double bb_n, dd_n;         // b and D of this warp's step after that (loads in flight)
     bool ieee;                 // the step's divisor needs the IEEE division
     const double *pm;          // request at U = 0 (+ U * 32), WITHOUT the lane offset
     int pm_lo, pm_hi;          // ... valid while pm_lo <= ls < pm_hi
@@ -289,6 +345,13 @@ struct State {
     const double *b_req, *d_req;   // b / D of the row this lane has BD steps later (+- U)
     uint64_t pol;
     const double *rec_next;    // record of local step ls + 1 + NST at U = 0 (+ U records)
+    // hand-over inside a cluster (see wave_kernel)
+    bool in_push;              // the previous plane runs in this cluster: its values arrive in this block's inbox
+    bool out_push;             // the next plane runs in this cluster: results also go into its inbox
+    uint32_t inbox;            // shared::cta address of this lane's inbox column, row 0
+    uint32_t push_to;          // shared::cluster address of the same place in the next plane's CTA
+    uint32_t prog;             // shared::cta address of this block's progress word (the next plane's CTA writes it)
+    uint32_t prog_to;          // shared::cluster address of the previous plane's progress word for this block
 #ifdef BIS_PERF_DEBUG
     long long polls;
 #endif
@@ -340,7 +403,26 @@ __device__ __forceinline__ void solve(const Args &a, State &st, const int Sw) {
     rp[U * RWC + 1] = r;
     rp[(U + RING) * RWC + 1] = r;
     // ---- results out ----------------------------------------------------------------------------------------
-    if (in_range && !WAVE_DBG(a, 16)) {
+    if (in_range && st.out_push) {
+        // inbox row ls % IB of the next plane's CTA is free once that CTA has taken step ls - IB out of it
+        if (ld_prog(st.prog) < ls - IB) {
+            unsigned int spins = 0;
+            unsigned long long t_wd = 0;
+            while (ld_prog(st.prog) < ls - IB) {
+                if ((++spins & 1023u) == 0) {
+                    if (t_wd == 0) t_wd = bis_globaltimer();
+                    if (*reinterpret_cast<volatile int *>(a.errflag) != 0 || bis_globaltimer() - t_wd > WATCHDOG_NS) {
+                        atomicExch(a.errflag, 6);
+                        break;
+                    }
+                }
+            }
+        }
+        st_cluster_u64(st.push_to + (uint32_t)((ls & (IB - 1)) * 256), (unsigned long long)__double_as_longlong(r));
+    }
+    // (a plane whose successor gets the values pushed needs no copy in the working vector; neither vector is touched
+    // there, so both stay "not ready" at these places -- the host resets them when the cluster size changes)
+    if (in_range && !st.out_push && !WAVE_DBG(a, 16)) {
         __stcg(st.w_out + U * 32, r);                                      // inactive lanes publish 0.0
         st.wc_out[U * 32] = SENT;
     }
@@ -348,6 +430,30 @@ __device__ __forceinline__ void solve(const Args &a, State &st, const int Sw) {
     // ---- b, D and 1/D of this warp's next step (ls + PH), off the chain ----------------------------------
     // b / D were requested BD steps ahead: five younger copy groups of this thread may still be in flight
     // (prepare / solve / prepare / solve / prepare)
+#if WAVE_BD_REG
+    // b and D are loaded straight into registers two of this warp's steps (four steps) ahead.  They used to come
+    // through cp.async rings, eight steps ahead -- but a thread's copy groups complete in order, so prepare's wait for
+    // its two-step-old request of previous-plane values also waited for the b / D copies committed in between, and under
+    // load those took longer than that (prepare 800 -> 1400 cycles in mid-sweep planes, profiles/r03_wave_*).
+    {
+        const bool act2 = (unsigned)(xp + PH) < (unsigned)st.nx_eff;
+        const double d2 = act2 ? st.dd_n : 1.0;
+        st.bb = act2 ? st.bb_n : 0.0;
+        st.dd = d2;
+        st.ieee = div_guard_d(d2);
+        st.rcp = rcp_exact(st.ieee ? 1.0 : d2);
+        if ((unsigned)(xp + 2 * PH) < (unsigned)st.nx_eff) {
+            st.bb_n = __ldcs(st.b_req + (UPPER ? -(U + 2 * PH - BD) : (U + 2 * PH - BD)));
+            st.dd_n = __ldcs(st.d_req + (UPPER ? -(U + 2 * PH - BD) : (U + 2 * PH - BD)));
+        }
+    }
+    if ((ls & 2) == 0 && (unsigned)(xp + PH + BD + 16) < (unsigned)st.nx_eff) {   // the sectors of later steps into L2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.b_req + (UPPER ? -(U + PH + 16) : (U + PH + 16))));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st.d_req + (UPPER ? -(U + PH + 16) : (U + PH + 16))));
+    }
+    cp_async_commit();
+    return;
+#endif
     if (!WAVE_DBG(a, 2)) cp_async_wait<BD - PH - 1>();
     double *bd = wave_sm + st.blk + O_RINGB + ((st.ls + PH) & (BD - 1)) * 32 + U * 32;    // slot (ls + PH) % BD: no wrap, st.ls is even
     {
@@ -390,10 +496,44 @@ __device__ __forceinline__ void prepare(const Args &a, State &st, const int Sw) 
     // the value of the previous plane this warp requested GA steps ago: global -> shared by an asynchronous copy
     // through L2 only (no register is tied up while it is in flight, sixteen lanes fetch the row's 256 bytes);
     // GA - 1 younger copy groups of this thread may still be in flight
+    unsigned long long vm = 0ull;
+    if (st.in_push) {
+        // the previous plane's CTA stores its step ls + 5 into row (ls + 5) % IB of this block's inbox (remote shared
+        // memory; the value is its own ready flag): take it, mark the row "not ready" again and tell the producer
+        const int q = ls + 5;
+        if (q >= 0 && q < Sw) {                                  // warp-uniform
+            const uint32_t slot = st.inbox + (uint32_t)((q & (IB - 1)) * 256);
+            vm = ld_volatile_shared_u64(slot);
+            if (__any_sync(0xffffffffu, vm == SENT)) {
+#ifdef BIS_PERF_DEBUG
+                st.polls += 1;
+#endif
+                unsigned int spins = 0;
+                unsigned long long t_wd = 0;
+                for (;;) {
+                    if (vm == SENT) vm = ld_volatile_shared_u64(slot);
+                    if (!__any_sync(0xffffffffu, vm == SENT)) break;
+                    bool give_up = false;
+                    if ((++spins & 1023u) == 0) {
+                        if (t_wd == 0) t_wd = bis_globaltimer();
+                        give_up = *reinterpret_cast<volatile int *>(a.errflag) != 0 || bis_globaltimer() - t_wd > WATCHDOG_NS;
+                    }
+                    if (__any_sync(0xffffffffu, give_up)) {
+                        atomicExch(a.errflag, 6);
+                        vm = 0ull;
+                        break;
+                    }
+                }
+            }
+            asm volatile("st.shared::cta.u64 [%0], %1;" ::"r"(slot), "l"(SENT) : "memory");
+            __syncwarp();
+            if (st.lane == 0) st_cluster_prog(st.prog_to, q);
+        }
+    } else {
     cp_async_wait<GA - 1>();
     __syncwarp();
     const int o_stage = st.blk + O_RINGS + U * 32;              // + slot * 32
-    unsigned long long vm = reinterpret_cast<const unsigned long long *>(wave_sm)[o_stage + ((st.ls & 2) ^ 2) * 32];   // slot (ls - GA) % SROWS
+    vm = reinterpret_cast<const unsigned long long *>(wave_sm)[o_stage + (((st.ls - GA) & (SROWS - 2))) * 32];   // slot (ls - GA) % SROWS
     if (__any_sync(0xffffffffu, vm == SENT)) {
 #ifdef BIS_PERF_DEBUG
         st.polls += 1;
@@ -416,6 +556,13 @@ __device__ __forceinline__ void prepare(const Args &a, State &st, const int Sw) 
                 break;
             }
         }
+        // Having had to poll means this plane sits right behind its predecessor, where every later request misses too
+        // and every step pays this round trip (a stable state: the plane then runs at step + round trip, and so does
+        // everything behind it).  Falling back puts the next requests into the zone where they hit.  Without clusters
+        // that is no gain (every plane falls back: the same lag per plane, measured); with clusters only one plane in
+        // CL is fed through L2, and the CL - 1 planes behind it follow at the pace of a step without a round trip.
+        if (a.backoff_ns) __nanosleep(a.backoff_ns);
+    }
     }
     const int s8 = st.ls & (RING - 1);
     const double *rp = wave_sm + st.ring + s8 * RWC;
@@ -454,8 +601,10 @@ __device__ __forceinline__ void prepare(const Args &a, State &st, const int Sw) 
         gp[RING * RWC] = gv;
     }
     // ---- request for a later step (consumed by this same warp: GA is a multiple of PH) ---------------------
-    const int o_req = (st.blk - st.lane) + O_RINGS + ((st.ls & 2) + U) * 32;     // slot ls % SROWS
-    if (ls >= st.pm_lo && ls < st.pm_hi && !WAVE_DBG(a, 8)) {
+    const int o_req = (st.blk - st.lane) + O_RINGS + ((st.ls & (SROWS - 2)) + U) * 32;     // slot ls % SROWS
+    if (st.in_push) {
+        // nothing to request: the values are pushed
+    } else if (ls >= st.pm_lo && ls < st.pm_hi && !WAVE_DBG(a, 8)) {
         if (st.lane < 16) cp_async16_cg(wave_sm + o_req + 2 * st.lane, st.pm + U * 32 + 2 * st.lane);
     } else {
         wave_sm[o_req + st.lane] = 0.0;     // no such value: 0.0 (never "not ready")
@@ -502,6 +651,13 @@ __device__ __forceinline__ void advance_pair(State &st) {
 template <bool UPPER>
 __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
     __shared__ long long s_plane;
+    __shared__ int s_prog[MAX_WARPS];
+    // CL consecutive planes are taken by the CL CTAs of a cluster (rank r: plane CL * ticket + r).  Ranks > 0 get
+    // the values of their previous plane PUSHED into shared memory by the CTA of rank r - 1 (st.shared::cluster,
+    // visible after ~0.1 us, polled in local shared memory); rank 0 fetches them from the working vector in L2 as
+    // before (the plane before it belongs to an earlier ticket, i.e. to a cluster that already runs).  Launched
+    // without clusters, CL = 1 and everything goes through L2.
+    const unsigned int CL = cluster_nctarank(), crank = cluster_ctarank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wl = warp / PH;                            // 32-line block of the plane
     const int ph = warp % PH;                            // this warp solves the block's steps with ls % PH == ph
@@ -518,17 +674,37 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
     const int y = wl * 32 + lane;
     uint64_t *full = reinterpret_cast<uint64_t *>(wave_sm + wl * BLK_DOUBLES + O_FULL);
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_plane = (long long)atomicAdd(a.ticket, 1u);
+        // every CTA of the cluster has left its plane: nothing is pushed into this CTA's inboxes any more
+        if (CL > 1) cluster_sync();
+        else __syncthreads();
+        if (threadIdx.x == 0 && crank == 0) {
+            const long long t = (long long)atomicAdd(a.ticket, 1u);
+            if (CL > 1) {
+                for (unsigned int r = 0; r < CL; ++r)
+                    st_cluster_u64(cluster_map(tma::smem_u32(&s_plane), r), (unsigned long long)(t * CL + r));
+            } else {
+                s_plane = t;
+            }
+        }
         for (int i = threadIdx.x; i < 2 * RROWS * RWC; i += blockDim.x) wave_sm[W * BLK_DOUBLES + i] = 0.0;   // both rings
-        for (int i = lane + 32 * ph; i < SROWS * 32; i += 32 * PH) wave_sm[wl * BLK_DOUBLES + O_RINGS + i] = 0.0;
+        {
+            const double arm = crank > 0 ? __longlong_as_double((long long)SENT) : 0.0;     // inbox rows start "not ready"
+            for (int i = lane + 32 * ph; i < SROWS * 32; i += 32 * PH) wave_sm[wl * BLK_DOUBLES + O_RINGS + i] = arm;
+        }
+        if (threadIdx.x < MAX_WARPS) s_prog[threadIdx.x] = -1;
         if (lane == 0 && ph == 0) {
             for (int i = 0; i < NST; ++i) tma::mbar_init(&full[i], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncthreads();
+        if (CL > 1) cluster_sync();
+        else __syncthreads();
         const long long z = s_plane;
-        if (z >= g.nz) break;
+        if (z - crank >= g.nz) break;          // the whole cluster is past the last plane
+        if (z >= g.nz) {                       // only this rank is: keep the cluster's barriers
+            if (lane == 0 && ph == 0)
+                for (int i = 0; i < NST; ++i) mbar_inval(&full[i]);
+            continue;
+        }
         const long long grp = z * W + wl;
         const long long line_p0 = (z * g.ny + y) * g.nx;
         const bool has_prev = z > 0;
@@ -538,8 +714,8 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
         st.xp = ls0 - 2 * lane;
         st.pre = 0.0;
         st.v_own = st.v_nb = 0.0;
-        st.bb = 0.0;
-        st.dd = st.rcp = 1.0;
+        st.bb = st.bb_n = 0.0;
+        st.dd = st.rcp = st.dd_n = 1.0;
         st.ieee = false;
 #pragma unroll
         for (int i = 0; i < K - 2; ++i) st.pp[i] = 0.0;
@@ -547,6 +723,12 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
         st.pm = a.w + ((has_prev ? grp - W : 0) * Sw + (ls0 + 5 + GA)) * 32;
         st.pm_lo = -(5 + GA);
         st.pm_hi = has_prev ? Sw - (5 + GA) : -(1 << 30);
+        st.in_push = crank > 0;
+        st.out_push = crank + 1 < CL && z + 1 < g.nz;
+        st.inbox = tma::smem_u32(wave_sm + wl * BLK_DOUBLES + O_RINGS + lane);
+        st.prog = tma::smem_u32(&s_prog[wl]);
+        st.push_to = st.out_push ? cluster_map(st.inbox, crank + 1) : 0u;
+        st.prog_to = st.in_push ? cluster_map(st.prog, crank - 1) : 0u;
         st.w_out = a.w + (grp * Sw + ls0) * 32 + lane;
         st.wc_out = reinterpret_cast<unsigned long long *>(a.w_clean) + (grp * Sw + ls0) * 32 + lane;
         {
@@ -640,7 +822,7 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
         if (a.stamps && threadIdx.x == 0) a.stamps[2 * z + 1] = bis_globaltimer();
         if (a.stamps && lane == 0 && wl == (W > 1 ? 1 : 0)) {
             int slot = -1;
-            const long long zs[5] = {1, 2, 8, 32, g.nz / 2};
+            const long long zs[5] = {1, 8, 33, g.nz / 2, g.nz / 2 + 4};
             for (int i = 0; i < 5; ++i)
                 if (z == zs[i]) slot = i;
             if (slot >= 0) {
