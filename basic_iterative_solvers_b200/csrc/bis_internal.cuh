@@ -205,7 +205,7 @@ struct bis_context {
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
     int opt_wave_cluster = 8;   // stencil wavefront: planes per thread-block cluster (1: no clusters, every hand-over through L2)
-    int opt_wave_backoff_ns = 1500;   // ... nanoseconds a plane fed through L2 falls back after it had to poll (clusters only)
+    int opt_wave_backoff_ns = 0;      // ... nanoseconds a plane fed through L2 falls back after it had to poll (clusters only)
     int wave_cluster_used = 0;  // ... what the last solve ran with
     int opt_wave_debug = 0;     // stencil-wavefront perf experiments (results invalid); only in -DBIS_PERF_DEBUG builds
     int opt_spmv_debug = 0;     // perf experiments (results invalid when non-zero); only in -DBIS_PERF_DEBUG builds

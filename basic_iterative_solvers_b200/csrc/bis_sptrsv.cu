@@ -597,7 +597,7 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     // shared memory (option wave_cluster: planes per cluster, 1 = everything through L2): the largest size <= the
     // option of which at least one cluster fits the device
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3((unsigned)(wf.W * wave::PH * 32));
+    cfg.blockDim = dim3((unsigned)((wf.W * wave::PH * 32 + 32)));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
@@ -672,11 +672,11 @@ int wave_solve(bis_context *c, const bis_matrix *T, double *x, const double *D, 
     } else {
         int blocks = c->sm_count;
         if (blocks > wf.nz) blocks = wf.nz;
-        if (a.g.upper) wave::wave_kernel<true><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
-        else wave::wave_kernel<false><<<blocks, wf.W * wave::PH * 32, smem, c->stream>>>(a);
+        if (a.g.upper) wave::wave_kernel<true><<<blocks, (wf.W * wave::PH * 32 + 32), smem, c->stream>>>(a);
+        else wave::wave_kernel<false><<<blocks, (wf.W * wave::PH * 32 + 32), smem, c->stream>>>(a);
     }
     c->wave_cluster_used = cl;
-    if (getenv("BIS_WAVE_VERBOSE")) fprintf(stderr, "[bis] wavefront: %d planes per cluster, %d clusters, %d threads, %zu bytes of shared memory per CTA\n", cl, n_clusters, wf.W * wave::PH * 32, smem);
+    if (getenv("BIS_WAVE_VERBOSE")) fprintf(stderr, "[bis] wavefront: %d planes per cluster, %d clusters, %d threads, %zu bytes of shared memory per CTA\n", cl, n_clusters, (wf.W * wave::PH * 32 + 32), smem);
     BIS_LAUNCH_CHECK(c);
 #ifdef BIS_PERF_DEBUG
     if (a.stamps) {

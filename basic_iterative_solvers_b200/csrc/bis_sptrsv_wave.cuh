@@ -649,7 +649,7 @@ __device__ __forceinline__ void advance_pair(State &st) {
 }
 
 template <bool UPPER>
-__global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
+__global__ void __launch_bounds__(MAX_WARPS * PH * 32 + 32, 1) wave_kernel(Args a) {
     __shared__ long long s_plane;
     __shared__ int s_prog[MAX_WARPS];
     // CL consecutive planes are taken by the CL CTAs of a cluster (rank r: plane CL * ticket + r).  Ranks > 0 get
@@ -659,7 +659,11 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
     // without clusters, CL = 1 and everything goes through L2.
     const unsigned int CL = cluster_nctarank(), crank = cluster_ctarank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wl = warp / PH;                            // 32-line block of the plane
+    // The CTA's last warp computes nothing: its lane w re-fills the record stages of block w (see refill).  With the
+    // bulk copies issued by lane 0 of the block's solving warp -- a proxy fence, an mbarrier transaction, the copy and an
+    // L2 prefetch, ~500 cycles of one lane -- every second solve started that much later (profiles/r03_wave_*).
+    const bool dma = warp >= a.g.W * PH;
+    const int wl = dma ? 0 : warp / PH;                  // 32-line block of the plane
     const int ph = warp % PH;                            // this warp solves the block's steps with ls % PH == ph
     const Grid g = a.g;
     const int W = g.W;
@@ -689,10 +693,11 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
         for (int i = threadIdx.x; i < 2 * RROWS * RWC; i += blockDim.x) wave_sm[W * BLK_DOUBLES + i] = 0.0;   // both rings
         {
             const double arm = crank > 0 ? __longlong_as_double((long long)SENT) : 0.0;     // inbox rows start "not ready"
-            for (int i = lane + 32 * ph; i < SROWS * 32; i += 32 * PH) wave_sm[wl * BLK_DOUBLES + O_RINGS + i] = arm;
+            if (!dma)
+                for (int i = lane + 32 * ph; i < SROWS * 32; i += 32 * PH) wave_sm[wl * BLK_DOUBLES + O_RINGS + i] = arm;
         }
         if (threadIdx.x < MAX_WARPS) s_prog[threadIdx.x] = -1;
-        if (lane == 0 && ph == 0) {
+        if (lane == 0 && ph == 0 && !dma) {
             for (int i = 0; i < NST; ++i) tma::mbar_init(&full[i], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -701,14 +706,37 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
         const long long z = s_plane;
         if (z - crank >= g.nz) break;          // the whole cluster is past the last plane
         if (z >= g.nz) {                       // only this rank is: keep the cluster's barriers
-            if (lane == 0 && ph == 0)
+            if (lane == 0 && ph == 0 && !dma)
                 for (int i = 0; i < NST; ++i) mbar_inval(&full[i]);
+            continue;
+        }
+        const int ls0 = -2 * RING;               // first local step of a block (request / ring-fill machinery only)
+        const int s_end = 64 * (W - 1) + Sw;
+        if (dma) {
+            // lane w < W: the record stream of block w; same steps and the same barriers as the computing warps
+            st.lane = 0;
+            st.blk = lane * BLK_DOUBLES;
+            st.ls = ls0;
+            st.rec_next = a.rec + (((z * W + lane) * Sw) + (ls0 + 1 + NST)) * REC_DOUBLES;
+#pragma unroll 1
+            for (int s = ls0; s < s_end; s += PH) {
+                const int l = s - 64 * lane;
+                const bool live = lane < W && l >= ls0 && l < Sw;
+                __syncthreads();
+                if (live) refill<0>(a, st, Sw);
+                __syncthreads();
+                if (live) {
+                    refill<1>(a, st, Sw);
+                    st.ls += PH;
+                    st.rec_next += (size_t)PH * REC_DOUBLES;
+                }
+            }
+            __syncthreads();
             continue;
         }
         const long long grp = z * W + wl;
         const long long line_p0 = (z * g.ny + y) * g.nx;
         const bool has_prev = z > 0;
-        const int ls0 = -2 * RING;               // first local step of a block (request / ring-fill machinery only)
         st.nx_eff = y < g.ny ? g.nx : 0;
         st.ls = ls0;
         st.xp = ls0 - 2 * lane;
@@ -742,7 +770,6 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
         st.rec_next = a.rec + (grp * Sw + (ls0 + 1 + NST)) * REC_DOUBLES;
         // global steps of the CTA: block w's local step is s - 64 w (its lane 0 is "lane 32 w" of the plane);
         // all warps walk the same steps and keep the same barriers
-        const int s_end = 64 * (W - 1) + Sw;
 #ifdef BIS_PERF_DEBUG
         if (a.stamps && threadIdx.x == 0) a.stamps[2 * z] = bis_globaltimer();
 #endif
@@ -754,24 +781,6 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
         for (int s = ls0; s < s_end; s += PH) {
             const int l = s - 64 * wl;
             const bool live = l >= ls0 && l < Sw;    // warp-uniform; st.ls == l while live
-#ifdef BIS_PERF_DEBUG
-            if (WAVE_DBG(a, 256)) {      // experiment: the two roles of a step one after the other
-                if (live && ph == 0) solve<0, UPPER>(a, st, Sw);
-                __syncthreads();
-                if (live && ph != 0) prepare<0, UPPER>(a, st, Sw);
-                __syncthreads();
-                if (live && ph != 0) refill<0>(a, st, Sw);
-                if (live && ph != 0) solve<1, UPPER>(a, st, Sw);
-                __syncthreads();
-                if (live && ph == 0) prepare<1, UPPER>(a, st, Sw);
-                __syncthreads();
-                if (live) {
-                    if (ph == 0) refill<1>(a, st, Sw);
-                    advance_pair<UPPER>(st);
-                }
-                continue;
-            }
-#endif
 #ifdef BIS_PERF_DEBUG
             const long long tc0 = clock64();
 #endif
@@ -790,7 +799,6 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
                 if (ph == 0) {
                     prepare<1, UPPER>(a, st, Sw);
                 } else {
-                    refill<0>(a, st, Sw);
                     solve<1, UPPER>(a, st, Sw);
                 }
             }
@@ -809,10 +817,7 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32, 1) wave_kernel(Args a) {
                 dbg_acc[4] += 1;
             }
 #endif
-            if (live) {
-                if (ph == 0) refill<1>(a, st, Sw);
-                advance_pair<UPPER>(st);
-            }
+            if (live) advance_pair<UPPER>(st);
         }
         cp_async_wait<0>();
         __syncthreads();

@@ -157,3 +157,32 @@ def test_wavefront_is_chosen_automatically_for_27_point_factors_only(ctx):
             m.free()
         for v in (D, b, x):
             ctx.free(v)
+
+
+@pytest.mark.parametrize("name", ["20x14x11", "33x70x3", "64x64x160", "224x225x8"])
+def test_wavefront_cluster_sizes_give_the_same_bits(ctx, name):
+    """Planes per thread-block cluster (option wave_cluster): 1 = every hand-over through L2, > 1 = planes of a cluster
+    push their values into the next plane's shared memory.  Every size -- also those that do not divide the number of
+    planes, and a change of size between two solves with the same factor (which planes leave a copy in the twin
+    working vectors depends on it) -- must give the bits of the dataflow solve."""
+    A = _matrix(ctx, name)
+    n = A.info()["n_rows"]
+    L, U = ctx.split_triangular(A)
+    D = ctx.alloc(n)
+    ctx.call("bis_matrix_extract_diagonal", A.h, D, None)
+    bh = np.random.default_rng(11).uniform(-1.0, 1.0, n)
+    try:
+        ctx.set_option("trsv_variant", 3)
+        want = _solves(ctx, L, U, D, bh, n)
+        ctx.set_option("trsv_variant", 5)
+        for cl in (8, 1, 2, 16, 4, 8):
+            ctx.set_option("wave_cluster", cl)
+            got = _solves(ctx, L, U, D, bh, n)
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w), f"wave_cluster = {cl}"
+    finally:
+        ctx.set_option("trsv_variant", 0)
+        ctx.set_option("wave_cluster", 8)
+    for m in (L, U, A):
+        m.free()
+    ctx.free(D)
