@@ -496,6 +496,35 @@ __device__ __forceinline__ void prepare(const Args &a, State &st, const int Sw) 
     // the value of the previous plane this warp requested GA steps ago: global -> shared by an asynchronous copy
     // through L2 only (no register is tied up while it is in flight, sixteen lanes fetch the row's 256 bytes);
     // GA - 1 younger copy groups of this thread may still be in flight
+    const int s8 = st.ls & (RING - 1);
+    const double *rp = wave_sm + st.ring + s8 * RWC;
+    {
+        const double *rv = wave_sm + st.blk + stage * REC_DOUBLES;
+        double v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = rv[k * 32];
+        double pre = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int kk = UPPER ? K - 1 - k : k;       // plane k of the record is stencil slot kk
+            const int dz = kk / 9 - 1, dy = (kk / 3) % 3 - 1, dx = kk % 3 - 1;
+            if (kk == K - 1) {
+                st.v_own = v[k];
+            } else if (kk == K - 2) {
+                st.v_nb = v[k];
+            } else {
+                // produced at step (s + 1) + dx + 2 dy of the producing line: logical ring row U + 1 + dx + 2 dy
+                // relative to the pair's even step, i.e. -2 .. 5: a copy of it sits at a fixed physical distance
+                const int d = U + 1 + dx + 2 * dy;
+                const double o = rp[(dz < 0 ? O_GHOST : 0) + (d < 0 ? d + RING : d) * RWC + 1 + dy];
+                if (!UPPER) pre = add_rn(pre, mul_rn(v[k], o));
+                else st.pp[k - 2] = mul_rn(v[k], o);
+            }
+        }
+        st.pre = pre;
+    }
+    // ---- arrival of the previous plane's value for ring row ls + 5: looked at only now, after the products, so that
+    // a value that is still on its way is waited for while this warp had something else to do
     unsigned long long vm = 0ull;
     if (st.in_push) {
         // the previous plane's CTA stores its step ls + 5 into row (ls + 5) % IB of this block's inbox (remote shared
@@ -563,33 +592,6 @@ __device__ __forceinline__ void prepare(const Args &a, State &st, const int Sw) 
         // CL is fed through L2, and the CL - 1 planes behind it follow at the pace of a step without a round trip.
         if (a.backoff_ns) __nanosleep(a.backoff_ns);
     }
-    }
-    const int s8 = st.ls & (RING - 1);
-    const double *rp = wave_sm + st.ring + s8 * RWC;
-    {
-        const double *rv = wave_sm + st.blk + stage * REC_DOUBLES;
-        double v[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = rv[k * 32];
-        double pre = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int kk = UPPER ? K - 1 - k : k;       // plane k of the record is stencil slot kk
-            const int dz = kk / 9 - 1, dy = (kk / 3) % 3 - 1, dx = kk % 3 - 1;
-            if (kk == K - 1) {
-                st.v_own = v[k];
-            } else if (kk == K - 2) {
-                st.v_nb = v[k];
-            } else {
-                // produced at step (s + 1) + dx + 2 dy of the producing line: logical ring row U + 1 + dx + 2 dy
-                // relative to the pair's even step, i.e. -2 .. 5: a copy of it sits at a fixed physical distance
-                const int d = U + 1 + dx + 2 * dy;
-                const double o = rp[(dz < 0 ? O_GHOST : 0) + (d < 0 ? d + RING : d) * RWC + 1 + dy];
-                if (!UPPER) pre = add_rn(pre, mul_rn(v[k], o));
-                else st.pp[k - 2] = mul_rn(v[k], o);
-            }
-        }
-        st.pre = pre;
     }
     // ---- the value of the previous plane requested GA steps ago enters the ring (logical row ls + 5) ------
     {
