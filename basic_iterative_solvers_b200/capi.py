@@ -73,6 +73,7 @@ _SIGS = {
     "bis_matrix_split_triangular": ([c_ctx, c_mat, C.POINTER(c_mat), C.POINTER(c_mat)], cint),
     "bis_matrix_scale_symmetric": ([c_ctx, c_mat, c_dev], cint),
     "bis_matrix_colouring_permutation": ([c_ctx, c_mat, C.c_void_p, C.c_void_p, C.POINTER(cint)], cint),
+    "bis_matrix_bfs_permutation": ([c_ctx, c_mat, cint, C.c_void_p, C.c_void_p, C.POINTER(cint)], cint),
     "bis_matrix_permute_symmetric": ([c_ctx, c_mat, C.c_void_p, C.c_void_p, C.POINTER(c_mat)], cint),
     "bis_vector_permute": ([c_ctx, c_dev, c_dev, C.c_void_p, i64], cint),
     "bis_index_alloc": ([c_ctx, i64, C.POINTER(C.c_void_p)], cint),
@@ -295,6 +296,21 @@ class Context:
             self.call("bis_matrix_upload_crs", n, n if n_cols is None else n_cols, int(rp[-1]),
                       _np_ptr(rp), _np_ptr(col), _np_ptr(val), C.byref(m))
         return Matrix(self, m)
+
+    def bfs_permutation(self, A: Matrix, mode: int):
+        """(perm, inv_perm, n_levels): mode 2 = BFS levels, 3 = reverse Cuthill-McKee, 4 = Cuthill-McKee (host arrays)."""
+        n = A.info()["n_rows"]
+        dp, di = C.c_void_p(), C.c_void_p()
+        self.call("bis_index_alloc", n, C.byref(dp))
+        self.call("bis_index_alloc", n, C.byref(di))
+        nl = cint(0)
+        self.call("bis_matrix_bfs_permutation", A.h, mode, dp, di, C.byref(nl))
+        perm, inv = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.call("bis_index_download", _np_ptr(perm), dp, n)
+        self.call("bis_index_download", _np_ptr(inv), di, n)
+        self.call("bis_index_free", dp)
+        self.call("bis_index_free", di)
+        return perm, inv, int(nl.value)
 
     def colouring_permutation(self, A: Matrix):
         """(perm, inv_perm, n_colours) of the multicolouring permutation of A (host arrays)."""

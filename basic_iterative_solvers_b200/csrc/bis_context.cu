@@ -87,7 +87,9 @@ static int context_init(bis_context *c, int device) {
     if (const char *e = getenv("BIS_WAVE_CLUSTER")) c->opt_wave_cluster = atoi(e);
     if (const char *e = getenv("BIS_WAVE_BACKOFF_NS")) c->opt_wave_backoff_ns = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("BIS_PRECOND_INNER_ITERS")) c->opt_precond_inner_iters = atoi(e);
-    if (const char *e = getenv("BIS_PERM_MODE")) c->opt_perm_mode = (e[0] == 'C' || e[0] == 'c' || e[0] == '1') ? 1 : 0;
+    if (const char *e = getenv("BIS_PERM_MODE"))     // NONE / C (colouring) / BFS / RCM / CM, or the option's number
+        c->opt_perm_mode = (e[0] == 'C' || e[0] == 'c') ? ((e[1] == 'M' || e[1] == 'm') ? 4 : 1)
+                         : (e[0] == 'B' || e[0] == 'b') ? 2 : (e[0] == 'R' || e[0] == 'r') ? 3 : (e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 0;
     return 0;
 }
 
@@ -450,7 +452,7 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_lanes") c->opt_spmv_lanes = value;
     else if (k == "graph") c->opt_graph = value;
     else if (k == "perm_mode") {
-        BIS_REQUIRE(value == 0 || value == 1, "perm_mode: 0 (NONE) or 1 (C, multicolouring)");
+        BIS_REQUIRE(value >= 0 && value <= 4, "perm_mode: 0 (NONE), 1 (C, multicolouring), 2 (BFS levels), 3 (reverse Cuthill-McKee) or 4 (Cuthill-McKee)");
         c->opt_perm_mode = value;
     }
     else if (k == "precond_inner_iters") {

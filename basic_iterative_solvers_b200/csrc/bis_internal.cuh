@@ -191,7 +191,7 @@ struct bis_context {
     int opt_spmv_fused = 1;     // distributed SpMV over peer memory as ONE kernel (0: pack / interior / wait / strips launches)
     int opt_dist_p2p = 1;       // 0: NCCL transport even when the peer-memory link is up
     int opt_factor_keep_crs = 1;       // 0: a triangular factor gives up its natural-order CRS once its level-ordered copy exists
-    int opt_perm_mode = 0;             // the reference's PERM_MODE: 0 NONE, 1 C (multicolouring), read by the host's preprocessing
+    int opt_perm_mode = 0;             // the reference's PERM_MODE: 0 NONE, 1 C (multicolouring), 2 BFS, 3 RCM, 4 CM; read by the host's preprocessing
     int opt_precond_inner_iters = 0;   // PRECOND_INNER_ITERS of the reference (kernels.hpp:321): inner sweeps of -p 2st / s2st
     int opt_graph = 1;          // the host stack records iteration bodies as CUDA graphs (bis_context_get_option)
     int opt_spmv_variant = 0;

@@ -20,6 +20,14 @@
 #include <thrust/scan.h>
 #include <thrust/sequence.h>
 #include <thrust/sort.h>
+#include <thrust/binary_search.h>
+#include <thrust/count.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/transform_reduce.h>
+#include <thrust/functional.h>
+#include <thrust/reverse.h>
+
+#include <vector>
 
 namespace {
 
@@ -100,6 +108,68 @@ __global__ void vec_perm_kernel(int64_t n, const double *in, const int *perm, do
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[perm[i]];
 }
 
+
+// ---- breadth-first / (reverse) Cuthill-McKee orderings ------------------------------------------------------
+template <typename RP>
+__global__ void degree_kernel(int64_t n, const RP *rp, const int *col, int *deg) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        int d = 0;
+        for (RP k = rp[r]; k < rp[r + 1]; ++k) d += (col[k] != r && col[k] >= 0 && col[k] < n) ? 1 : 0;
+        deg[r] = d;
+    }
+}
+
+// one round of the level-synchronous search: rows of level `cur` give level cur + 1 to the rows they read that have none
+// yet (every writer stores the same number: the race is benign)
+template <typename RP>
+__global__ void bfs_round_kernel(int64_t n, const RP *rp, const int *col, int cur, int *level, int *found) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        if (level[r] != cur) continue;
+        bool any = false;
+        for (RP k = rp[r]; k < rp[r + 1]; ++k) {
+            const int c = col[k];
+            if (c < 0 || c >= n || c == r) continue;
+            if (level[c] < 0) {
+                level[c] = cur + 1;
+                any = true;
+            }
+        }
+        if (any) *reinterpret_cast<volatile int *>(found) = 1;
+    }
+}
+
+// Cuthill-McKee key of the rows ids[s..e) of level l: (position of the earliest-numbered row of level l - 1 the row
+// reads, degree); rows that read none of them (roots of further components) come by degree alone
+template <typename RP>
+__global__ void cm_key_kernel(int64_t s, int64_t e, int l, const RP *rp, const int *col, const int *level, const int *deg,
+                              const int *pos, const int *ids, unsigned long long *key, int64_t n) {
+    for (int64_t i = s + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = ids[i];
+        unsigned int parent = 0xFFFFFFFFu;
+        for (RP k = rp[v]; k < rp[v + 1]; ++k) {
+            const int c = col[k];
+            if (c < 0 || c >= n || c == v) continue;
+            if (level[c] == l - 1) parent = min(parent, (unsigned int)pos[c]);
+        }
+        const unsigned int d = min((unsigned int)deg[v], 0xFFFFFFu);
+        key[i - s] = ((unsigned long long)parent << 24) | d;
+    }
+}
+
+__global__ void cm_pos_kernel(int64_t s, int64_t e, const int *ids, int *pos) {
+    for (int64_t i = s + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) pos[ids[i]] = (int)i;
+}
+
+struct UnvisitedKey {
+    const int *level, *deg;
+    __device__ unsigned long long operator()(int v) const {
+        return level[v] >= 0 ? 0xFFFFFFFFFFFFFFFFull : (((unsigned long long)(unsigned int)deg[v] << 32) | (unsigned int)v);
+    }
+};
+struct IsVisited {
+    __device__ bool operator()(int l) const { return l >= 0; }
+};
+
 template <typename T> int dalloc(T **p, size_t count) {
     BIS_CUDA(bis_cuda_malloc(p, sizeof(T) * (count > 0 ? count : 1)));
     return 0;
@@ -179,6 +249,114 @@ extern "C" int bis_matrix_colouring_permutation(bis_context *c, const bis_matrix
     BIS_CUDA(cudaStreamSynchronize(st));
     cleanup();
     if (n_colours) *n_colours = colours;
+    return 0;
+}
+
+// generate_perm (smax_helpers.hpp:51-53) for the breadth-first family of PERM_MODEs.  mode 2: rows by (BFS level, row);
+// mode 4: Cuthill-McKee (inside a level by the position of the earliest-numbered row of the previous level the row
+// reads, then by degree, then by row), mode 3: that order reversed (RCM).  The numbers are those of the context option
+// "perm_mode" (1 is the multicolouring above).  The search starts at the row of smallest
+// degree (smallest index among equals) and restarts there among the rows not reached yet; neighbours are the columns
+// of a row (the matrices of this code are structurally symmetric; for others this is the search on the directed graph).
+// Deterministic: tests/test_perm_gpu.py restates it in numpy and compares the permutations entry for entry.
+extern "C" int bis_matrix_bfs_permutation(bis_context *c, const bis_matrix *A, int mode, int *d_perm, int *d_inv_perm, int *n_levels) {
+    BIS_REQUIRE(c && A && d_perm && d_inv_perm, "bis_matrix_bfs_permutation: null argument");
+    BIS_REQUIRE(mode >= 2 && mode <= 4, "bis_matrix_bfs_permutation: mode must be 2 (BFS), 3 (reverse Cuthill-McKee) or 4 (Cuthill-McKee)");
+    BIS_REQUIRE_CRS(A);
+    BIS_REQUIRE(!A->distributed && c->nranks == 1, "bis_matrix_bfs_permutation: single-GPU only");
+    BIS_CUDA(cudaSetDevice(c->device));
+    const int64_t n = A->n_rows;
+    if (n_levels) *n_levels = 0;
+    if (n == 0) return 0;
+    BIS_REQUIRE(n < ((int64_t)1 << 31), "bis_matrix_bfs_permutation: more than 2^31 rows");
+    cudaStream_t st = c->stream;
+    auto pol = thrust::cuda::par.on(st);
+    const int grid = bis_blocks_for(n, 256, c->sm_count * 16);
+    int *level = nullptr, *deg = nullptr, *d_found = nullptr, *pos = nullptr, *lkey = nullptr, *lstart = nullptr;
+    unsigned long long *key = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(level); cudaFree(deg); cudaFree(d_found); cudaFree(pos); cudaFree(lkey); cudaFree(lstart); cudaFree(key);
+    };
+    BIS_CHECK(dalloc(&level, (size_t)n));
+    BIS_CHECK(dalloc(&deg, (size_t)n));
+    BIS_CHECK(dalloc(&d_found, 1));
+    BIS_CHECK(dalloc(&lkey, (size_t)n));
+    const bool rp64 = A->rp_bytes == 8;
+    const int64_t *rp8 = static_cast<const int64_t *>(A->d_rp);
+    const int32_t *rp4 = static_cast<const int32_t *>(A->d_rp);
+    if (rp64) degree_kernel<int64_t><<<grid, 256, 0, st>>>(n, rp8, A->d_col, deg);
+    else degree_kernel<int32_t><<<grid, 256, 0, st>>>(n, rp4, A->d_col, deg);
+    c->launches++;
+    cudaMemsetAsync(level, 0xFF, sizeof(int) * (size_t)n, st);
+    int cur = 0;
+    int64_t visited = 0;
+    bool ok = true;
+    for (int comp = 0; visited < n && ok; ++comp) {
+        if (comp >= 65536) {     // one search (with host round trips) per component: not meant for graphs of fragments
+            ok = false;
+            break;
+        }
+        const unsigned long long rk = thrust::transform_reduce(pol, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>((int)n),
+                                                               UnvisitedKey{level, deg}, 0xFFFFFFFFFFFFFFFFull, thrust::minimum<unsigned long long>());
+        const int root = (int)(rk & 0xFFFFFFFFull);
+        cudaMemcpyAsync(level + root, &cur, sizeof(int), cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);      // `cur` is a host variable that changes below
+        for (;;) {
+            cudaMemsetAsync(d_found, 0, sizeof(int), st);
+            if (rp64) bfs_round_kernel<int64_t><<<grid, 256, 0, st>>>(n, rp8, A->d_col, cur, level, d_found);
+            else bfs_round_kernel<int32_t><<<grid, 256, 0, st>>>(n, rp4, A->d_col, cur, level, d_found);
+            c->launches++;
+            int found = 0;
+            cudaMemcpyAsync(&found, d_found, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) {
+                ok = false;
+                break;
+            }
+            ++cur;
+            if (!found) break;
+        }
+        visited = thrust::count_if(pol, thrust::device_pointer_cast(level), thrust::device_pointer_cast(level) + n, IsVisited());
+    }
+    if (!ok || cudaGetLastError() != cudaSuccess) {
+        cleanup();
+        bis_set_error("bis_matrix_bfs_permutation: the search did not finish (more than 65536 components, or a device error)");
+        return 3;
+    }
+    const int L = cur;      // levels 0 .. L-1 (a component's levels follow those of the one before it)
+    // rows by (level, row)
+    cudaMemcpyAsync(lkey, level, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st);
+    thrust::sequence(pol, thrust::device_pointer_cast(d_perm), thrust::device_pointer_cast(d_perm) + n);
+    thrust::stable_sort_by_key(pol, thrust::device_pointer_cast(lkey), thrust::device_pointer_cast(lkey) + n, thrust::device_pointer_cast(d_perm));
+    if (mode >= 3) {
+        BIS_CHECK(dalloc(&pos, (size_t)n));
+        BIS_CHECK(dalloc(&lstart, (size_t)L + 1));
+        BIS_CHECK(dalloc(&key, (size_t)n));
+        thrust::lower_bound(pol, thrust::device_pointer_cast(lkey), thrust::device_pointer_cast(lkey) + n, thrust::counting_iterator<int>(0),
+                            thrust::counting_iterator<int>(L + 1), thrust::device_pointer_cast(lstart));
+        std::vector<int> hs((size_t)L + 1);
+        cudaMemcpyAsync(hs.data(), lstart, sizeof(int) * ((size_t)L + 1), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        for (int l = 0; l < L; ++l) {
+            const int64_t s = hs[l], e = hs[l + 1];
+            if (e <= s) continue;
+            const int g = bis_blocks_for(e - s, 256, c->sm_count * 16);
+            if (e - s > 1) {
+                if (rp64) cm_key_kernel<int64_t><<<g, 256, 0, st>>>(s, e, l, rp8, A->d_col, level, deg, pos, d_perm, key, n);
+                else cm_key_kernel<int32_t><<<g, 256, 0, st>>>(s, e, l, rp4, A->d_col, level, deg, pos, d_perm, key, n);
+                c->launches++;
+                thrust::stable_sort_by_key(pol, thrust::device_pointer_cast(key), thrust::device_pointer_cast(key) + (e - s),
+                                           thrust::device_pointer_cast(d_perm) + s);
+            }
+            cm_pos_kernel<<<g, 256, 0, st>>>(s, e, d_perm, pos);
+            c->launches++;
+        }
+        if (mode == 3) thrust::reverse(pol, thrust::device_pointer_cast(d_perm), thrust::device_pointer_cast(d_perm) + n);
+    }
+    invert_perm_kernel<<<grid, 256, 0, st>>>(n, d_perm, d_inv_perm);
+    BIS_LAUNCH_CHECK(c);
+    BIS_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+    if (n_levels) *n_levels = L;
     return 0;
 }
 

@@ -50,7 +50,7 @@ inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
 
     // Permutation seam (preprocessing.hpp:52-65, permute_mat of utilities/smax_helpers.hpp:44-80): with the context
     // option "perm_mode" = 1 (the reference's PERM_MODE = C) A, b and x_0 are permuted by a multicolouring of A's
-    // graph before factoring -- a LABELLED mode: iteration counts differ from the unpermuted solve, and x_star stays
+    // graph (2: by BFS levels, 3: reverse Cuthill-McKee, 4: Cuthill-McKee) before factoring -- a LABELLED mode: iteration counts differ from the unpermuted solve, and x_star stays
     // in the permuted numbering as in the reference.  Like there, the solver's own copy of x_0 (init_structs, above)
     // is not touched.
     int perm_mode = 0;
@@ -58,7 +58,8 @@ inline void preprocessing(Args *cli_args, Solver *solver, Timers *timers,
         int *d_perm = nullptr, *d_inv = nullptr;
         BIS_OK(bis_index_alloc(dev, n, &d_perm));
         BIS_OK(bis_index_alloc(dev, n, &d_inv));
-        BIS_OK(bis_matrix_colouring_permutation(dev, solver->dA->handle, d_perm, d_inv, &solver->n_colours));
+        if (perm_mode == 1) BIS_OK(bis_matrix_colouring_permutation(dev, solver->dA->handle, d_perm, d_inv, &solver->n_colours));
+        else BIS_OK(bis_matrix_bfs_permutation(dev, solver->dA->handle, perm_mode, d_perm, d_inv, &solver->n_colours));   // 2 BFS, 3 RCM, 4 CM
         bis_matrix *pa = nullptr;
         BIS_OK(bis_matrix_permute_symmetric(dev, solver->dA->handle, d_perm, d_inv, &pa));
         solver->dA = adopt_device_matrix(dev, pa);

@@ -117,7 +117,7 @@ class Solver {
             if (slot.graph) bis_graph_free(dev, slot.graph);
         graph_slots.clear();
     }
-    int n_colours = 0;        // colours of the permutation (0: unpermuted)
+    int n_colours = 0;        // colours (perm_mode 1) or BFS levels (perm_mode 2..4) of the permutation (0: unpermuted)
     int exchange_count = 0;   // pointer exchanges so far: the key of the iteration's graph
 
     virtual void iterate(Timers *) = 0;

@@ -229,6 +229,11 @@ int bis_matrix_scale_symmetric(bis_context *ctx, bis_matrix *A,
  * Iteration counts differ from the unpermuted solve; x_star stays in the permuted numbering, as in the reference. */
 int bis_matrix_colouring_permutation(bis_context *ctx, const bis_matrix *A, int *perm /* [dev] int32[n], perm[new] = old */,
                                      int *inv_perm /* [dev] int32[n] */, int *n_colours /* [host] */);
+/* The breadth-first family of orderings (what SMAX's generate_perm offers besides colouring; smax_helpers.hpp:51-53):
+ * mode 2 = rows by (BFS level, row), 3 = reverse Cuthill-McKee, 4 = Cuthill-McKee; the search starts at the row of
+ * smallest degree and restarts there for every further component.  n_levels: BFS levels over all components. */
+int bis_matrix_bfs_permutation(bis_context *ctx, const bis_matrix *A, int mode, int *perm /* [dev] int32[n], perm[new] = old */,
+                               int *inv_perm /* [dev] int32[n] */, int *n_levels /* [host] */);
 int bis_matrix_permute_symmetric(bis_context *ctx, const bis_matrix *A, const int *perm /* [dev] */,
                                  const int *inv_perm /* [dev] */, bis_matrix **B /* out: P A P^T */);
 int bis_vector_permute(bis_context *ctx, double *out /* [dev] */, const double *in /* [dev] */,
