@@ -6,6 +6,8 @@
 // reference's.
 #pragma once
 
+#include <cstdlib>
+
 #include "common.hpp"
 #include "kernels.hpp"
 #include "sparse_matrix.hpp"
@@ -71,6 +73,10 @@ class Solver {
         int v = 0;
         if (dev && bis_context_get_option(dev, "graph", &v) == 0) graphs_on = v != 0;
         if (dev && bis_context_get_option(dev, "precond_inner_iters", &v) == 0) precond_inner_iters = v;
+        // RES_CHECK_LEN is a compile-time constant of the reference (CMakeLists.txt:232-243); BIS_RES_CHECK_LEN overrides it
+        // at run time (measurements: how much of an iteration is the read-back of the residual norm)
+        if (const char *e = std::getenv("BIS_RES_CHECK_LEN"))
+            if (std::atoi(e) > 0) residual_check_len = std::atoi(e);
     }
 
     // ---- CUDA graphs (new in the build) ------------------------------------------------------------
