@@ -537,7 +537,7 @@ int wave_build_t(bis_context *c, const bis_matrix *T) {
     if (c->opt_trsv_variant != 5) {
         // automatic choice (the level analysis has run): the wavefront pays ~4 us per PLANE (hand-over from plane to
         // plane: 2.3 us at four blocks per plane, 4.3 us at eight, with clusters of eight planes) plus ~0.5 us per
-        // step of one plane, the dataflow solve ~1.3 us per LEVEL (measured on B200, profiles/r02_wave_*, r03_wave_*).
+        // step of one plane, the dataflow solve ~1.3 us per LEVEL (measured on B200, profiles/r02_wave_*, r02b_wave_*).
         // 27-point factors have 4 levels per plane and win; 7-point factors have 1 and do not.
         const double est_wave = 4.0 * wf.nz + 0.5 * (wf.nx + 2.0 * wf.ny + 64.0 * (wf.W - 1));
         const double est_flow = 1.3 * T->lv.n_levels;

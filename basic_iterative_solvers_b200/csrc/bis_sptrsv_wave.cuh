@@ -434,7 +434,7 @@ __device__ __forceinline__ void solve(const Args &a, State &st, const int Sw) {
     // b and D are loaded straight into registers two of this warp's steps (four steps) ahead.  They used to come
     // through cp.async rings, eight steps ahead -- but a thread's copy groups complete in order, so prepare's wait for
     // its two-step-old request of previous-plane values also waited for the b / D copies committed in between, and under
-    // load those took longer than that (prepare 800 -> 1400 cycles in mid-sweep planes, profiles/r03_wave_*).
+    // load those took longer than that (prepare 800 -> 1400 cycles in mid-sweep planes, profiles/r02b_wave_*).
     {
         const bool act2 = (unsigned)(xp + PH) < (unsigned)st.nx_eff;
         const double d2 = act2 ? st.dd_n : 1.0;
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(MAX_WARPS * PH * 32 + 32, 1) wave_kernel(Args 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // The CTA's last warp computes nothing: its lane w re-fills the record stages of block w (see refill).  With the
     // bulk copies issued by lane 0 of the block's solving warp -- a proxy fence, an mbarrier transaction, the copy and an
-    // L2 prefetch, ~500 cycles of one lane -- every second solve started that much later (profiles/r03_wave_*).
+    // L2 prefetch, ~500 cycles of one lane -- every second solve started that much later (profiles/r02b_wave_*).
     const bool dma = warp >= a.g.W * PH;
     const int wl = dma ? 0 : warp / PH;                  // 32-line block of the plane
     const int ph = warp % PH;                            // this warp solves the block's steps with ls % PH == ph

@@ -100,7 +100,11 @@ int bis_flush_l2(bis_context *ctx);
 /* Tuning knobs (all have defaults): key = "spmv_variant" (0 auto, 1 vector
  * CRS, 2 TMA-staged tiles + gathers, 3 windowed x), "spmv_lanes" (0 auto,
  * 2..32), "trsv_variant" (0 auto, 1 launch per level, 2 level counters,
- * 3 dataflow, 4 chains, 5 stencil wavefront), "graph" (0/1: the host stack
+ * 3 dataflow, 4 chains, 5 stencil wavefront), "wave_cluster" (stencil
+ * wavefront: planes per thread-block cluster, 1 / 2 / 4 / 8 (default) / 16;
+ * 1 = every plane-to-plane hand-over through L2), "perm_mode" (0 none,
+ * 1 multicolouring, 2 BFS levels, 3 reverse Cuthill-McKee, 4 Cuthill-McKee:
+ * read by the host's preprocessing), "graph" (0/1: the host stack
  * replays the iteration body as a CUDA graph; default 1 on one GPU),
  * "factor_keep_crs" (default 1; 0: bis_matrix_split_triangular / bis_matrix_ilu0
  * return factors that keep only their level-ordered copy -- bis_sptrsv /
