@@ -481,6 +481,40 @@ def main():
                              "1-thread and 8-thread runs are reported beside the device's distance for scale",
             }
 
+    # ---- the triangular-solve configuration of BASELINE (configs[2]: HPCG-256 -cg -p sgs), one GPU ------------------
+    sgs = None
+    if world == 1 and rank == 0 and not args.weak and n > 256:
+        ctx.set_option("graph", 0)      # per-launch event pairs need the launches issued one by one
+        s3 = host.BenchSession(ctx, "HPCG-256", "cg", "sgs")
+        s3.prepare(W)
+        ctx.profile_enable(True)
+        s3.run(K)
+        trsv_ms, trsv_cnt = ctx.profile_read("sptrsv")
+        ctx.profile_enable(False)
+        ctx.set_option("graph", 1)
+        s3.close()
+        s3 = host.BenchSession(ctx, "HPCG-256", "cg", "sgs")
+        s3.prepare(W)
+        r3 = s3.run(K)
+        h3 = s3.history(W + K + 1)
+        s3.close()
+        nnz_tri = (449455096 - 256 ** 3) // 2
+        sweep_bytes = 12 * nnz_tri + 4 * (256 ** 3 + 1) + 24 * 256 ** 3
+        sgs = {"workload": "HPCG-256 -cg -p sgs (BASELINE configs[2])", "gpu_ms_per_iter": r3["device_ms"] / K,
+               "sptrsv_ms_per_sweep": trsv_ms / trsv_cnt if trsv_cnt else None, "sweeps_timed": int(trsv_cnt),
+               "sptrsv_kernel": "wave_kernel (stencil wavefront, thread-block clusters of 8 planes)",
+               "sptrsv_algorithmic_gbs": sweep_bytes / (trsv_ms / trsv_cnt) / 1e6 if trsv_cnt else None,
+               "note": "the sweeps are a dependency chain of 7n-6 levels: latency-bound by nature, rated in ms per sweep"}
+        gpath = os.path.join(ROOT, "tests", "golden", "large_hpcg256_cg_sgs.npz")
+        if os.path.exists(gpath):
+            g = np.load(gpath)
+            k = min(h3.size, g["history"].size, g["history8"].size)
+            r0 = float(g["history"][0])
+            sgs["parity_vs_reference"] = {
+                "golden": "tests/golden/large_hpcg256_cg_sgs.npz (reference, 1 and 8 OpenMP threads)", "n_residuals": int(k),
+                "max_abs_diff_over_r0": float(np.max(np.abs(h3[:k] - g["history"][:k])) / r0),
+                "reference_1_vs_8_threads_over_r0": float(np.max(np.abs(g["history8"][:k] - g["history"][:k])) / r0)}
+
     out = {
         "metric": METRIC, "value": ms_iter, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_iter, "higher_is_better": False, "scaling": scaling, "vs_baseline": None,
@@ -521,6 +555,8 @@ def main():
                                     "the other ranks' slab sums, and CTA 0's producer for the halo flags (max over ranks)"}
     if same is not None:
         out["same_config"] = same
+    if sgs is not None:
+        out["also"]["hpcg256_cg_sgs"] = sgs
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
             n_s = args.cpu_sample or pick_cpu_sample(n)

@@ -42,6 +42,10 @@ with capi.Context(0) as ctx:
         if args.only and tag not in args.only.split(","):
             continue
         out = {"config": tag, "matrix": name, "method": method, "precond": pre}
+        # per-launch event pairs need the launches issued one by one: graph replay off for this pass (with it on, the
+        # iterations whose graph had been captured during the warm-up replayed without brackets and the per-family
+        # sums of the first two rounds' tables came out at half their value for the methods with two graphs)
+        ctx.set_option("graph", 0)
         sess = host.BenchSession(ctx, name, method, pre, rl)
         t0 = time.time()
         info = sess.prepare(W)
@@ -50,6 +54,7 @@ with capi.Context(0) as ctx:
         r = sess.run(K)
         fam = {f: ctx.profile_read(f) for f in ("spmv", "sptrsv", "vector")}
         ctx.profile_enable(False)
+        ctx.set_option("graph", 1)
         sess.close()
         # the number that counts: profiling off, iteration bodies replayed as CUDA graphs
         sess = host.BenchSession(ctx, name, method, pre, rl)
