@@ -260,6 +260,11 @@ class Context:
     def set_option(self, key: str, value: int):
         self.call("bis_context_set_option", key.encode(), int(value))
 
+    def get_option(self, key: str) -> int:
+        v = cint(0)
+        self.call("bis_context_get_option", key.encode(), C.byref(v))
+        return int(v.value)
+
     # vectors -----------------------------------------------------------------
     def alloc(self, n: int) -> int:
         p = c_dev()

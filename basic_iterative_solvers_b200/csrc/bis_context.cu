@@ -85,6 +85,7 @@ static int context_init(bis_context *c, int device) {
     if (const char *e = getenv("BIS_GRAPH")) c->opt_graph = atoi(e);
     if (const char *e = getenv("BIS_WIN_ROWS")) c->opt_win_rows = atoi(e);
     if (const char *e = getenv("BIS_WAVE_CLUSTER")) c->opt_wave_cluster = atoi(e);
+    if (const char *e = getenv("BIS_SPMV_VDICT")) c->opt_spmv_vdict = atoi(e) ? 1 : 0;
     if (const char *e = getenv("BIS_WAVE_BACKOFF_NS")) c->opt_wave_backoff_ns = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("BIS_PRECOND_INNER_ITERS")) c->opt_precond_inner_iters = atoi(e);
     if (const char *e = getenv("BIS_PERM_MODE"))     // NONE / C (colouring) / BFS / RCM / CM, or the option's number
@@ -417,6 +418,8 @@ extern "C" int bis_context_get_option(bis_context *c, const char *key, int *valu
     if (k == "graph") *value = (c->opt_graph && c->nranks == 1) ? 1 : 0;
     else if (k == "precond_inner_iters") *value = c->opt_precond_inner_iters;
     else if (k == "perm_mode") *value = c->opt_perm_mode;
+    else if (k == "spmv_vdict") *value = c->opt_spmv_vdict;
+    else if (k == "spmv_value_bytes") *value = c->last_spmv_value_bytes;   // read-only: what the last windowed SpMV streamed per nonzero
     else if (k == "factor_keep_crs") *value = c->opt_factor_keep_crs;
     else if (k == "spmv_variant") *value = c->opt_spmv_variant;
     else if (k == "trsv_variant") *value = c->opt_trsv_variant;
@@ -481,6 +484,7 @@ extern "C" int bis_context_set_option(bis_context *c, const char *key, int value
     else if (k == "spmv_mult") c->opt_spmv_mult = value;
     else if (k == "win_rows") c->opt_win_rows = value;
     else if (k == "wave_cluster") c->opt_wave_cluster = value;
+    else if (k == "spmv_vdict") c->opt_spmv_vdict = value ? 1 : 0;
     else if (k == "wave_backoff_ns") c->opt_wave_backoff_ns = value < 0 ? 0 : value;
 #ifdef BIS_PERF_DEBUG
     else if (k == "wave_debug") c->opt_wave_debug = value;

@@ -204,6 +204,9 @@ struct bis_context {
     int opt_trsv_debug = 0;     // dump per-row timestamps of each solve to $BIS_TRSV_DEBUG_FILE
     int opt_spmv_rows = 0;      // TMA variant: rows per tile (0 auto)
     int opt_spmv_stages = 0;    // TMA variant: max stages (0 auto)
+    int opt_spmv_vdict = 0;     // windowed SpMV: 1 = stream 1-byte value indices when the matrix has <= 256 distinct values (lossless; off by
+                                // default: 12 % faster at HPCG-512, + 1 byte per nonzero of memory)
+    int last_spmv_value_bytes = 8;   // bytes per nonzero the last windowed SpMV streamed for the values (8 or 1)
     int opt_wave_cluster = 8;   // stencil wavefront: planes per thread-block cluster (1: no clusters, every hand-over through L2)
     int opt_wave_backoff_ns = 0;      // ... nanoseconds a plane fed through L2 falls back after it had to poll (clusters only)
     int wave_cluster_used = 0;  // ... what the last solve ran with
@@ -320,6 +323,13 @@ struct WinFormat {
     unsigned short *d_seg_off = nullptr;
     int *d_nseg = nullptr;
     unsigned short *d_lidx = nullptr;
+    // value dictionary (lossless): when the matrix holds at most 256 distinct values (constant-coefficient stencils:
+    // HPCG has two), the tiles stream a 1-byte index per nonzero instead of the 8-byte value and the kernel looks the
+    // value up in a 2 KB table in shared memory -- the bits of every product are those of the CRS value
+    int dict_state = 0;            // 0 not tried, 1 usable, -1 more than 256 distinct values (or switched off)
+    int n_dict = 0;
+    unsigned char *d_vidx = nullptr;   // [nnz + 32]
+    double *d_vdict = nullptr;         // [256], ascending bit patterns
     // processing order of the tiles (bis_spmv.cu: win_build_order)
     int *d_order = nullptr;        // [n_tiles]; bit 31: the tile reads ghosts
     int n_slab = 1;                // local virtual slabs the order is cut into
@@ -376,6 +386,8 @@ int bis_matrix_finalize_distributed(bis_context *ctx, bis_matrix *A,
 int bis_build_levels_device(bis_context *ctx, bis_matrix *T);
 // the level sets of a factor that has been served by the stencil wavefront so far (bis_factor.cu)
 int bis_ensure_levels(bis_context *ctx, const bis_matrix *T);
+// the values of A changed in place (bis_matrix_scale_symmetric): the SpMV's value dictionary is rebuilt on next use (bis_spmv.cu)
+void bis_win_values_changed(const bis_matrix *A);
 // tries to build the stencil-wavefront records of a triangular factor (bis_sptrsv.cu); wave.state tells
 int bis_wave_build(bis_context *ctx, const bis_matrix *T);
 int bis_matrix_stats(bis_context *ctx, bis_matrix *A);

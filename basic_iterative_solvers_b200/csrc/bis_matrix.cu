@@ -56,6 +56,8 @@ void free_matrix_storage(bis_matrix *A) {
     cudaFree(A->win.d_nseg);
     cudaFree(A->win.d_lidx);
     cudaFree(A->win.d_order);
+    cudaFree(A->win.d_vidx);
+    cudaFree(A->win.d_vdict);
 }
 
 template <typename RP>
@@ -725,5 +727,6 @@ extern "C" int bis_matrix_scale_symmetric(bis_context *c, bis_matrix *A, double 
     else
         scale_apply_kernel<int32_t><<<blocks, 256, 0, c->stream>>>(n, static_cast<const int32_t *>(A->d_rp), A->d_col, A->d_val, D_scale, A->halo.cur_ghost, A->n_cols);
     BIS_LAUNCH_CHECK(c);
+    bis_win_values_changed(A);
     return 0;
 }

@@ -22,6 +22,9 @@
 #include "bis_device.cuh"
 #include "bis_spmv_tma.cuh"
 #include "bis_spmv_win.cuh"
+#include <algorithm>
+#include <cstring>
+#include <vector>
 
 namespace {
 
@@ -322,9 +325,149 @@ namespace {
 int win_free(bis_matrix *A) {
     WinFormat &w = A->win;
     cudaFree(w.d_seg_start); cudaFree(w.d_seg_len); cudaFree(w.d_seg_off); cudaFree(w.d_nseg); cudaFree(w.d_lidx);
-    cudaFree(w.d_order);
+    cudaFree(w.d_order); cudaFree(w.d_vidx); cudaFree(w.d_vdict);
     w.d_seg_start = nullptr; w.d_seg_len = nullptr; w.d_seg_off = nullptr; w.d_nseg = nullptr; w.d_lidx = nullptr;
-    w.d_order = nullptr;
+    w.d_order = nullptr; w.d_vidx = nullptr; w.d_vdict = nullptr;
+    w.dict_state = 0; w.n_dict = 0;
+    return 0;
+}
+
+// ---- value dictionary (WinFormat::d_vidx / d_vdict) ------------------------------------------------
+// Pass 1 collects the distinct bit patterns of val[] (a block keeps the ones it has met in shared memory, so the global
+// table sees each pattern once per block, not once per nonzero) and gives up beyond 256; the host sorts them; pass 2
+// writes the index of every value.  A matrix with many distinct values leaves pass 1 after a few thousand nonzeros.
+constexpr int VD_SLOTS = 1024;                         // global table (power of two, > 2 * 256)
+constexpr int VD_LOCAL = 512;                          // per-block table
+constexpr unsigned long long VD_EMPTY = ~0ull;         // a NaN pattern: a matrix that holds it gets no dictionary
+
+__device__ __forceinline__ unsigned int vd_hash(unsigned long long v) {
+    v ^= v >> 33;
+    v *= 0xff51afd7ed558ccdull;
+    v ^= v >> 29;
+    return (unsigned int)v;
+}
+
+__global__ void __launch_bounds__(256) vdict_collect_kernel(int64_t nnz, const double *val, unsigned long long *slots, int *state) {
+    __shared__ unsigned long long s_slots[VD_LOCAL];
+    __shared__ int s_count;
+    for (int i = threadIdx.x; i < VD_LOCAL; i += blockDim.x) s_slots[i] = VD_EMPTY;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    int it = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x, ++it) {
+        if (*reinterpret_cast<volatile int *>(&s_count) > 256) return;
+        if ((it & 63) == 0 && *reinterpret_cast<volatile int *>(state + 1)) return;    // somebody gave up (looked at rarely: one address)
+        const unsigned long long v = (unsigned long long)__double_as_longlong(val[i]);
+        if (v == VD_EMPTY) {
+            atomicExch(state + 1, 1);
+            return;
+        }
+        unsigned int h = vd_hash(v) & (VD_LOCAL - 1);
+        bool fresh = false;
+        for (int probe = 0; probe < VD_LOCAL; ++probe) {
+            const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&s_slots[h]);
+            if (cur == v) break;
+            if (cur == VD_EMPTY) {
+                const unsigned long long old = atomicCAS(&s_slots[h], VD_EMPTY, v);
+                if (old == VD_EMPTY) {
+                    fresh = true;
+                    atomicAdd(&s_count, 1);
+                    break;
+                }
+                if (old == v) break;
+            }
+            h = (h + 1) & (VD_LOCAL - 1);
+        }
+        if (!fresh) continue;
+        // new to this block: into the global table
+        unsigned int g = vd_hash(v) & (VD_SLOTS - 1);
+        for (int probe = 0; probe < VD_SLOTS; ++probe) {
+            const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&slots[g]);
+            if (cur == v) break;
+            if (cur == VD_EMPTY) {
+                const unsigned long long old = atomicCAS(&slots[g], VD_EMPTY, v);
+                if (old == VD_EMPTY) {
+                    if (atomicAdd(state, 1) + 1 > 256) atomicExch(state + 1, 1);
+                    break;
+                }
+                if (old == v) break;
+            }
+            g = (g + 1) & (VD_SLOTS - 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vdict_index_kernel(int64_t nnz, const double *val, const double *dict, int n_dict,
+                                                          unsigned char *vidx, int *missing) {
+    __shared__ unsigned long long s_d[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_d[i] = i < n_dict ? (unsigned long long)__double_as_longlong(dict[i]) : VD_EMPTY;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = (unsigned long long)__double_as_longlong(val[i]);
+        int lo = 0, hi = n_dict - 1;
+        while (lo < hi) {           // first entry >= v (ascending bit patterns)
+            const int mid = (lo + hi) >> 1;
+            if (s_d[mid] < v) lo = mid + 1;
+            else hi = mid;
+        }
+        if (s_d[lo] != v) atomicExch(missing, 1);
+        vidx[i] = (unsigned char)lo;
+    }
+}
+
+// Builds the dictionary of A's values when there are at most 256 distinct ones (dict_state 1), else dict_state -1.
+int win_build_dict(bis_context *c, const bis_matrix *A) {
+    WinFormat &w = A->win;
+    if (w.dict_state != 0 || !c->opt_spmv_vdict) return 0;     // (switched on later, it is built then)
+    w.dict_state = -1;
+    if (A->nnz == 0 || !A->d_val) return 0;
+    unsigned long long *d_slots = nullptr;
+    int *d_state = nullptr;
+    BIS_CUDA(bis_cuda_malloc(&d_slots, sizeof(unsigned long long) * VD_SLOTS));
+    BIS_CUDA(bis_cuda_malloc(&d_state, 3 * sizeof(int)));
+    BIS_CUDA(cudaMemsetAsync(d_slots, 0xFF, sizeof(unsigned long long) * VD_SLOTS, c->stream));
+    BIS_CUDA(cudaMemsetAsync(d_state, 0, 3 * sizeof(int), c->stream));
+    const int blocks = bis_blocks_for(A->nnz, 256 * 16, c->sm_count * 8);
+    vdict_collect_kernel<<<blocks, 256, 0, c->stream>>>(A->nnz, A->d_val, d_slots, d_state);
+    BIS_LAUNCH_CHECK(c);
+    std::vector<unsigned long long> slots(VD_SLOTS);
+    int state[3] = {0, 0, 0};
+    BIS_CUDA(cudaMemcpyAsync(slots.data(), d_slots, sizeof(unsigned long long) * VD_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaMemcpyAsync(state, d_state, sizeof state, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_slots);
+    std::vector<unsigned long long> pats;
+    for (unsigned long long v : slots)
+        if (v != VD_EMPTY) pats.push_back(v);
+    if (state[1] != 0 || pats.empty() || pats.size() > 256) {
+        cudaFree(d_state);
+        return 0;
+    }
+    std::sort(pats.begin(), pats.end());
+    double dict[256] = {};
+    for (size_t i = 0; i < pats.size(); ++i) memcpy(&dict[i], &pats[i], sizeof(double));
+    if (cudaMalloc(&w.d_vidx, (size_t)A->nnz + 32) != cudaSuccess) {     // no room for the index array: the values are streamed
+        cudaGetLastError();
+        w.d_vidx = nullptr;
+        cudaFree(d_state);
+        return 0;
+    }
+    BIS_CUDA(bis_cuda_malloc(&w.d_vdict, sizeof(double) * 256));
+    BIS_CUDA(cudaMemcpyAsync(w.d_vdict, dict, sizeof dict, cudaMemcpyHostToDevice, c->stream));
+    BIS_CUDA(cudaMemsetAsync(w.d_vidx + A->nnz, 0, 32, c->stream));
+    vdict_index_kernel<<<blocks, 256, 0, c->stream>>>(A->nnz, A->d_val, w.d_vdict, (int)pats.size(), w.d_vidx, d_state + 2);
+    BIS_LAUNCH_CHECK(c);
+    BIS_CUDA(cudaMemcpyAsync(state, d_state, sizeof state, cudaMemcpyDeviceToHost, c->stream));
+    BIS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_state);
+    if (state[2] != 0) {        // cannot happen unless val[] changed between the two passes
+        cudaFree(w.d_vidx); cudaFree(w.d_vdict);
+        w.d_vidx = nullptr; w.d_vdict = nullptr;
+        return 0;
+    }
+    w.n_dict = (int)pats.size();
+    w.dict_state = 1;
     return 0;
 }
 
@@ -472,7 +615,7 @@ int win_build(bis_context *c, const bis_matrix *A) {
     BIS_CUDA(bis_cuda_malloc(&w.d_seg_len, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
     BIS_CUDA(bis_cuda_malloc(&w.d_seg_off, sizeof(unsigned short) * (size_t)n_tiles * WIN_MAXSEG));
     BIS_CUDA(bis_cuda_malloc(&w.d_nseg, sizeof(int) * (size_t)n_tiles));
-    BIS_CUDA(bis_cuda_malloc(&w.d_lidx, sizeof(unsigned short) * ((size_t)A->nnz + 8)));
+    BIS_CUDA(bis_cuda_malloc(&w.d_lidx, sizeof(unsigned short) * ((size_t)A->nnz + 32)));
     WinBuildArgs a;
     a.rp = A->d_rp; a.col = A->d_col; a.n_rows = A->n_rows; a.n_owned = A->n_cols; a.R = R; a.sort_cap = sort_cap;
     a.seg_start = w.d_seg_start; a.seg_len = w.d_seg_len; a.seg_off = w.d_seg_off; a.nseg = w.d_nseg;
@@ -495,7 +638,7 @@ int win_build(bis_context *c, const bis_matrix *A) {
         return 0;
     }
     w.R = R;
-    w.cap = (R * A->max_row + 16 + 7) & ~7;
+    w.cap = (R * A->max_row + 32 + 15) & ~15;      // a tile's nonzeros + the alignment padding of its copies (up to 15 either side)
     w.xcap = (status[0] + 1) & ~1;
     if (w.xcap < 2) w.xcap = 2;
     w.n_tiles = n_tiles;
@@ -509,13 +652,15 @@ int win_build(bis_context *c, const bis_matrix *A) {
 
 struct WinPlan {
     int nstage;
+    int ngroups;
     int stage_bytes;
     size_t smem_bytes;
 };
 
 bool win_plan(const bis_context *c, const bis_matrix *A, WinPlan *p) {
     const WinFormat &w = A->win;
-    size_t stage = (size_t)w.cap * 8 + (size_t)w.xcap * 8 + (size_t)(w.R + 4) * 8 + (size_t)w.cap * 2;
+    const bool dict = w.dict_state == 1 && c->opt_spmv_vdict;
+    size_t stage = (size_t)w.cap * (dict ? 1 : 8) + (size_t)w.xcap * 8 + (size_t)(w.R + 4) * 8 + (size_t)w.cap * 2;
     stage = (stage + 127) & ~(size_t)127;
     const size_t budget = (size_t)(c->opt_spmv_smem_kb > 0 ? c->opt_spmv_smem_kb : 110) << 10;
     int nstage = (int)((budget - 128) / stage);
@@ -528,9 +673,18 @@ bool win_plan(const bis_context *c, const bis_matrix *A, WinPlan *p) {
     }
     // CTA size: at most 320 threads (two or more CTAs per SM) unless the tile itself is 256 rows long
     const int max_threads = w.R > 128 ? WIN_MAX_THREADS : 320;
-    while (nstage > 2 && w.R * nstage + 32 > max_threads) --nstage;
-    if (w.R * nstage + 32 > max_threads) return false;
+    // one consumer group per stage ...
+    int ngroups = nstage;
+    while (ngroups > 2 && w.R * ngroups + 32 > max_threads) --ngroups;
+    if (w.R * ngroups + 32 > max_threads) return false;
+    // ... unless the stages are small (value dictionary: a 128-row tile of a 27-point matrix is 21 KB instead of 44): then
+    // the two groups of a CTA are fed by a deeper pipeline.  With two stages the kernel was bound by the latency of a
+    // tile (two tiles in flight per CTA whatever their size: 5.5 ms at HPCG-512); the groups, and with them the sets of
+    // tiles a thread accumulates over, are those of the value-streaming launch, so fused dot products keep their bits.
+    if (dict && nstage > ngroups) nstage -= nstage % ngroups;
+    else nstage = ngroups;
     p->nstage = nstage;
+    p->ngroups = ngroups;
     p->stage_bytes = (int)stage;
     p->smem_bytes = 128 + stage * nstage;
     return true;
@@ -543,7 +697,7 @@ int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const doub
     auto kern = spmv_win_kernel<RP, Epi, FUSED>;
     BIS_CHECK(bis_ensure_dynamic_smem(c, reinterpret_cast<const void *>(kern), p.smem_bytes));
     const WinFormat &w = A->win;
-    const int threads = w.R * p.nstage + 32;          // one consumer group per stage + the producer warp
+    const int threads = w.R * p.ngroups + 32;         // the consumer groups + the producer warp
     int occ = 1;
     BIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, p.smem_bytes));
     if (occ < 1) occ = 1;
@@ -562,7 +716,14 @@ int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const doub
     for (int i = 0; i <= BIS_NSLAB; ++i) in.ord.pos0[i] = w.pos0[i];
     in.ord.G = G;
     in.ord.part_stride = (int)grid;
-    in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.stage_bytes = p.stage_bytes;
+    in.R = w.R; in.cap = w.cap; in.xcap = w.xcap; in.nstage = p.nstage; in.ngroups = p.ngroups; in.stage_bytes = p.stage_bytes;
+    const bool dict = w.dict_state == 1 && c->opt_spmv_vdict;
+    in.vidx = dict ? w.d_vidx : nullptr;
+    in.vdict = dict ? w.d_vdict : nullptr;
+    in.n_dict = dict ? w.n_dict : 0;
+    in.val_region = dict ? w.cap : w.cap * 8;
+    in.amask = dict ? 15 : 7;
+    c->last_spmv_value_bytes = dict ? 1 : 8;
 #ifdef BIS_PERF_DEBUG
     in.debug = c->opt_spmv_debug;
 #endif
@@ -600,7 +761,19 @@ int launch_win(bis_context *c, const bis_matrix *A, const WinPlan &p, const doub
 
 int bis_spmv_prepare(bis_context *c, const bis_matrix *A) {
     if (c->opt_spmv_variant != 0 && c->opt_spmv_variant != 3) return 0;
-    return win_build(c, A);
+    BIS_CHECK(win_build(c, A));
+    if (A->win.state == 1) BIS_CHECK(win_build_dict(c, A));
+    return 0;
+}
+
+void bis_win_values_changed(const bis_matrix *A) {
+    WinFormat &w = A->win;
+    cudaFree(w.d_vidx);
+    cudaFree(w.d_vdict);
+    w.d_vidx = nullptr;
+    w.d_vdict = nullptr;
+    w.n_dict = 0;
+    w.dict_state = 0;       // looked at again by the next SpMV
 }
 
 // Shared driver: halo exchange (distributed) overlapped with the interior rows.
@@ -618,6 +791,7 @@ static int spmv_driver(bis_context *c, const bis_matrix *A, const double *x, con
     WinPlan wplan;
     if ((c->opt_spmv_variant == 0 || c->opt_spmv_variant == 3) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         BIS_CHECK(win_build(c, A));
+        if (A->win.state == 1) BIS_CHECK(win_build_dict(c, A));
         use_win = A->win.state == 1 && win_plan(c, A, &wplan);
     }
     BIS_REQUIRE(use_win || c->opt_spmv_variant != 3,

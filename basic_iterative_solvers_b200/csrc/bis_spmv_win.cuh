@@ -303,10 +303,18 @@ struct SpmvWinIn {
     const double *ghost;
     int64_t n_rows;
     WinOrderArgs ord;
+    // value dictionary (WinFormat): when vidx != nullptr a stage receives the 1-byte indices vidx[s..e) instead of
+    // val[s..e) and the row walk reads vdict[index] (a copy of the <= 256 entry table in shared memory)
+    const unsigned char *vidx;
+    const double *vdict;
+    int n_dict;
+    int val_region;               // bytes of a stage's value part: cap * 8, or cap with the dictionary
+    int amask;                    // copies start at element (rp[r0] & ~amask): 7, or 15 with the dictionary (16-byte units)
     int R;                        // rows per tile == consumer threads
-    int cap;                      // nonzeros per stage (multiple of 8)
+    int cap;                      // nonzeros per stage (multiple of 16)
     int xcap;                     // window doubles per stage (even)
-    int nstage;
+    int nstage;                   // stages of the pipeline (tile s lands in stage s % nstage)
+    int ngroups;                  // consumer groups (tile s is computed by group s % ngroups); nstage is a multiple of it
     int stage_bytes;
 #ifdef BIS_PERF_DEBUG
     int debug;                    // perf experiments only (results invalid): 1 = consumers skip the row walk, 2 = no x-window copies
@@ -318,7 +326,7 @@ struct SpmvWinIn {
 #define BIS_WIN_DEBUG(in, bit) 0
 #endif
 
-// stage layout: [val cap*8][xwin xcap*8][rp (R+4)*8][lidx cap*2], every part 16-byte aligned
+// stage layout: [val cap*8 | vidx cap][xwin xcap*8][rp (R+4)*8][lidx cap*2], every part 16-byte aligned
 constexpr int WIN_MAX_THREADS = 544;   // consumer groups (R x nstage <= 512) + the producer warp
 
 // This CTA's sequence of tiles: the s-th one is position pos0[i] + b + (s - cum[i]) * G of slab i.
@@ -362,7 +370,7 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
     // starts the moment its copies land -- nstage tiles can be in the compute phase at once
     const int n_cons_warps = R >> 5;                  // per group
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool producer = warp == n_cons_warps * in.nstage;       // the last warp
+    const bool producer = warp == n_cons_warps * in.ngroups;       // the last warp
     const int group = warp / n_cons_warps;
     const int tid_g = (int)threadIdx.x - group * R;   // thread index inside its group
     WinSeq seq;
@@ -373,6 +381,9 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
 #pragma unroll
     for (int q = 0; q < (Epi::NRED > 0 ? Epi::NRED : 1); ++q) acc[q] = 0.0;
 
+    __shared__ double s_dict[256];
+    if (in.vidx)
+        for (int i = threadIdx.x; i < in.n_dict; i += blockDim.x) s_dict[i] = in.vdict[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < in.nstage; ++s) {
             tma::mbar_init(&full[s], 1);
@@ -437,7 +448,7 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
             unsigned short len, off; // window length / offset    (lanes 3..)
             int tile;                // raw order entry
         };
-        const uint32_t off_xw = (uint32_t)in.cap * 8u;
+        const uint32_t off_xw = (uint32_t)in.val_region;
         const uint32_t off_rp = off_xw + (uint32_t)in.xcap * 8u;
         const uint32_t off_li = off_rp + (uint32_t)(R + 4) * 8u;
         auto tile_rows = [&](int tile, int64_t &r0, int64_t &r1) {
@@ -502,11 +513,17 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
             const void *src = nullptr;
             uint32_t bytes = 0, dst = 0;
             if (lane < 2) {
-                const int64_t s_al = (int64_t)d.a & ~(int64_t)7;
-                const uint32_t n_el = (uint32_t)((((int64_t)d.b + 7) & ~(int64_t)7) - s_al);
+                const int64_t am = in.amask;
+                const int64_t s_al = (int64_t)d.a & ~am;
+                const uint32_t n_el = (uint32_t)((((int64_t)d.b + am) & ~am) - s_al);
                 if (lane == 0) {
-                    src = in.val + s_al;
-                    bytes = n_el * 8u;
+                    if (in.vidx) {
+                        src = in.vidx + s_al;
+                        bytes = n_el;
+                    } else {
+                        src = in.val + s_al;
+                        bytes = n_el * 8u;
+                    }
                 } else {
                     src = in.lidx + s_al;
                     bytes = n_el * 2u;
@@ -559,12 +576,12 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
         // took the slab's first tile counts as group 0, so the sum is independent of where in this CTA's
         // sequence the slab starts), two parities so that one barrier per slab suffices
         __shared__ double s_wsum[2][Epi::NRED > 0 ? Epi::NRED : 1][32];
-        const int n_cons_threads = R * in.nstage;
+        const int n_cons_threads = R * in.ngroups;
         auto close_slab = [&](int slab) {
             if constexpr (Epi::NRED > 0) {
                 const int par = slab & 1;
-                const int g0 = seq.cum[slab] % in.nstage;                    // group that got the slab's first tile
-                const int lgroup = (group - g0 + in.nstage) % in.nstage;
+                const int g0 = seq.cum[slab] % in.ngroups;                    // group that got the slab's first tile
+                const int lgroup = (group - g0 + in.ngroups) % in.ngroups;
                 const int lwarp = lgroup * n_cons_warps + (warp - group * n_cons_warps);
 #pragma unroll
                 for (int q = 0; q < Epi::NRED; ++q) {
@@ -574,7 +591,7 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
                 }
                 asm volatile("bar.sync 1, %0;" ::"r"(n_cons_threads) : "memory");
                 if (warp == 0) {
-                    const int nw = n_cons_warps * in.nstage;
+                    const int nw = n_cons_warps * in.ngroups;
 #pragma unroll
                     for (int q = 0; q < Epi::NRED; ++q) {
                         double v = lane < nw ? s_wsum[par][q][lane] : 0.0;
@@ -586,19 +603,20 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
             }
         };
         int raw_next = group < my_tiles ? in.ord.order[seq.pos(in.ord, (int)blockIdx.x, group)] : 0;
-        for (int s = group; s < my_tiles; s += in.nstage) {
-            const int st = group;
+        for (int s = group; s < my_tiles; s += in.ngroups) {
+            const int st = s % in.nstage;
             const int tile = raw_next & ~WIN_ORDER_GHOST;
             if constexpr (Epi::NRED > 0) {
                 const int slab = seq.slab_of(s);
                 while (cur_slab < slab) close_slab(cur_slab++);
             }
             // the next tile's id is requested a whole tile ahead
-            if (s + in.nstage < my_tiles) raw_next = in.ord.order[seq.pos(in.ord, (int)blockIdx.x, s + in.nstage)];
+            if (s + in.ngroups < my_tiles) raw_next = in.ord.order[seq.pos(in.ord, (int)blockIdx.x, s + in.ngroups)];
             const int64_t row = (int64_t)tile * R + tid_g;
             const unsigned char *sb = stages + (size_t)st * in.stage_bytes;
             const double *__restrict__ sval = reinterpret_cast<const double *>(sb);
-            const double *__restrict__ sxw = sval + in.cap;
+            const unsigned char *__restrict__ svi = sb;
+            const double *__restrict__ sxw = reinterpret_cast<const double *>(sb + in.val_region);
             const RP *__restrict__ srp = reinterpret_cast<const RP *>(sxw + in.xcap);
             const unsigned short *__restrict__ sli =
                 reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(srp) + (size_t)(R + 4) * 8);
@@ -606,11 +624,24 @@ spmv_win_kernel(SpmvWinIn in, Epi epi, RedArgs ra, typename std::conditional<DIS
             if (row < in.n_rows) pre = epi.load(row);   // in flight during the wait and the row walk
             tma::mbar_wait(&full[st], (uint32_t)((s / in.nstage) & 1));
             if (row < in.n_rows && !BIS_WIN_DEBUG(in, 1)) {
-                const int64_t base = (int64_t)srp[0] & ~(int64_t)7;
+                const int64_t base = (int64_t)srp[0] & ~(int64_t)in.amask;
                 const int ks = (int)((int64_t)srp[tid_g] - base);
                 const int ke = (int)((int64_t)srp[tid_g + 1] - base);
                 double sum = 0.0;
                 int k = ks;
+                if (in.vidx) {          // the same walk with the value looked up by its 1-byte index (warp-uniform)
+                    for (; k + 9 <= ke; k += 9) {
+                        double a[9], xv[9];
+#pragma unroll
+                        for (int u = 0; u < 9; ++u) {
+                            a[u] = s_dict[svi[k + u]];
+                            xv[u] = sxw[sli[k + u]];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 9; ++u) sum = add_rn(sum, mul_rn(a[u], xv[u]));
+                    }
+                    for (; k < ke; ++k) sum = add_rn(sum, mul_rn(s_dict[svi[k]], sxw[sli[k]]));
+                }
                 for (; k + 9 <= ke; k += 9) {
                     double a[9], xv[9];
 #pragma unroll
